@@ -1,0 +1,172 @@
+/*
+ * pcops.h -- C ABI of libpcops.so: the PointNet++ set-abstraction / feature-propagation geometry ops
+ * (and the per-neighbourhood attention contraction) as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in seam between a framework's op kernels and the device code.  In the reference
+ * (tpfeifle/pointcloud-segmentation-attention, paths below relative to pointnet2_tensorflow/tf_ops/) that seam is
+ * the set of C++ "launcher" prototypes each TensorFlow OpKernel::Compute calls; every entry point here names the
+ * launcher (file:line) it replaces and keeps that launcher's (b, n, m, ...) argument order, so a TF OpKernel, a
+ * ctypes stub or a torch wrapper forwards its arguments 1:1.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to dense row-major float32 / int32 arrays, 4-byte aligned; rows need not
+ *     be 16-byte aligned (vector paths are chosen at run time from the actual addresses);
+ *   - the caller owns every buffer, including workspaces (size from the matching *_workspace_bytes query);
+ *     the library allocates nothing and keeps no state besides per-device kernel attributes set lazily;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call returns immediately;
+ *   - outputs are fully overwritten (gradient outputs need no pre-zeroing by the caller);
+ *   - indices are trusted to lie in range exactly as in the reference kernels;
+ *   - return value: PC_OK (0); a negative PC_ERR_* for a rejected argument (nothing enqueued); or a positive
+ *     cudaError_t from the launch.  Calls with an empty problem (b*n*m == 0 ...) return PC_OK without launching.
+ *   - re-entrant and thread-safe; no host synchronisation inside any call (CUDA-graph capturable after one
+ *     warm-up call per device).
+ *
+ * Arithmetic contract: fp32, never fused (no FMA contraction), evaluated in the reference's written order, so that
+ * FPS / ball-query / kNN / three_nn / gather indices and grouped or gathered values are bit-exact against the
+ * reference algorithm; three_interpolate, all gradients and the attention contraction are deterministic (fixed
+ * summation order, no float atomics).
+ */
+#ifndef PCOPS_H_
+#define PCOPS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_OK 0
+#define PC_ERR_INVALID_ARGUMENT (-1) /* shape / attribute the reference op would reject with InvalidArgument */
+#define PC_ERR_UNSUPPORTED (-2)      /* valid, but outside what this build implements (documented per call)   */
+#define PC_ERR_WORKSPACE (-3)        /* workspace pointer is NULL although *_workspace_bytes() > 0             */
+
+typedef void *pc_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define PC_API __attribute__((visibility("default")))
+#else
+#define PC_API
+#endif
+
+PC_API int pc_version(void);                   /* 100*major + minor */
+PC_API const char *pc_error_string(int code);  /* PC_ERR_* names, or cudaGetErrorString for positive codes */
+PC_API int pc_num_sms(void);                   /* SM count of the current device (grid sizing / tests); <0 on error */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sampling library (reference: sampling/tf_sampling_g.cu, sampling/tf_sampling.cpp)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Farthest point sampling.  Replaces farthestpointsamplingLauncher(b,n,m,inp,temp,out)
+ * (tf_sampling_g.cu:203-205, prototype tf_sampling.cpp:94; op FarthestPointSample tf_sampling.cpp:28-40,95-123).
+ *   xyz (b,n,3) f32 -> out_idx (b,m) i32.  out_idx[:,0] = 0; ties resolve to the smallest (k mod 512, k) as the
+ *   reference's 512-thread partition + left-biased tree does (tf_sampling_g.cu:130,153-163).
+ * workspace: pc_fps_workspace_bytes(b,n,m) bytes (0 for n <= 8192: all state stays on chip); the reference needed
+ * a (32,n) f32 temp tensor (tf_sampling.cpp:115).  m <= 0 returns PC_OK at once (tf_sampling_g.cu:106-107). */
+PC_API size_t pc_fps_workspace_bytes(int b, int n, int m);
+PC_API int pc_fps(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, pc_stream_t stream);
+
+/* gather_point.  Replaces gatherpointLauncher(b,n,m,inp,idx,out) (tf_sampling_g.cu:206-208, prototype
+ * tf_sampling.cpp:125; op GatherPoint tf_sampling.cpp:41-54,126-148).
+ *   inp (b,n,3), idx (b,m) -> out (b,m,3);  out[b,j,:] = inp[b,idx[b,j],:] */
+PC_API int pc_gather_point(int b, int n, int m, const float *inp, const int *idx, float *out, pc_stream_t stream);
+
+/* gather_point gradient.  Replaces cudaMemset + scatteraddpointLauncher(b,n,m,out_g,idx,inp_g)
+ * (tf_sampling.cpp:174-175, tf_sampling_g.cu:209-211, prototype tf_sampling.cpp:150; op GatherPointGrad).
+ *   out_g (b,m,3), idx (b,m) -> inp_g (b,n,3), fully overwritten; contributions to one point are summed in
+ *   ascending j (deterministic; the reference's float atomicAdd order is undefined). */
+PC_API size_t pc_gather_point_grad_workspace_bytes(int b, int n, int m);
+PC_API int pc_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g, void *workspace,
+                         pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Grouping library (reference: grouping/tf_grouping_g.cu, grouping/tf_grouping.cpp, grouping/tf_grouping.py)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Ball query.  Replaces queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)
+ * (tf_grouping_g.cu:125-128, prototype tf_grouping.cpp:66; op QueryBallPoint tf_grouping.cpp:13-30,67-106).
+ *   xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32.
+ *   Per query: the first nsample dataset indices k (ascending) with max(sqrtf(d2),1e-20f) < radius; unfilled
+ *   slots repeat the first hit; pts_cnt = hits (saturating at nsample); rows of empty balls are zero (the
+ *   reference leaves them unwritten).  radius <= 0 or nsample <= 0 -> PC_ERR_INVALID_ARGUMENT
+ *   (tf_grouping.cpp:70-74). */
+PC_API int pc_query_ball(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                  int *pts_cnt, pc_stream_t stream);
+
+/* group_point.  Replaces groupPointLauncher(b,n,c,m,nsample,points,idx,out) (tf_grouping_g.cu:133-136, prototype
+ * tf_grouping.cpp:142; op GroupPoint tf_grouping.cpp:41-54,143-171).
+ *   points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c);  out[b,j,k,:] = points[b,idx[b,j,k],:] */
+PC_API int pc_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out,
+                   pc_stream_t stream);
+
+/* group_point gradient.  Replaces cudaMemset + groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points)
+ * (tf_grouping.cpp:204-205, tf_grouping_g.cu:137-141, prototype tf_grouping.cpp:173; op GroupPointGrad).
+ *   grad_out (b,m,nsample,c), idx (b,m,nsample) -> grad_points (b,n,c), fully overwritten, each row summed in
+ *   ascending (j,k) order = the serial order of grouping/test/query_ball_point.cpp:70-84. */
+PC_API size_t pc_group_point_grad_workspace_bytes(int b, int n, int c, int m, int nsample);
+PC_API int pc_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                        float *grad_points, void *workspace, pc_stream_t stream);
+
+/* SelectionSort.  Replaces selectionSortLauncher(b,n,m,k,dist,outi,out) (tf_grouping_g.cu:129-132, prototype
+ * tf_grouping.cpp:108; op SelectionSort tf_grouping.cpp:31-40,109-139).
+ *   dist (b,m,n) -> outi (b,m,n) i32, out (b,m,n) f32: the arrays the reference's k swap steps leave behind
+ *   (first k columns = k smallest, swap-induced tie order).  k <= 0 -> PC_ERR_INVALID_ARGUMENT. */
+PC_API int pc_selection_sort(int b, int n, int m, int k, const float *dist, int *outi, float *out, pc_stream_t stream);
+
+/* knn_point, fused.  Replaces the TF graph of grouping/tf_grouping.py:48-73 (tile, subtract, square, reduce_sum,
+ * SelectionSort, slice) without materialising the (b,m,n) matrix.
+ *   xyz1 (b,n,c) dataset, xyz2 (b,m,c) queries -> val (b,m,k) f32 squared distances, idx (b,m,k) i32, identical
+ *   to the first k columns of SelectionSort on that matrix, swap-induced tie order included.
+ *   Supported: 1 <= k <= 128, k <= n, 1 <= c <= 16; otherwise PC_ERR_UNSUPPORTED. */
+PC_API int pc_knn(int b, int n, int m, int k, int c, const float *xyz1, const float *xyz2, float *val, int *idx,
+           pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Interpolation library (reference: interpolation_3d/tf_interpolate.cpp -- CPU-only ops in the reference)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* three_nn.  Replaces threenn_cpu(b,n,m,xyz1,xyz2,dist,idx) (tf_interpolate.cpp:60-103; op ThreeNN :12-21,157-187).
+ *   xyz1 (b,n,3) unknown/dense, xyz2 (b,m,3) known/sparse -> dist (b,n,3) f32 SQUARED distances ascending,
+ *   idx (b,n,3) i32; equal distances keep ascending index order; missing neighbours (m < 3) are (+inf, 0). */
+PC_API int pc_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                pc_stream_t stream);
+
+/* Inverse-distance weights of pointnet_fp_module (utils/pointnet_util.py:219-222, stock TF ops in the reference):
+ *   d = max(dist,1e-10); w_t = (1/d_t) / ((1/d_0 + 1/d_1) + 1/d_2).   dist, weight: (rows,3). */
+PC_API int pc_three_weights(size_t rows, const float *dist, float *weight, pc_stream_t stream);
+
+/* three_interpolate.  Replaces threeinterpolate_cpu(b,m,c,n,points,idx,weight,out) (tf_interpolate.cpp:107-127;
+ * op ThreeInterpolate :22-36,191-222).
+ *   points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c);  out = (p1*w1 + p2*w2) + p3*w3, un-fused. */
+PC_API int pc_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight,
+                         float *out, pc_stream_t stream);
+
+/* three_interpolate gradient.  Replaces memset + threeinterpolate_grad_cpu(b,n,c,m,grad_out,idx,weight,grad_points)
+ * (tf_interpolate.cpp:258-259,131-153; op ThreeInterpolateGrad :37-46,225-262).
+ *   grad_out (b,n,c), idx (b,n,3), weight (b,n,3) -> grad_points (b,m,c), fully overwritten, each row summed in
+ *   the reference's serial (j,t) order. */
+PC_API size_t pc_three_interpolate_grad_workspace_bytes(int b, int n, int c, int m);
+PC_API int pc_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                              const float *weight, float *grad_points, void *workspace, pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Per-neighbourhood attention contraction (reference: attention_points/attention_scannet/attention_layer.py:35-42,
+ * i.e. AttentionLayer.call after its three Dense projections)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* G neighbourhoods of S samples, H heads of key_dim D (= output_dim), width HD = H*D:
+ *   Q (G,HD), K (G,S,HD), V (G,S,HD) -> out (G,HD)
+ * with the reference's RAW reshape of each neighbourhood's (S,HD) buffer to (H,S,D) (attention_layer.py:35):
+ *   logit[h,s] = sum_d Q[h*D+d] * Kflat[h*S*D + s*D + d] / sqrt(D);  a = softmax_s(logit)
+ *   out[h*D+d] = sum_s a[h,s] * Vflat[h*S*D + s*D + d]
+ * Supported: D in {1,2,4,8,16}, 1 <= S <= 128 (else PC_ERR_UNSUPPORTED).  fp32 throughout. */
+PC_API int pc_attention_fwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, float *out,
+                     pc_stream_t stream);
+
+/* Gradient of pc_attention_fwd w.r.t. Q, K, V given dout (G,HD); dQ (G,HD), dK and dV (G,S,HD) fully overwritten. */
+PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, const float *dout,
+                     float *dQ, float *dK, float *dV, pc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCOPS_H_ */

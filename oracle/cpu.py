@@ -1,0 +1,216 @@
+"""numpy wrappers over liboracle.so (oracle/pcops_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Function names and argument order follow the reference's Python op wrappers
+(tf_ops/sampling/tf_sampling.py, tf_ops/grouping/tf_grouping.py,
+tf_ops/interpolation_3d/tf_interpolate.py) so parity tests read like the reference's own.
+``omp=True`` selects the OpenMP-over-batch loops used only for cpu_baseline timing.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f = ctypes.POINTER(ctypes.c_float)
+_i = ctypes.POINTER(ctypes.c_int)
+
+
+def build():
+    """Compile liboracle.so (and oracle/_ref when /root/reference is mounted)."""
+    subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True, capture_output=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.orc_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def farthest_point_sample(npoint, inp, omp=False):
+    inp = _f32(inp)
+    b, n, _ = inp.shape
+    out = np.zeros((b, npoint), np.int32)
+    fn = lib().orc_fps_omp if omp else lib().orc_fps
+    fn(b, n, npoint, _fp(inp), _ip(out))
+    return out
+
+
+def gather_point(inp, idx):
+    inp, idx = _f32(inp), _i32(idx)
+    b, n, _ = inp.shape
+    m = idx.shape[1]
+    out = np.zeros((b, m, 3), np.float32)
+    lib().orc_gather_point(b, n, m, _fp(inp), _ip(idx), _fp(out))
+    return out
+
+
+def gather_point_grad(inp, idx, out_g):
+    inp, idx, out_g = _f32(inp), _i32(idx), _f32(out_g)
+    b, n, _ = inp.shape
+    m = idx.shape[1]
+    inp_g = np.zeros((b, n, 3), np.float32)
+    lib().orc_gather_point_grad(b, n, m, _fp(out_g), _ip(idx), _fp(inp_g))
+    return inp_g
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2, omp=False):
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = np.zeros((b, m, nsample), np.int32)
+    cnt = np.zeros((b, m), np.int32)
+    fn = lib().orc_query_ball_omp if omp else lib().orc_query_ball
+    fn(b, n, m, ctypes.c_float(radius), nsample, _fp(xyz1), _fp(xyz2), _ip(idx), _ip(cnt))
+    return idx, cnt
+
+
+def group_point(points, idx, omp=False):
+    points, idx = _f32(points), _i32(idx)
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    out = np.zeros((b, m, ns, c), np.float32)
+    fn = lib().orc_group_point_omp if omp else lib().orc_group_point
+    fn(b, n, c, m, ns, _fp(points), _ip(idx), _fp(out))
+    return out
+
+
+def group_point_grad(points, idx, grad_out, omp=False):
+    points, idx, grad_out = _f32(points), _i32(idx), _f32(grad_out)
+    b, n, c = points.shape
+    _, m, ns = idx.shape
+    gp = np.zeros((b, n, c), np.float32)
+    fn = lib().orc_group_point_grad_omp if omp else lib().orc_group_point_grad
+    fn(b, n, c, m, ns, _fp(grad_out), _ip(idx), _fp(gp))
+    return gp
+
+
+def select_top_k(k, dist):
+    dist = _f32(dist)
+    b, m, n = dist.shape
+    outi = np.zeros((b, m, n), np.int32)
+    out = np.zeros((b, m, n), np.float32)
+    lib().orc_selection_sort(b, n, m, k, _fp(dist), _ip(outi), _fp(out))
+    return outi, out
+
+
+def knn_dist(xyz1, xyz2):
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, c = xyz1.shape
+    m = xyz2.shape[1]
+    dist = np.zeros((b, m, n), np.float32)
+    lib().orc_knn_dist(b, n, m, c, _fp(xyz1), _fp(xyz2), _fp(dist))
+    return dist
+
+
+def knn_point(k, xyz1, xyz2):
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, c = xyz1.shape
+    m = xyz2.shape[1]
+    val = np.zeros((b, m, k), np.float32)
+    idx = np.zeros((b, m, k), np.int32)
+    lib().orc_knn(b, n, m, k, c, _fp(xyz1), _fp(xyz2), _fp(val), _ip(idx))
+    return val, idx
+
+
+def three_nn(xyz1, xyz2, omp=False):
+    xyz1, xyz2 = _f32(xyz1), _f32(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = np.zeros((b, n, 3), np.float32)
+    idx = np.zeros((b, n, 3), np.int32)
+    fn = lib().orc_three_nn_omp if omp else lib().orc_three_nn
+    fn(b, n, m, _fp(xyz1), _fp(xyz2), _fp(dist), _ip(idx))
+    return dist, idx
+
+
+def three_weights(dist):
+    dist = _f32(dist)
+    w = np.zeros_like(dist)
+    lib().orc_three_weights(ctypes.c_size_t(dist.size // 3), _fp(dist), _fp(w))
+    return w
+
+
+def three_interpolate(points, idx, weight, omp=False):
+    points, idx, weight = _f32(points), _i32(idx), _f32(weight)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    out = np.zeros((b, n, c), np.float32)
+    fn = lib().orc_three_interpolate_omp if omp else lib().orc_three_interpolate
+    fn(b, m, c, n, _fp(points), _ip(idx), _fp(weight), _fp(out))
+    return out
+
+
+def three_interpolate_grad(points, idx, weight, grad_out, omp=False):
+    points, idx, weight, grad_out = _f32(points), _i32(idx), _f32(weight), _f32(grad_out)
+    b, m, c = points.shape
+    n = idx.shape[1]
+    gp = np.zeros((b, m, c), np.float32)
+    fn = lib().orc_three_interpolate_grad_omp if omp else lib().orc_three_interpolate_grad
+    fn(b, n, c, m, _fp(grad_out), _ip(idx), _fp(weight), _fp(gp))
+    return gp
+
+
+def attention_fwd(Q, K, V, heads, key_dim, return_attn=False):
+    """Q (G,HD), K (G,S,HD), V (G,S,HD) -> out (G,HD) [, attn (G,H,S)]."""
+    Q, K, V = _f32(Q), _f32(K), _f32(V)
+    G, S, HD = K.shape
+    assert HD == heads * key_dim and Q.shape == (G, HD) and V.shape == K.shape
+    out = np.zeros((G, HD), np.float32)
+    attn = np.zeros((G, heads, S), np.float32) if return_attn else None
+    lib().orc_attention_fwd(G, S, heads, key_dim, _fp(Q), _fp(K), _fp(V), _fp(out),
+                            _fp(attn) if return_attn else None)
+    return (out, attn) if return_attn else out
+
+
+def attention_bwd(Q, K, V, dout, heads, key_dim):
+    Q, K, V, dout = _f32(Q), _f32(K), _f32(V), _f32(dout)
+    G, S, HD = K.shape
+    dQ, dK, dV = np.zeros_like(Q), np.zeros_like(K), np.zeros_like(V)
+    lib().orc_attention_bwd(G, S, heads, key_dim, _fp(Q), _fp(K), _fp(V), _fp(dout), _fp(dQ), _fp(dK), _fp(dV))
+    return dQ, dK, dV
+
+
+def dense(x, W, bias):
+    x, W = _f32(x), _f32(W)
+    cin, cout = W.shape
+    rows = x.size // cin
+    y = np.zeros(x.shape[:-1] + (cout,), np.float32)
+    bias = _f32(bias) if bias is not None else None
+    lib().orc_dense(ctypes.c_size_t(rows), cin, cout, _fp(x), _fp(W), _fp(bias) if bias is not None else None, _fp(y))
+    return y
+
+
+def attention_layer(x, xq, Wq, bq, Wk, bk, Wv, bv, heads, key_dim):
+    """AttentionLayer.call (attention_layer.py:29-45): x (G,S,Cin), xq (G,Cin) -> (G, heads*key_dim)."""
+    Q = dense(xq, Wq, bq)
+    K = dense(x, Wk, bk)
+    V = dense(x, Wv, bv)
+    return attention_fwd(Q, K, V, heads, key_dim)

@@ -1,0 +1,109 @@
+"""ctypes binding of libpcops.so (include/pcops.h) -- the only doorway from Python to the CUDA kernels.
+
+There is NO fallback: if the shared library is missing, or an op is handed a non-CUDA tensor, the call raises.
+torch is used for device memory and the current stream only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcops.so")
+_lib = None
+
+PC_OK = 0
+PC_ERR_INVALID_ARGUMENT = -1
+PC_ERR_UNSUPPORTED = -2
+PC_ERR_WORKSPACE = -3
+
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/pcops.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "pc_version": (_i, []),
+    "pc_error_string": (ctypes.c_char_p, [_i]),
+    "pc_num_sms": (_i, []),
+    "pc_fps_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pc_fps": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pc_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pc_gather_point_grad_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pc_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_query_ball": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_group_point": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pc_group_point_grad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "pc_group_point_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_selection_sort": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pc_knn": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_three_nn": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_three_weights": (_i, [_sz, _vp, _vp, _vp]),
+    "pc_three_interpolate": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_three_interpolate_grad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pc_three_interpolate_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+class PcopsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpcops.so once.  Raises if it has not been built (python __graft_entry__.py / build.sh)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PcopsError("libpcops.so not found at %s -- build it with `sh %s` (there is no CPU fallback)"
+                             % (LIB_PATH, os.path.join(_HERE, "build.sh")))
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what, invalid_message=None):
+    """Turn a pcops return code into the exception the reference op would raise."""
+    if rc == PC_OK:
+        return
+    if rc == PC_ERR_INVALID_ARGUMENT:
+        raise ValueError(invalid_message or ("%s: invalid argument" % what))
+    name = lib().pc_error_string(rc).decode()
+    if rc == PC_ERR_UNSUPPORTED:
+        raise NotImplementedError("%s: %s" % (what, name))
+    raise PcopsError("%s failed: %s (%d)" % (what, name, rc))
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def cuda_f32(t, what):
+    return _prep(t, torch.float32, what)
+
+
+def cuda_i32(t, what):
+    return _prep(t, torch.int32, what)
+
+
+def _prep(t, dtype, what):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % what)
+    if not t.is_cuda:
+        raise PcopsError("%s must be a CUDA tensor: these ops have no CPU implementation" % what)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (what, dtype, t.dtype))
+    return t.contiguous()
+
+
+def workspace(nbytes, device):
+    if nbytes == 0:
+        return None
+    return torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)

@@ -1,0 +1,255 @@
+// Per-neighbourhood attention contraction for sm_100a (fp32, HBM-streaming).
+//
+// Replaces the reshape / matmul / softmax / matmul tail of AttentionLayer.call (reference
+// attention_points/attention_scannet/attention_layer.py:35-42), which TensorFlow runs as two batched cuBLAS GEMMs
+// with M=1, K=key_dim=4 plus a softmax and three intermediate tensors.  Here one warp owns one (neighbourhood, head):
+// thanks to the reference's RAW reshape (:35) a head's S pseudo-keys are one contiguous run of S*D floats in the K and
+// V buffers, so lane s reads key s with a single 128-bit load (D=4), the softmax is two warp reductions and the
+// weighted value sum is D warp reductions.  K and V are read exactly once; nothing is written but the (G,HD) output.
+// Arithmetic intensity is 0.5 flop/byte -- this op is HBM-bound by construction, it is not tensor-core work.
+#include <math.h>
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int kAttWarps = 8;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(PC_FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PC_FULL_MASK, v, o);
+  return v;
+}
+
+template <int D, bool VEC>
+__device__ __forceinline__ void load_row(const float *__restrict__ p, float (&r)[D]) {
+  if (VEC && D % 4 == 0) {
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(p + d));
+      r[d] = t.x; r[d + 1] = t.y; r[d + 2] = t.z; r[d + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = __ldg(p + d);
+  }
+}
+
+template <int D, bool VEC>
+__device__ __forceinline__ void store_row(float *__restrict__ p, const float (&r)[D]) {
+  if (VEC && D % 4 == 0) {
+#pragma unroll
+    for (int d = 0; d < D; d += 4) *reinterpret_cast<float4 *>(p + d) = make_float4(r[d], r[d + 1], r[d + 2], r[d + 3]);
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d) p[d] = r[d];
+  }
+}
+
+// Softmax weights of one head for the lane's samples s = lane + 32*i (i < NS); returns them in a[].
+template <int D, int NS, bool VEC>
+__device__ __forceinline__ void head_softmax(int S, const float *__restrict__ kh, const float (&q)[D], float rsd,
+                                             float (&a)[NS]) {
+  const int lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int s = lane + 32 * i;
+    a[i] = -INFINITY;
+    if (s < S) {
+      float k[D];
+      load_row<D, VEC>(kh + (size_t)s * D, k);
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc = fmaf(q[d], k[d], acc);
+      a[i] = acc * rsd;
+    }
+    mx = fmaxf(mx, a[i]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    a[i] = (lane + 32 * i < S) ? expf(a[i] - mx) : 0.f;
+    sum += a[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) a[i] *= inv;
+}
+
+template <int D, int NS, bool VEC>
+__global__ void __launch_bounds__(kAttWarps * 32)
+attention_fwd_kernel(size_t heads_total, int S, int H, const float *__restrict__ Q, const float *__restrict__ K,
+                     const float *__restrict__ V, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const size_t gh = (size_t)blockIdx.x * kAttWarps + (threadIdx.x >> 5);  // g*H + h
+  if (gh >= heads_total) return;
+  const float rsd = 1.0f / sqrtf((float)D);
+  // (g,h) chunk: K + g*S*H*D + h*S*D == K + gh*S*D ;  Q + g*H*D + h*D == Q + gh*D
+  const float *kh = K + gh * (size_t)S * D;
+  const float *vh = V + gh * (size_t)S * D;
+  float q[D];
+  load_row<D, VEC>(Q + gh * D, q);
+  float a[NS];
+  head_softmax<D, NS, VEC>(S, kh, q, rsd, a);
+  float o[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int s = lane + 32 * i;
+    if (s < S) {
+      float v[D];
+      load_row<D, VEC>(vh + (size_t)s * D, v);
+#pragma unroll
+      for (int d = 0; d < D; ++d) o[d] = fmaf(a[i], v[d], o[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = warp_sum(o[d]);
+  if (lane == 0) store_row<D, VEC>(out + gh * D, o);
+}
+
+template <int D, int NS, bool VEC>
+__global__ void __launch_bounds__(kAttWarps * 32)
+attention_bwd_kernel(size_t heads_total, int S, int H, const float *__restrict__ Q, const float *__restrict__ K,
+                     const float *__restrict__ V, const float *__restrict__ dout, float *__restrict__ dQ,
+                     float *__restrict__ dK, float *__restrict__ dV) {
+  const int lane = threadIdx.x & 31;
+  const size_t gh = (size_t)blockIdx.x * kAttWarps + (threadIdx.x >> 5);
+  if (gh >= heads_total) return;
+  const float rsd = 1.0f / sqrtf((float)D);
+  const float *kh = K + gh * (size_t)S * D;
+  const float *vh = V + gh * (size_t)S * D;
+  float q[D], go[D];
+  load_row<D, VEC>(Q + gh * D, q);
+  load_row<D, VEC>(dout + gh * D, go);
+  float a[NS], da[NS];
+  head_softmax<D, NS, VEC>(S, kh, q, rsd, a);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int s = lane + 32 * i;
+    da[i] = 0.f;
+    if (s < S) {
+      float v[D];
+      load_row<D, VEC>(vh + (size_t)s * D, v);
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc = fmaf(go[d], v[d], acc);
+      da[i] = acc;
+      float gv[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) gv[d] = a[i] * go[d];
+      store_row<D, VEC>(dV + gh * (size_t)S * D + (size_t)s * D, gv);
+    }
+    dot = fmaf(a[i], da[i], dot);
+  }
+  dot = warp_sum(dot);
+  float gq[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) gq[d] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int s = lane + 32 * i;
+    if (s < S) {
+      const float dl = a[i] * (da[i] - dot) * rsd;
+      float k[D], gk[D];
+      load_row<D, VEC>(kh + (size_t)s * D, k);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        gq[d] = fmaf(dl, k[d], gq[d]);
+        gk[d] = dl * q[d];
+      }
+      store_row<D, VEC>(dK + gh * (size_t)S * D + (size_t)s * D, gk);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) gq[d] = warp_sum(gq[d]);
+  if (lane == 0) store_row<D, VEC>(dQ + gh * D, gq);
+}
+
+template <int D, int NS, bool VEC>
+int launch_fwd(size_t heads, int S, int H, const float *Q, const float *K, const float *V, float *out,
+               cudaStream_t st) {
+  const size_t blocks = (heads + kAttWarps - 1) / kAttWarps;
+  attention_fwd_kernel<D, NS, VEC><<<(unsigned)blocks, kAttWarps * 32, 0, st>>>(heads, S, H, Q, K, V, out);
+  PC_RETURN_LAUNCH_STATUS();
+}
+template <int D, int NS, bool VEC>
+int launch_bwd(size_t heads, int S, int H, const float *Q, const float *K, const float *V, const float *dout,
+               float *dQ, float *dK, float *dV, cudaStream_t st) {
+  const size_t blocks = (heads + kAttWarps - 1) / kAttWarps;
+  attention_bwd_kernel<D, NS, VEC><<<(unsigned)blocks, kAttWarps * 32, 0, st>>>(heads, S, H, Q, K, V, dout, dQ, dK, dV);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace
+}  // namespace pc
+
+namespace {
+int check_att(int G, int S, int H, int D) {
+  if (G < 0 || S <= 0 || H <= 0 || D <= 0) return PC_ERR_INVALID_ARGUMENT;
+  if (!(D == 1 || D == 2 || D == 4 || D == 8 || D == 16) || S > 128) return PC_ERR_UNSUPPORTED;
+  if ((size_t)G * H > 0x7fffffffu * (size_t)pc::kAttWarps) return PC_ERR_UNSUPPORTED;
+  return PC_OK;
+}
+}  // namespace
+
+extern "C" int pc_attention_fwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V,
+                                float *out, pc_stream_t stream) {
+  int rc = check_att(G, S, H, D);
+  if (rc) return rc;
+  if (G == 0) return PC_OK;
+  if (!Q || !K || !V || !out) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t heads = (size_t)G * H;
+  const bool vec = (D % 4 == 0) && pc::aligned16(Q) && pc::aligned16(K) && pc::aligned16(V) && pc::aligned16(out);
+#define PC_FWD(DD, VV)                                                                        \
+  do {                                                                                        \
+    if (S <= 32) return pc::launch_fwd<DD, 1, VV>(heads, S, H, Q, K, V, out, st);             \
+    if (S <= 64) return pc::launch_fwd<DD, 2, VV>(heads, S, H, Q, K, V, out, st);             \
+    return pc::launch_fwd<DD, 4, VV>(heads, S, H, Q, K, V, out, st);                          \
+  } while (0)
+  switch (D) {
+    case 1: PC_FWD(1, false);
+    case 2: PC_FWD(2, false);
+    case 4: if (vec) PC_FWD(4, true); else PC_FWD(4, false);
+    case 8: if (vec) PC_FWD(8, true); else PC_FWD(8, false);
+    default: if (vec) PC_FWD(16, true); else PC_FWD(16, false);
+  }
+#undef PC_FWD
+}
+
+extern "C" int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V,
+                                const float *dout, float *dQ, float *dK, float *dV, pc_stream_t stream) {
+  int rc = check_att(G, S, H, D);
+  if (rc) return rc;
+  if (G == 0) return PC_OK;
+  if (!Q || !K || !V || !dout || !dQ || !dK || !dV) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t heads = (size_t)G * H;
+  const bool vec = (D % 4 == 0) && pc::aligned16(Q) && pc::aligned16(K) && pc::aligned16(V) && pc::aligned16(dout) &&
+                   pc::aligned16(dQ) && pc::aligned16(dK) && pc::aligned16(dV);
+#define PC_BWD(DD, VV)                                                                                  \
+  do {                                                                                                  \
+    if (S <= 32) return pc::launch_bwd<DD, 1, VV>(heads, S, H, Q, K, V, dout, dQ, dK, dV, st);          \
+    if (S <= 64) return pc::launch_bwd<DD, 2, VV>(heads, S, H, Q, K, V, dout, dQ, dK, dV, st);          \
+    return pc::launch_bwd<DD, 4, VV>(heads, S, H, Q, K, V, dout, dQ, dK, dV, st);                       \
+  } while (0)
+  switch (D) {
+    case 1: PC_BWD(1, false);
+    case 2: PC_BWD(2, false);
+    case 4: if (vec) PC_BWD(4, true); else PC_BWD(4, false);
+    case 8: if (vec) PC_BWD(8, true); else PC_BWD(8, false);
+    default: if (vec) PC_BWD(16, true); else PC_BWD(16, false);
+  }
+#undef PC_BWD
+}

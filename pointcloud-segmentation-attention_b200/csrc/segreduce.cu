@@ -1,0 +1,356 @@
+// Deterministic backward passes: group_point_grad, gather_point_grad, three_interpolate_grad.
+//
+// The reference scatters with float atomicAdd (tf_ops/grouping/tf_grouping_g.cu:61-78, tf_ops/sampling/
+// tf_sampling_g.cu:183-192: order undefined, run-to-run different bits) or with a serial host loop
+// (tf_ops/interpolation_3d/tf_interpolate.cpp:131-153).  Here every op is a SEGMENTED REDUCTION:
+//   1. csr_build: per scene, a stable counting sort of the index tensor's flat positions by the point they refer to
+//      -> row_ptr (nkeys+1) and list (npos) with each point's contributors in ascending position;
+//   2. csr_reduce: one thread per (point, 4 channels) adds its contributors in that fixed order with 128-bit loads.
+// The sum order equals the reference's serial CPU loops (ascending (j,k) / (j,t)), so results are bit-identical to
+// them, and identical from run to run.  No atomics on floats anywhere; outputs are fully overwritten (no memset).
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int kCsrThreads = 1024;
+constexpr size_t kCsrSmemBudget = 200 * 1024;
+
+// One CTA per scene.  Positions are split into W contiguous parts; counters cnt[w][key] live in shared memory.
+__global__ void __launch_bounds__(kCsrThreads, 1)
+csr_build_kernel(int nkeys, int npos, int W, int part, const int *__restrict__ idx, int *__restrict__ ws) {
+  extern __shared__ int cnt[];  // W * nkeys
+  __shared__ int s_carry;
+  __shared__ int s_warp[32];
+  const int scene = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *keys = idx + (size_t)scene * npos;
+  int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
+  int *list = row_ptr + nkeys + 1;
+
+  for (int i = tid; i < W * nkeys; i += kCsrThreads) cnt[i] = 0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  // histogram per part (integer atomics: the final counts do not depend on order)
+  for (int p = tid; p < npos; p += kCsrThreads) atomicAdd(&cnt[(p / part) * nkeys + keys[p]], 1);
+  __syncthreads();
+  // cnt[w][key] <- row_ptr[key] + number of positions with this key in parts < w
+  for (int base = 0; base < nkeys; base += kCsrThreads) {
+    const int key = base + tid;
+    int total = 0;
+    if (key < nkeys)
+      for (int w = 0; w < W; ++w) {
+        int t = cnt[w * nkeys + key];
+        cnt[w * nkeys + key] = total;
+        total += t;
+      }
+    // block-wide exclusive scan of `total`
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(PC_FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane], iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(PC_FULL_MASK, iv, o);
+        if (lane >= o) iv += u;
+      }
+      s_warp[lane] = iv - v;  // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + s_warp[warp] + incl - total;
+    if (key < nkeys) {
+      row_ptr[key] = excl;
+      for (int w = 0; w < W; ++w) cnt[w * nkeys + key] += excl;
+    }
+    __syncthreads();
+    if (tid == kCsrThreads - 1) s_carry = excl + total;
+    __syncthreads();
+  }
+  if (tid == 0) row_ptr[nkeys] = npos;
+  // stable fill: warp w walks part w in order, 32 positions per step
+  if (warp < W) {
+    int *c = cnt + warp * nkeys;
+    const int lo = warp * part, hi = min(npos, lo + part);
+    const unsigned lt = lanemask_lt();
+    for (int p0 = lo; p0 < hi; p0 += 32) {
+      const int p = p0 + lane;
+      const bool valid = p < hi;
+      const unsigned act = __ballot_sync(PC_FULL_MASK, valid);
+      if (valid) {
+        const int key = keys[p];
+        const unsigned peers = __match_any_sync(act, key);
+        const int leader = __ffs(peers) - 1;
+        int slot = 0;
+        if (lane == leader) {
+          slot = c[key];
+          c[key] = slot + __popc(peers);
+        }
+        slot = __shfl_sync(peers, slot, leader);
+        list[slot + __popc(peers & lt)] = p;
+      }
+      __syncwarp();  // orders this step's counter stores before the next step's loads
+    }
+  }
+}
+
+// Fallback for key ranges too large for shared memory: counters in the row_ptr area itself, one warp walks all
+// positions in order.  Slow, correct, only reached for nkeys > ~50k.
+__global__ void __launch_bounds__(1024, 1)
+csr_build_big_kernel(int nkeys, int npos, const int *__restrict__ idx, int *__restrict__ ws) {
+  __shared__ int s_carry;
+  __shared__ int s_warp[32];
+  const int scene = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *keys = idx + (size_t)scene * npos;
+  int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
+  int *list = row_ptr + nkeys + 1;
+  for (int i = tid; i <= nkeys; i += 1024) row_ptr[i] = 0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int p = tid; p < npos; p += 1024) atomicAdd(&row_ptr[keys[p]], 1);
+  __syncthreads();
+  for (int base = 0; base < nkeys; base += 1024) {
+    const int key = base + tid;
+    const int total = key < nkeys ? row_ptr[key] : 0;
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(PC_FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane], iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(PC_FULL_MASK, iv, o);
+        if (lane >= o) iv += u;
+      }
+      s_warp[lane] = iv - v;
+    }
+    __syncthreads();
+    const int excl = s_carry + s_warp[warp] + incl - total;
+    if (key < nkeys) row_ptr[key] = excl;
+    __syncthreads();
+    if (tid == 1023) s_carry = excl + total;
+    __syncthreads();
+  }
+  // row_ptr now holds starts; fill advances them, then they are shifted back.
+  if (warp == 0) {
+    const unsigned lt = lanemask_lt();
+    for (int p0 = 0; p0 < npos; p0 += 32) {
+      const int p = p0 + lane;
+      const bool valid = p < npos;
+      const unsigned act = __ballot_sync(PC_FULL_MASK, valid);
+      if (valid) {
+        const int key = keys[p];
+        const unsigned peers = __match_any_sync(act, key);
+        const int leader = __ffs(peers) - 1;
+        int slot = 0;
+        if (lane == leader) {
+          slot = row_ptr[key];
+          row_ptr[key] = slot + __popc(peers);
+        }
+        slot = __shfl_sync(peers, slot, leader);
+        list[slot + __popc(peers & lt)] = p;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // row_ptr[key] now = end of key = start of key+1: shift right by one (back to front, chunked).
+  for (int top = nkeys; top > 0; top -= 1024) {
+    const int i = top - tid;  // handles indices (top-1023 .. top)
+    int v = 0;
+    if (i >= 1) v = row_ptr[i - 1];
+    __syncthreads();
+    if (i >= 1) row_ptr[i] = v;
+    __syncthreads();
+  }
+  if (tid == 0) row_ptr[0] = 0;
+}
+
+// out[scene, i, 4q..4q+3] = sum_{e in row i} src[scene, list[e]/div, 4q..] * (w ? w[scene, list[e]] : 1)
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+csr_reduce_vec4_kernel(int nkeys, int npos, int c4, int div, const float4 *__restrict__ src,
+                       const float *__restrict__ w, const int *__restrict__ ws, float4 *__restrict__ out) {
+  const int scene = blockIdx.y;
+  const int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
+  const int *list = row_ptr + nkeys + 1;
+  const float4 *s = src + (size_t)scene * (npos / div) * c4;
+  const float *ww = WEIGHTED ? w + (size_t)scene * npos : nullptr;
+  const size_t total = (size_t)nkeys * c4;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / c4), q = (int)(t - (size_t)i * c4);
+    const int lo = row_ptr[i], hi = row_ptr[i + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lo; e < hi; ++e) {
+      const int p = list[e];
+      float4 g = __ldg(s + (size_t)(p / div) * c4 + q);
+      if (WEIGHTED) {
+        const float wt = __ldg(ww + p);
+        g.x = __fmul_rn(g.x, wt); g.y = __fmul_rn(g.y, wt); g.z = __fmul_rn(g.z, wt); g.w = __fmul_rn(g.w, wt);
+      }
+      acc.x = __fadd_rn(acc.x, g.x); acc.y = __fadd_rn(acc.y, g.y);
+      acc.z = __fadd_rn(acc.z, g.z); acc.w = __fadd_rn(acc.w, g.w);
+    }
+    out[((size_t)scene * nkeys + i) * c4 + q] = acc;
+  }
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+csr_reduce_scalar_kernel(int nkeys, int npos, int c, int div, const float *__restrict__ src,
+                         const float *__restrict__ w, const int *__restrict__ ws, float *__restrict__ out) {
+  const int scene = blockIdx.y;
+  const int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
+  const int *list = row_ptr + nkeys + 1;
+  const float *s = src + (size_t)scene * (npos / div) * c;
+  const float *ww = WEIGHTED ? w + (size_t)scene * npos : nullptr;
+  const size_t total = (size_t)nkeys * c;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / c), l = (int)(t - (size_t)i * c);
+    const int lo = row_ptr[i], hi = row_ptr[i + 1];
+    float acc = 0.f;
+    for (int e = lo; e < hi; ++e) {
+      const int p = list[e];
+      float g = __ldg(s + (size_t)(p / div) * c + l);
+      if (WEIGHTED) g = __fmul_rn(g, __ldg(ww + p));
+      acc = __fadd_rn(acc, g);
+    }
+    out[((size_t)scene * nkeys + i) * c + l] = acc;
+  }
+}
+
+}  // namespace
+
+size_t csr_workspace_bytes(int b, int nkeys, int npos) {
+  if (b <= 0 || nkeys <= 0) return 0;
+  return (size_t)b * ((size_t)nkeys + 1 + (size_t)(npos > 0 ? npos : 0)) * sizeof(int);
+}
+
+int csr_build(int b, int nkeys, int npos, const int *idx, int *workspace, cudaStream_t st) {
+  if (b > 65535) return PC_ERR_UNSUPPORTED;
+  const size_t per_part = (size_t)nkeys * sizeof(int);
+  if (per_part <= kCsrSmemBudget) {
+    int W = (int)(kCsrSmemBudget / per_part);
+    if (W > 32) W = 32;
+    // no more parts than 32-position steps
+    const int steps = (npos + 31) / 32;
+    if (W > steps) W = steps > 0 ? steps : 1;
+    int part = ((npos + W - 1) / W + 31) / 32 * 32;
+    if (part < 32) part = 32;
+    W = (npos + part - 1) / part;
+    if (W < 1) W = 1;
+    const size_t smem = (size_t)W * per_part;
+    if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(csr_build_kernel, smem));
+    csr_build_kernel<<<b, kCsrThreads, smem, st>>>(nkeys, npos, W, part, idx, workspace);
+  } else {
+    csr_build_big_kernel<<<b, 1024, 0, st>>>(nkeys, npos, idx, workspace);
+  }
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+int csr_reduce(int b, int nkeys, int npos, int c, int div, const float *src, const float *w, const int *workspace,
+               float *out, cudaStream_t st) {
+  const int sms = num_sms();
+  if (c % 4 == 0 && aligned16(src) && aligned16(out)) {
+    const size_t total = (size_t)nkeys * (c / 4);
+    unsigned gx = (unsigned)((total + 255) / 256);
+    if (gx > (unsigned)sms * 32) gx = (unsigned)sms * 32;
+    dim3 grid(gx, b);
+    if (w) csr_reduce_vec4_kernel<true><<<grid, 256, 0, st>>>(nkeys, npos, c / 4, div, (const float4 *)src, w, workspace, (float4 *)out);
+    else   csr_reduce_vec4_kernel<false><<<grid, 256, 0, st>>>(nkeys, npos, c / 4, div, (const float4 *)src, w, workspace, (float4 *)out);
+  } else {
+    const size_t total = (size_t)nkeys * c;
+    unsigned gx = (unsigned)((total + 255) / 256);
+    if (gx > (unsigned)sms * 32) gx = (unsigned)sms * 32;
+    dim3 grid(gx, b);
+    if (w) csr_reduce_scalar_kernel<true><<<grid, 256, 0, st>>>(nkeys, npos, c, div, src, w, workspace, out);
+    else   csr_reduce_scalar_kernel<false><<<grid, 256, 0, st>>>(nkeys, npos, c, div, src, w, workspace, out);
+  }
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace pc
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" size_t pc_group_point_grad_workspace_bytes(int b, int n, int c, int m, int nsample) {
+  (void)c;
+  if (m <= 0 || nsample <= 0) return 0;
+  return pc::csr_workspace_bytes(b, n, m * nsample);
+}
+
+extern "C" int pc_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx,
+                                   float *grad_points, void *workspace, pc_stream_t stream) {
+  if (b < 0 || n < 0 || c < 0 || m < 0 || nsample < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0 || c == 0) return PC_OK;
+  if (!grad_points) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0 || nsample == 0) {  // nothing scatters: the op still zero-fills (tf_grouping.cpp:204)
+    PC_CUDA_TRY(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, st));
+    return PC_OK;
+  }
+  if (!grad_out || !idx) return PC_ERR_INVALID_ARGUMENT;
+  if (!workspace) return PC_ERR_WORKSPACE;
+  if ((long long)m * nsample > 0x7fffffffLL) return PC_ERR_UNSUPPORTED;
+  int rc = pc::csr_build(b, n, m * nsample, idx, (int *)workspace, st);
+  if (rc) return rc;
+  return pc::csr_reduce(b, n, m * nsample, c, 1, grad_out, nullptr, (const int *)workspace, grad_points, st);
+}
+
+extern "C" size_t pc_gather_point_grad_workspace_bytes(int b, int n, int m) {
+  if (m <= 0) return 0;
+  return pc::csr_workspace_bytes(b, n, m);
+}
+
+extern "C" int pc_gather_point_grad(int b, int n, int m, const float *out_g, const int *idx, float *inp_g,
+                                    void *workspace, pc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0) return PC_OK;
+  if (!inp_g) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) {
+    PC_CUDA_TRY(cudaMemsetAsync(inp_g, 0, sizeof(float) * (size_t)b * n * 3, st));  // tf_sampling.cpp:174
+    return PC_OK;
+  }
+  if (!out_g || !idx) return PC_ERR_INVALID_ARGUMENT;
+  if (!workspace) return PC_ERR_WORKSPACE;
+  int rc = pc::csr_build(b, n, m, idx, (int *)workspace, st);
+  if (rc) return rc;
+  return pc::csr_reduce(b, n, m, 3, 1, out_g, nullptr, (const int *)workspace, inp_g, st);
+}
+
+extern "C" size_t pc_three_interpolate_grad_workspace_bytes(int b, int n, int c, int m) {
+  (void)c;
+  if (n <= 0) return 0;
+  return pc::csr_workspace_bytes(b, m, n * 3);
+}
+
+extern "C" int pc_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx,
+                                         const float *weight, float *grad_points, void *workspace,
+                                         pc_stream_t stream) {
+  if (b < 0 || n < 0 || c < 0 || m < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || m == 0 || c == 0) return PC_OK;
+  if (!grad_points) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    PC_CUDA_TRY(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, st));  // tf_interpolate.cpp:258
+    return PC_OK;
+  }
+  if (!grad_out || !idx || !weight) return PC_ERR_INVALID_ARGUMENT;
+  if (!workspace) return PC_ERR_WORKSPACE;
+  if ((long long)n * 3 > 0x7fffffffLL) return PC_ERR_UNSUPPORTED;
+  int rc = pc::csr_build(b, m, n * 3, idx, (int *)workspace, st);
+  if (rc) return rc;
+  return pc::csr_reduce(b, m, n * 3, c, 3, grad_out, weight, (const int *)workspace, grad_points, st);
+}

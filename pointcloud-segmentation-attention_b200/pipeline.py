@@ -1,0 +1,159 @@
+"""The whole geometry hot path of one PointNet++ ScanNet forward, with every buffer pre-allocated.
+
+``ScanNetGeometry`` runs, for a batch of B chunks of N points (xyz + 6 feature channels), every call the reference's
+4 set-abstraction + 4 feature-propagation levels make into the custom-op libraries plus the
+attention contraction (a13) of the four attention SA levels:
+
+  SA level l (pointnet_util.py:34-52, attention_layer.py:225,255-261; hyper-parameters of
+  attention_points/models/pointnet2_sem_seg_attention.py:28-43):
+      FPS -> gather_point -> query_ball_point -> group_point(xyz) -> group_point(features) -> attention contraction
+  FP level (pointnet_util.py:218-223):
+      three_nn -> inverse-distance weights -> three_interpolate
+
+The shared MLPs / Dense projections between those calls are stock dense layers and out of scope, so the tensors they
+would produce (per-level point features, and Q/K/V of each attention level) are fixed synthetic stand-ins of the
+right shape, resident in HBM.  Because of that, an FP level's ops are issued as soon as the xyz they depend on exists.
+
+Two streams: the four FPS calls form a strictly sequential chain (level l+1 samples level l's centroids) on the
+main stream; everything else runs on a side stream behind per-level events, so grouping / interpolation / attention of
+level l overlap FPS of level l+1.  The sequence is CUDA-graph capturable (no allocation, no host sync inside).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+# (npoint, radius, nsample, mlp[-1]) per SA level -- pointnet2_sem_seg_attention.py:28-43
+SA_LEVELS = ((1024, 0.1, 32, 64), (256, 0.2, 32, 128), (64, 0.4, 32, 256), (16, 0.8, 32, 512))
+KEY_DIM = 4  # attention_layer.py:256-258: heads = C // 4, key_dim = output_dim = 4
+
+
+class ScanNetGeometry:
+    def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0):
+        self.B, self.N, self.CF = batch, npoints, feat_channels
+        self.dev = torch.device(device)
+        self.attention = attention
+        self.L = _lib.lib()
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        f32, i32 = torch.float32, torch.int32
+        dev = self.dev
+
+        def rnd(*shape):
+            return torch.randn(*shape, generator=g, dtype=f32).to(dev)
+
+        self.xyz0 = torch.zeros((batch, npoints, 3), dtype=f32, device=dev)
+        self.feat0 = torch.zeros((batch, npoints, feat_channels), dtype=f32, device=dev)
+        self.levels = []
+        n, cin = npoints, feat_channels
+        xyz = self.xyz0
+        for (m, r, ns, cout) in SA_LEVELS:
+            lv = dict(n=n, m=m, r=r, ns=ns, cin=cin, cout=cout, xyz=xyz)
+            lv["feat"] = self.feat0 if n == npoints else rnd(batch, n, cin)  # stand-in for the previous level's MLP output
+            lv["fps_idx"] = torch.empty((batch, m), dtype=i32, device=dev)
+            lv["new_xyz"] = torch.empty((batch, m, 3), dtype=f32, device=dev)
+            lv["idx"] = torch.empty((batch, m, ns), dtype=i32, device=dev)
+            lv["cnt"] = torch.empty((batch, m), dtype=i32, device=dev)
+            lv["gxyz"] = torch.empty((batch, m, ns, 3), dtype=f32, device=dev)
+            lv["gfeat"] = torch.empty((batch, m, ns, cin), dtype=f32, device=dev)
+            if attention:  # stand-ins for the Dense projections of the level's (B,m,ns,cout) activations
+                lv["Q"] = rnd(batch * m, cout)
+                lv["K"] = rnd(batch * m, ns, cout)
+                lv["V"] = rnd(batch * m, ns, cout)
+                lv["att"] = torch.empty((batch * m, cout), dtype=f32, device=dev)
+            ws = self.L.pc_fps_workspace_bytes(batch, n, m)
+            lv["fps_ws"] = _lib.workspace(ws, dev)
+            self.levels.append(lv)
+            xyz, n, cin = lv["new_xyz"], m, cout
+        # FP levels: dense xyz = level input, sparse xyz = level output; channels of the sparse features
+        # (pointnet2_sem_seg_attention.py:46-53): FP1 c=512, FP2 c=256, FP3 c=256, FP4 c=128
+        self.fps = []
+        for li, c in ((3, 512), (2, 256), (1, 256), (0, 128)):
+            lv = self.levels[li]
+            fp = dict(n=lv["n"], m=lv["m"], c=c, xyz1=lv["xyz"], xyz2=lv["new_xyz"], level=li)
+            fp["points2"] = rnd(batch, lv["m"], c)  # stand-in for the deeper level's features
+            fp["dist"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
+            fp["idx"] = torch.empty((batch, lv["n"], 3), dtype=i32, device=dev)
+            fp["w"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
+            fp["out"] = torch.empty((batch, lv["n"], c), dtype=f32, device=dev)
+            self.fps.append(fp)
+        self.side = torch.cuda.Stream(device=dev)
+        self.launches_per_step = len(self.levels) * (6 if attention else 5) + len(self.fps) * 3
+        self._graph = None
+
+    # ---- inputs / outputs ----------------------------------------------------------------------------------
+    def set_inputs(self, xyz, feats, non_blocking=True):
+        self.xyz0.copy_(xyz, non_blocking=non_blocking)
+        self.feat0.copy_(feats, non_blocking=non_blocking)
+
+    def input_bytes(self):
+        return self.xyz0.numel() * 4 + self.feat0.numel() * 4
+
+    def result_tensors(self):
+        """The integer geometry decisions of a forward (what a host-side consumer can check): FPS indices, ball
+        indices and counts per SA level, three_nn indices per FP level."""
+        out = []
+        for lv in self.levels:
+            out += [lv["fps_idx"], lv["idx"], lv["cnt"]]
+        for fp in self.fps:
+            out.append(fp["idx"])
+        return out
+
+    # ---- one forward -----------------------------------------------------------------------------------------
+    def _sa_rest(self, lv, st):
+        L, B, p = self.L, self.B, _lib.ptr
+        n, m, ns, cin = lv["n"], lv["m"], lv["ns"], lv["cin"]
+        _c(L.pc_query_ball(B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), st))
+        _c(L.pc_group_point(B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
+        _c(L.pc_group_point(B, n, cin, m, ns, p(lv["feat"]), p(lv["idx"]), p(lv["gfeat"]), st))
+        if self.attention:
+            _c(L.pc_attention_fwd(B * m, ns, lv["cout"] // KEY_DIM, KEY_DIM, p(lv["Q"]), p(lv["K"]), p(lv["V"]),
+                                  p(lv["att"]), st))
+
+    def _fp(self, fp, st):
+        L, B, p = self.L, self.B, _lib.ptr
+        n, m, c = fp["n"], fp["m"], fp["c"]
+        _c(L.pc_three_nn(B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
+        _c(L.pc_three_weights(B * n, p(fp["dist"]), p(fp["w"]), st))
+        _c(L.pc_three_interpolate(B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
+
+    def forward(self, overlap=True):
+        """Enqueue one forward on the current stream (plus the side stream when overlap=True)."""
+        L, B, p = self.L, self.B, _lib.ptr
+        main = torch.cuda.current_stream(self.dev)
+        side = self.side if overlap else main
+        s_main = ctypes.c_void_p(main.cuda_stream)
+        s_side = ctypes.c_void_p(side.cuda_stream)
+        fp_of = {fp["level"]: fp for fp in self.fps}
+        if overlap:
+            side.wait_stream(main)
+        for li, lv in enumerate(self.levels):
+            _c(L.pc_fps(B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), s_main))
+            _c(L.pc_gather_point(B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+            self._sa_rest(lv, s_side)
+            self._fp(fp_of[li], s_side)
+        if overlap:
+            main.wait_stream(side)
+
+    # ---- CUDA graph ------------------------------------------------------------------------------------------
+    def capture(self, overlap=True):
+        """Capture forward() into a CUDA graph (after one eager warm-up); replay with .replay()."""
+        self.forward(overlap)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward(overlap)
+        self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()
+
+
+def _c(rc):
+    if rc != 0:
+        _lib.check(rc, "pcops pipeline call")

@@ -1,0 +1,47 @@
+"""Scene sharding across the GPUs of one box.
+
+Every op on the path is independent per batch element (reference kernels start from ``batch_index = blockIdx.x``,
+tf_grouping_g.cu:4,41,62,84; tf_sampling_g.cu:113,173,184) and every 8192-point chunk of a scene is independent
+(complete_scene_loader.py:57-109), so the multi-GPU story is a static partition of the scene / chunk list with NO
+data-path collective: one process per GPU, each runs the same kernels on its slice and writes disjoint outputs.
+torch.distributed is used only to agree on timings (max over ranks) and totals (sum over ranks).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_units, rank, world):
+    """Contiguous balanced split of ``n_units`` into ``world`` parts; returns [lo, hi) of ``rank``.
+    The first ``n_units % world`` ranks get one extra unit."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank/world: %r/%r" % (rank, world))
+    base, extra = divmod(int(n_units), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_units, world):
+    return [shard_bounds(n_units, r, world)[1] - shard_bounds(n_units, r, world)[0] for r in range(world)]
+
+
+def _reduce(value, op, device=None):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=op)
+    return float(t.item())
+
+
+def max_over_ranks(value, device=None):
+    return _reduce(value, dist.ReduceOp.MAX, device)
+
+
+def sum_over_ranks(value, device=None):
+    return _reduce(value, dist.ReduceOp.SUM, device)
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

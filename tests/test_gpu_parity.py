@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (through the C ABI / the reference-named wrappers) against the CPU oracle, the committed
+golden fixtures (reference outputs) and -- when oracle/_ref/libref_gpu_nofma.so travelled to the box -- the
+reference's own CUDA kernels.  Bit-exact for every index / gathered value / gradient / interpolation; 1e-5 relative
+for the attention contraction (tolerance from BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import pcops_b200 as ops
+from oracle import cpu, ref, synth
+from tests.test_oracle_pins import radius_probe
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def same(t, a):
+    return np.array_equal(npy(t), a)
+
+
+@pytest.fixture(scope="module")
+def refgpu():
+    if not ref.available_gpu(True):
+        pytest.skip("oracle/_ref/libref_gpu_nofma.so not present")
+    return ref.Gpu(nofma=True)
+
+
+# ------------------------------------------------------------------------------------------------------ FPS (a1)
+@pytest.mark.parametrize("n,m", [(64, 16), (256, 64), (511, 40), (512, 40), (513, 40), (1024, 256), (3072, 100),
+                                 (3073, 100), (8192, 1024), (5000, 200), (1, 1), (2, 2), (33, 7)])
+def test_fps_matches_oracle(n, m):
+    xyz, _ = synth.scannet_batch(n + m, 3, n)
+    assert same(ops.farthest_point_sample(m, cu(xyz)), cpu.farthest_point_sample(m, xyz))
+
+
+def test_fps_ties_duplicates_and_big_batches():
+    rs = np.random.RandomState(11)
+    xyz = (rs.randint(0, 5, size=(40, 700, 3)) / 4.0).astype(np.float32)   # b > 32 (reference grid-strides at 32)
+    assert same(ops.farthest_point_sample(60, cu(xyz)), cpu.farthest_point_sample(60, xyz))
+    ones = np.ones((2, 100, 3), np.float32)
+    assert same(ops.farthest_point_sample(9, cu(ones)), np.zeros((2, 9), np.int32))
+    small = synth.uniform_cube(3, 2, 10, 3)
+    assert same(ops.farthest_point_sample(16, cu(small)), cpu.farthest_point_sample(16, small))   # m > n
+
+
+def test_fps_streaming_path_above_8192_points():
+    xyz, _ = synth.scannet_batch(77, 2, 20000)
+    assert same(ops.farthest_point_sample(96, cu(xyz)), cpu.farthest_point_sample(96, xyz))
+
+
+def test_fps_matches_reference_cuda_kernel(refgpu):
+    xyz, _ = synth.scannet_batch(5, 4, 8192)
+    x = cu(xyz)
+    assert torch.equal(ops.farthest_point_sample(1024, x), refgpu.farthest_point_sample(1024, x))
+    x = cu(synth.uniform_cube(100, 33, 512, 3))
+    assert torch.equal(ops.farthest_point_sample(128, x), refgpu.farthest_point_sample(128, x))
+
+
+# --------------------------------------------------------------------------------------------- gather_point (a2,a3)
+def test_gather_point_and_grad():
+    xyz, _ = synth.scannet_batch(1, 3, 1000)
+    idx = cpu.farthest_point_sample(77, xyz)
+    idx[:, 5] = idx[:, 3]                                           # repeated index -> two contributions
+    out = ops.gather_point(cu(xyz), cu(idx))
+    assert same(out, cpu.gather_point(xyz, idx))
+    og = synth.features(4, 3, 77, 3)
+    assert same(ops.gather_point_grad(cu(xyz), cu(idx), cu(og)), cpu.gather_point_grad(xyz, idx, og))
+    x = cu(xyz).requires_grad_(True)
+    ops.gather_point(x, cu(idx)).backward(cu(og))
+    assert same(x.grad, cpu.gather_point_grad(xyz, idx, og))
+
+
+def test_gather_point_matches_reference_cuda_kernel(refgpu):
+    xyz, _ = synth.scannet_batch(2, 5, 2048)
+    idx = cu(cpu.farthest_point_sample(300, xyz))
+    assert torch.equal(ops.gather_point(cu(xyz), idx), refgpu.gather_point(cu(xyz), idx))
+
+
+# ------------------------------------------------------------------------------------------------ ball query (a4)
+def test_ball_query_golden(golden):
+    g = golden("grouping")
+    for r, ns in ((0.1, 64), (0.2, 8), (0.4, 32)):
+        idx, cnt = ops.query_ball_point(r, ns, cu(g["xyz1"]), cu(g["xyz2"]))
+        assert same(idx, g["idx_r%g_ns%d" % (r, ns)])
+        oi, oc = cpu.query_ball_point(r, ns, g["xyz1"], g["xyz2"])
+        assert same(cnt, oc)
+
+
+@pytest.mark.parametrize("n,m,r,ns", [(8192, 1024, 0.1, 32), (1024, 256, 0.2, 32), (256, 64, 0.4, 32),
+                                      (64, 16, 0.8, 32), (2500, 333, 0.3, 5), (100, 7, 10.0, 64), (3000, 50, 1e-4, 8)])
+def test_ball_query_matches_oracle(n, m, r, ns):
+    xyz, _ = synth.scannet_batch(n, 2, n)
+    new_xyz = cpu.gather_point(xyz, cpu.farthest_point_sample(m, xyz))
+    idx, cnt = ops.query_ball_point(r, ns, cu(xyz), cu(new_xyz))
+    oi, oc = cpu.query_ball_point(r, ns, xyz, new_xyz)
+    assert same(idx, oi) and same(cnt, oc)
+
+
+def test_ball_query_radius_boundary_and_empty_balls():
+    for r in (0.1, 0.2, 0.4, 0.8, 0.3, 1.7):
+        cand, expect, _ = radius_probe(r)
+        idx, cnt = ops.query_ball_point(r, cand.shape[1], cu(cand), cu(np.zeros((1, 1, 3), np.float32)))
+        assert int(cnt[0, 0]) == expect.sum()
+        assert np.array_equal(npy(idx)[0, 0, :expect.sum()], np.flatnonzero(expect))
+    xyz = synth.uniform_cube(1, 2, 50, 3)
+    far = np.full((2, 3, 3), 50.0, np.float32)
+    idx, cnt = ops.query_ball_point(0.5, 6, cu(xyz), cu(far))
+    assert int(cnt.sum()) == 0 and int(idx.abs().sum()) == 0
+
+
+def test_ball_query_matches_reference_cuda_kernel(refgpu):
+    xyz, _ = synth.scannet_batch(9, 4, 8192)
+    new_xyz = cu(cpu.gather_point(xyz, cpu.farthest_point_sample(1024, xyz)))
+    idx, cnt = ops.query_ball_point(0.1, 32, cu(xyz), new_xyz)
+    ridx, rcnt = refgpu.query_ball_point(0.1, 32, cu(xyz), new_xyz)   # rows pre-zeroed by the wrapper
+    assert torch.equal(idx, ridx) and torch.equal(cnt, rcnt)
+
+
+# ---------------------------------------------------------------------------------------- group_point (a5, a6)
+@pytest.mark.parametrize("c", [1, 3, 6, 9, 64, 128, 256, 512])
+def test_group_point_and_grad_match_oracle(c):
+    n, m, ns = 600, 130, 32
+    xyz = synth.uniform_cube(c, 2, n, 3)
+    idx, _ = cpu.query_ball_point(0.25, ns, xyz, xyz[:, :m])
+    pts = synth.features(c, 2, n, c)
+    assert same(ops.group_point(cu(pts), cu(idx)), cpu.group_point(pts, idx))
+    go = synth.features(c + 1, 2, m, ns, c)
+    want = cpu.group_point_grad(pts, idx, go)
+    assert same(ops.group_point_grad(cu(pts), cu(idx), cu(go)), want)
+    p = cu(pts).requires_grad_(True)
+    ops.group_point(p, cu(idx)).backward(cu(go))
+    assert same(p.grad, want)
+
+
+def test_group_point_unaligned_buffers_and_golden(golden):
+    g = golden("grouping")
+    idx = g["idx_r0.2_ns8"]
+    assert same(ops.group_point(cu(g["pts"]), cu(idx)), g["group"])
+    assert same(ops.group_point_grad(cu(g["pts"]), cu(idx), cu(g["grad_out"])), g["group_grad"])
+    # c % 4 == 0 but the base pointer is only 4-byte aligned: the library must pick the scalar path itself
+    b, n, c = g["pts"].shape
+    raw = torch.zeros(b * n * c + 1, device=DEV)
+    raw[1:] = cu(g["pts"]).reshape(-1)
+    pts_off = raw[1:].view(b, n, c)
+    assert pts_off.data_ptr() % 16 != 0
+    assert same(ops.group_point(pts_off, cu(idx)), g["group"])
+
+
+def test_group_point_matches_reference_cuda_kernels(refgpu):
+    n, m, ns, c = 1024, 256, 32, 64
+    xyz, _ = synth.scannet_batch(3, 4, n)
+    idx, _ = cpu.query_ball_point(0.2, ns, xyz, xyz[:, :m])
+    pts, go = cu(synth.features(1, 4, n, c)), cu(synth.features(2, 4, m, ns, c))
+    assert torch.equal(ops.group_point(pts, cu(idx)), refgpu.group_point(pts, cu(idx)))
+    mine = ops.group_point_grad(pts, cu(idx), go)
+    theirs = refgpu.group_point_grad(pts, cu(idx), go)              # float atomics: same sum, undefined order
+    torch.testing.assert_close(mine, theirs, rtol=1e-5, atol=1e-5)
+    assert torch.equal(mine, ops.group_point_grad(pts, cu(idx), go))   # ours is bit-reproducible
+
+
+def test_group_point_grad_popular_point_and_big_key_range():
+    # every slot points at one row (longest possible segment) and a key range beyond the shared-memory counters
+    b, n, m, ns, c = 2, 70000, 40, 16, 8
+    idx = np.zeros((b, m, ns), np.int32)
+    idx[1] = np.random.RandomState(0).randint(0, n, size=(m, ns))
+    go = synth.features(3, b, m, ns, c)
+    pts = np.zeros((b, n, c), np.float32)
+    assert same(ops.group_point_grad(cu(pts), cu(idx), cu(go)), cpu.group_point_grad(pts, idx, go))
+
+
+# ------------------------------------------------------------------------------------ selection sort / kNN (a7)
+def test_selection_sort_golden_and_ties(golden):
+    g = golden("selsort")
+    for tag, k in (("0", 3), ("1", 9), ("2", 4)):
+        outi, out = ops.select_top_k(k, cu(g["d" + tag]))
+        assert same(outi, g["i" + tag]) and same(out, g["v" + tag])
+    rs = np.random.RandomState(2)
+    d = rs.randint(0, 9, size=(4, 33, 300)).astype(np.float32)
+    outi, out = ops.select_top_k(64, cu(d))
+    oi, oo = cpu.select_top_k(64, d)
+    assert same(outi, oi) and same(out, oo)
+    outi, out = ops.select_top_k(500, cu(d))                        # k > n behaves like k = n
+    oi, oo = cpu.select_top_k(500, d)
+    assert same(outi, oi) and same(out, oo)
+
+
+def test_selection_sort_matches_reference_cuda_kernel(refgpu):
+    d = cu(np.random.RandomState(4).randint(0, 50, size=(3, 70, 512)).astype(np.float32))
+    a, b = ops.select_top_k(64, d)
+    ra, rb = refgpu.select_top_k(64, d)
+    assert torch.equal(a, ra) and torch.equal(b, rb)
+
+
+@pytest.mark.parametrize("n,m,k,c,quant", [(512, 128, 64, 3, False), (512, 40, 32, 3, True), (300, 33, 7, 5, True),
+                                           (2100, 20, 100, 3, False), (64, 16, 64, 3, True), (40, 9, 1, 2, True),
+                                           (8192, 64, 32, 3, False)])
+def test_knn_matches_oracle(n, m, k, c, quant):
+    rs = np.random.RandomState(n + k)
+    if quant:   # quantised coordinates -> many exactly equal distances -> the swap-induced tie order matters
+        xyz1 = (rs.randint(0, 6, size=(2, n, c)) / 4.0).astype(np.float32)
+    else:
+        xyz1 = rs.random_sample((2, n, c)).astype(np.float32)
+    xyz2 = xyz1[:, rs.permutation(n)[:m]].copy()
+    val, idx = ops.knn_point(k, cu(xyz1), cu(xyz2))
+    oval, oidx = cpu.knn_point(k, xyz1, xyz2)
+    assert same(idx, oidx) and same(val, oval)
+
+
+# --------------------------------------------------------------------------------- three_nn / interpolate (a8-a11)
+def test_interpolation_golden(golden):
+    g = golden("interpolate")
+    dist, idx = ops.three_nn(cu(g["xyz1"]), cu(g["xyz2"]))
+    assert same(idx, g["idx"]) and same(dist, g["dist"])
+    w = ops.three_weights(dist)
+    assert same(w, g["weight"])
+    assert same(ops.three_interpolate(cu(g["pts"]), idx, w), g["out"])
+    assert same(ops.three_interpolate_grad(cu(g["pts"]), idx, w, cu(g["grad_out"])), g["grad_points"])
+    d2, i2 = ops.three_nn(cu(g["xyz1"][:, :16]), cu(g["xyz2"][:, :2]))
+    assert same(i2, g["idx_m2"]) and same(d2, g["dist_m2"])
+
+
+@pytest.mark.parametrize("n,m,c", [(64, 16, 512), (256, 64, 256), (1024, 256, 256), (8192, 1024, 128), (1000, 37, 6),
+                                   (50, 3, 9), (2048, 1500, 1)])
+def test_three_nn_and_interpolate_match_oracle(n, m, c):
+    xyz, _ = synth.scannet_batch(n, 2, n)
+    known = cpu.gather_point(xyz, cpu.farthest_point_sample(m, xyz))
+    dist, idx = ops.three_nn(cu(xyz), cu(known))
+    od, oi = cpu.three_nn(xyz, known)
+    assert same(idx, oi) and same(dist, od)
+    ow = cpu.three_weights(od)
+    w = ops.three_weights(dist)
+    assert same(w, ow)
+    pts = synth.features(c, 2, m, c)
+    want = cpu.three_interpolate(pts, oi, ow)
+    assert same(ops.three_interpolate(cu(pts), idx, w), want)
+    go = synth.features(c + 7, 2, n, c)
+    wantg = cpu.three_interpolate_grad(pts, oi, ow, go)
+    assert same(ops.three_interpolate_grad(cu(pts), idx, w, cu(go)), wantg)
+    p = cu(pts).requires_grad_(True)
+    ops.three_interpolate(p, idx, w).backward(cu(go))
+    assert same(p.grad, wantg)
+
+
+# ------------------------------------------------------------------------------------------------- attention (a13)
+@pytest.mark.parametrize("G,S,H,D", [(50, 32, 16, 4), (20, 32, 128, 4), (7, 16, 5, 4), (9, 64, 4, 8), (5, 100, 3, 16),
+                                     (11, 32, 6, 2), (13, 33, 3, 1)])
+def test_attention_contraction_matches_oracle(G, S, H, D):
+    rs = np.random.RandomState(G + S)
+    Q = rs.standard_normal((G, H * D)).astype(np.float32)
+    K = rs.standard_normal((G, S, H * D)).astype(np.float32)
+    V = rs.standard_normal((G, S, H * D)).astype(np.float32)
+    dout = rs.standard_normal((G, H * D)).astype(np.float32)
+    q, k, v = (cu(t).requires_grad_(True) for t in (Q, K, V))
+    out = ops.attention_contract(q, k, v, H, D)
+    np.testing.assert_allclose(npy(out), cpu.attention_fwd(Q, K, V, H, D), rtol=1e-5, atol=1e-6)
+    out.backward(cu(dout))
+    dQ, dK, dV = cpu.attention_bwd(Q, K, V, dout, H, D)
+    np.testing.assert_allclose(npy(q.grad), dQ, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(npy(k.grad), dK, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(npy(v.grad), dV, rtol=1e-5, atol=2e-6)
+
+
+def test_attention_layer_golden(golden):
+    g = golden("attention")
+    x = cu(g["x"])
+    H, D = int(g["heads"]), int(g["key_dim"])
+    layer = ops.AttentionLayer(output_dim=D, key_dim=D, num_heads=H, in_features=x.shape[-1]).to(DEV)
+    with torch.no_grad():
+        for lin, W, b in ((layer.query_net, "Wq", "bq"), (layer.key_net, "Wk", "bk"), (layer.value_net, "Wv", "bv")):
+            lin.weight.copy_(cu(g[W]).t())                          # TF Dense stores (in,out); torch Linear (out,in)
+            lin.bias.copy_(cu(g[b]))
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = layer([x, x[:, :, 0:1, :]])                           # attention_layer.py:259-261
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    np.testing.assert_allclose(npy(out), g["out"], rtol=2e-5, atol=2e-5)
+
+
+# -------------------------------------------------------------------- full-size, size-independent properties
+def test_full_size_properties_b16():
+    B, N = 16, 8192
+    xyz_np, feat_np = synth.scannet_batch(1000, B, N)
+    xyz, feat = cu(xyz_np), cu(feat_np)
+    fi = ops.farthest_point_sample(1024, xyz)
+    assert torch.equal(fi, ops.farthest_point_sample(1024, xyz))                      # deterministic
+    assert int(fi.min()) >= 0 and int(fi.max()) < N and bool((fi[:, 0] == 0).all())
+    new_xyz = ops.gather_point(xyz, fi)
+    assert torch.equal(new_xyz, torch.gather(xyz, 1, fi.long().unsqueeze(-1).expand(-1, -1, 3)))
+    # farthest-point property: the min distance to the chosen set never increases along the sequence
+    d_first = (new_xyz[:, 1:] - new_xyz[:, :1]).pow(2).sum(-1)
+    assert bool((d_first[:, 0] >= d_first.max(dim=1).values - 1e-4).all())
+    idx, cnt = ops.query_ball_point(0.1, 32, xyz, new_xyz)
+    g = ops.group_point(xyz, idx)
+    assert torch.equal(g, torch.gather(xyz.unsqueeze(1).expand(-1, 1024, -1, -1), 2,
+                                       idx.long().unsqueeze(-1).expand(-1, -1, -1, 3)))
+    dist = (g - new_xyz.unsqueeze(2)).pow(2).sum(-1).sqrt()
+    assert bool((dist < 0.1 + 1e-6).all())                                              # every slot inside the ball
+    ar = torch.arange(32, device=DEV).view(1, 1, 32)
+    valid = ar < cnt.unsqueeze(-1)
+    inc = (idx[:, :, 1:] > idx[:, :, :-1]) | ~valid[:, :, 1:]
+    assert bool(inc.all())                                                              # hits ascending
+    pad_ok = (idx == idx[:, :, :1]) | valid
+    assert bool(pad_ok.all()) and int(cnt.min()) >= 1                                   # padding repeats the first hit
+    gf = ops.group_point(feat, idx)
+    go = torch.randn_like(gf)
+    gp = ops.group_point_grad(feat, idx, go)
+    lhs, rhs = (gp.double() * feat.double()).sum(), (go.double() * gf.double()).sum()
+    assert abs(float(lhs - rhs)) < 1e-6 * max(1.0, abs(float(rhs)))                     # adjointness
+    d3, i3 = ops.three_nn(xyz, new_xyz)
+    assert bool((d3[:, :, 0] <= d3[:, :, 1]).all()) and bool((d3[:, :, 1] <= d3[:, :, 2]).all())
+    assert bool((d3[:, :, 0].gather(1, fi.long()) == 0).all())                          # a centroid is its own 1-NN
+    w = ops.three_weights(d3)
+    torch.testing.assert_close(w.sum(-1), torch.ones_like(w[..., 0]), rtol=0, atol=1e-6)
+    const = torch.full((B, 1024, 128), 2.5, device=DEV)
+    torch.testing.assert_close(ops.three_interpolate(const, i3, w), torch.full((B, N, 128), 2.5, device=DEV),
+                               rtol=0, atol=1e-5)
+    # and one full-size scene against the oracle
+    assert same(fi[3], cpu.farthest_point_sample(1024, xyz_np[3:4])[0])
+    oi, oc = cpu.query_ball_point(0.1, 32, xyz_np[3:4], npy(new_xyz[3:4]))
+    assert same(idx[3], oi[0]) and same(cnt[3], oc[0])
+
+
+def test_sample_and_group_and_fp_front_end():
+    xyz_np, feat_np = synth.scannet_batch(50, 2, 2048)
+    xyz, feat = cu(xyz_np), cu(feat_np)
+    new_xyz, new_points, idx, grouped_xyz = ops.sample_and_group(256, 0.2, 32, xyz, feat)
+    fi = cpu.farthest_point_sample(256, xyz_np)
+    nx = cpu.gather_point(xyz_np, fi)
+    oi, _ = cpu.query_ball_point(0.2, 32, xyz_np, nx)
+    gx = cpu.group_point(xyz_np, oi) - nx[:, :, None, :]
+    assert same(new_xyz, nx) and same(idx, oi) and same(grouped_xyz, gx)
+    assert same(new_points, np.concatenate([gx, cpu.group_point(feat_np, oi)], -1))     # [xyz_local, feats] order
+    p2 = synth.features(1, 2, 256, 32)
+    out = ops.fp_interpolate(xyz, new_xyz, feat, cu(p2))
+    od, o3 = cpu.three_nn(xyz_np, nx)
+    want = np.concatenate([cpu.three_interpolate(p2, o3, cpu.three_weights(od)), feat_np], 2)
+    assert same(out, want)
+    _, npk, idxk, _ = ops.sample_and_group(256, 0.2, 16, xyz, None, knn=True)
+    assert same(idxk, cpu.knn_point(16, xyz_np, nx)[1])

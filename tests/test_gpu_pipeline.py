@@ -1,0 +1,61 @@
+"""The pre-allocated two-stream geometry pipeline (what bench.py times) against the oracle, eager and as a CUDA graph."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu, synth
+from pcops_b200.pipeline import KEY_DIM, ScanNetGeometry
+
+pytestmark = pytest.mark.gpu
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def check_against_oracle(pipe, xyz_np, feat_np):
+    xyz = xyz_np
+    for lv in pipe.levels:
+        fi = cpu.farthest_point_sample(lv["m"], xyz)
+        assert np.array_equal(npy(lv["fps_idx"]), fi)
+        new_xyz = cpu.gather_point(xyz, fi)
+        assert np.array_equal(npy(lv["new_xyz"]), new_xyz)
+        idx, cnt = cpu.query_ball_point(lv["r"], lv["ns"], xyz, new_xyz)
+        assert np.array_equal(npy(lv["idx"]), idx) and np.array_equal(npy(lv["cnt"]), cnt)
+        assert np.array_equal(npy(lv["gxyz"]), cpu.group_point(xyz, idx))
+        assert np.array_equal(npy(lv["gfeat"]), cpu.group_point(npy(lv["feat"]), idx))
+        if pipe.attention:
+            want = cpu.attention_fwd(npy(lv["Q"]), npy(lv["K"]), npy(lv["V"]), lv["cout"] // KEY_DIM, KEY_DIM)
+            np.testing.assert_allclose(npy(lv["att"]), want, rtol=1e-5, atol=1e-6)
+        xyz = new_xyz
+    for fp in pipe.fps:
+        d, i3 = cpu.three_nn(npy(fp["xyz1"]), npy(fp["xyz2"]))
+        assert np.array_equal(npy(fp["idx"]), i3) and np.array_equal(npy(fp["dist"]), d)
+        w = cpu.three_weights(d)
+        assert np.array_equal(npy(fp["w"]), w)
+        assert np.array_equal(npy(fp["out"]), cpu.three_interpolate(npy(fp["points2"]), i3, w))
+
+
+def test_pipeline_matches_oracle_eager_and_graph():
+    B = 2
+    xyz_np, feat_np = synth.scannet_batch(300, B, 8192)
+    pipe = ScanNetGeometry(B)
+    pipe.set_inputs(torch.from_numpy(xyz_np), torch.from_numpy(feat_np))
+    pipe.forward(overlap=False)
+    torch.cuda.synchronize()
+    check_against_oracle(pipe, xyz_np, feat_np)
+    assert pipe.launches_per_step == 36
+
+    eager = [t.clone() for t in pipe.result_tensors()] + [fp["out"].clone() for fp in pipe.fps]
+    pipe.capture(overlap=True)
+    xyz2, feat2 = synth.scannet_batch(400, B, 8192)                 # new inputs through the captured graph
+    pipe.set_inputs(torch.from_numpy(xyz2), torch.from_numpy(feat2))
+    pipe.replay()
+    torch.cuda.synchronize()
+    check_against_oracle(pipe, xyz2, feat2)
+    pipe.set_inputs(torch.from_numpy(xyz_np), torch.from_numpy(feat_np))
+    pipe.replay()
+    torch.cuda.synchronize()
+    again = pipe.result_tensors() + [fp["out"] for fp in pipe.fps]
+    for a, b in zip(eager, again):
+        assert torch.equal(a, b)                                     # overlap + graph change nothing, bit for bit
