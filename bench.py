@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/s of the PointNet++ ScanNet geometry hot path (4 SA + 4 FP + attention contraction).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of B=16 synthetic 8192-point ScanNet-shaped chunks (xyz + 6
+feature channels), BASELINE.json configs[1] plus the attention contraction the metric names: per SA level
+FPS -> gather_point -> query_ball_point -> group_point(xyz) -> group_point(features) -> attention contraction, per FP
+level three_nn -> weights -> three_interpolate (36 kernel launches; pointcloud-segmentation-attention_b200/pipeline.py).
+
+Own arm (default).  One process per GPU, scenes sharded by rank, no data-path collective (weak scaling).  Prints ONE
+JSON line on rank 0:
+  value         scenes/s, inputs resident in HBM, K steps timed with CUDA events, max over ranks.  Every step reads a
+                different input batch (ring of R batches); one step touches > 500 MB (> 126 MB L2).
+  e2e           same metric through host buffers: per step H2D of the batch from pinned memory, the forward, D2H of
+                the geometry results (FPS / ball / three_nn indices, counts, three_nn distances) into pinned memory.
+  roofline      the kernel with the largest share of the step, duration from CUDA events on its own stream inside
+                the timed region, against its own bound; `rooflines` lists every op from a separate probed pass.
+  cpu_baseline  the CPU oracle (C port of the reference algorithms) on this box's host cores, bounded sample.
+Reference arm (--impl reference): the reference's own CPU code (oracle/_ref, compiled from /root/reference sources)
+where the reference has CPU code for an op, the C port elsewhere, on all host threads, same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "8192-pt scenes/sec (4 SA + 4 FP + attn)"
+UNIT = "scenes/s"
+WORKLOAD = "ScanNet semseg geometry forward, B=16x8192 xyz+6ch, 4 SA (1024/256/64/16, r=0.1/0.2/0.4/0.8, k=32) + 4 FP + attention contraction"
+NPOINTS = 8192
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="scenes per GPU per step (the config names 16)")
+    ap.add_argument("--ring", type=int, default=4, help="distinct input batches cycled through")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the forward as a CUDA graph in the value region")
+    ap.add_argument("--no-overlap", action="store_true", help="single stream")
+    ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-probe", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [ln for (t, ln) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [ln for (_, ln) in self.lines]
+        sm, mx, reasons = [], [], set()
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def _cpu_standins(rng_seed=7):
+    """Per-scene stand-ins for the dense-layer outputs the geometry ops consume (same role as in pipeline.py)."""
+    import numpy as np
+    from pcops_b200.pipeline import SA_LEVELS
+    rng = np.random.Generator(np.random.PCG64(rng_seed))
+    st, cin = {}, 6
+    for li, (m, r, ns, cout) in enumerate(SA_LEVELS):
+        n = NPOINTS if li == 0 else SA_LEVELS[li - 1][0]
+        st["feat%d" % li] = None if li == 0 else rng.standard_normal((1, n, cin), dtype=np.float32)
+        st["Q%d" % li] = rng.standard_normal((m, cout), dtype=np.float32)
+        st["K%d" % li] = rng.standard_normal((m, ns, cout), dtype=np.float32)
+        st["V%d" % li] = rng.standard_normal((m, ns, cout), dtype=np.float32)
+        cin = cout
+    for li, c in ((3, 512), (2, 256), (1, 256), (0, 128)):
+        st["p2_%d" % li] = rng.standard_normal((1, SA_LEVELS[li][0], c), dtype=np.float32)
+    return st
+
+
+def cpu_scene_forward(xyz, feat, st, use_ref):
+    """The same 36 op calls for ONE scene on the host.  use_ref: call the reference's own compiled CPU functions
+    (oracle/_ref) for the ops the reference implements on the CPU (ball query, group_point:
+    grouping/test/query_ball_point.cpp:19-84; three_nn, three_interpolate: tf_interpolate.cpp:60-127); FPS, gather and
+    the attention contraction have no CPU implementation in the reference -> C port (oracle/pcops_oracle.c)."""
+    from oracle import cpu, ref
+    from pcops_b200.pipeline import KEY_DIM, SA_LEVELS
+    cur, chk = xyz, 0
+    fp_in = {}
+    for li, (m, r, ns, cout) in enumerate(SA_LEVELS):
+        fi = cpu.farthest_point_sample(m, cur)
+        new_xyz = cpu.gather_point(cur, fi)
+        f = feat if li == 0 else st["feat%d" % li]
+        if use_ref:
+            idx = ref.cpu_query_ball_point(r, ns, cur, new_xyz)
+            ref.cpu_group_point(cur, idx)
+            ref.cpu_group_point(f, idx)
+        else:
+            idx, _ = cpu.query_ball_point(r, ns, cur, new_xyz)
+            cpu.group_point(cur, idx)
+            cpu.group_point(f, idx)
+        cpu.attention_fwd(st["Q%d" % li], st["K%d" % li], st["V%d" % li], cout // KEY_DIM, KEY_DIM)
+        fp_in[li] = (cur, new_xyz)
+        chk += int(fi.sum()) + int(idx.sum())
+        cur = new_xyz
+    for li in (3, 2, 1, 0):
+        x1, x2 = fp_in[li]
+        if use_ref:
+            d, i3 = ref.cpu_three_nn(x1, x2)
+            w = cpu.three_weights(d)
+            ref.cpu_three_interpolate(st["p2_%d" % li], i3, w)
+        else:
+            d, i3 = cpu.three_nn(x1, x2)
+            w = cpu.three_weights(d)
+            cpu.three_interpolate(st["p2_%d" % li], i3, w)
+        chk += int(i3.sum())
+    return chk
+
+
+def cpu_scenes_per_s(scenes_xyz, scenes_feat, threads, use_ref):
+    """Runs the per-scene host forward over the sample on `threads` host threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    st = _cpu_standins()
+    n = scenes_xyz.shape[0]
+
+    def one(i):
+        return cpu_scene_forward(scenes_xyz[i:i + 1], scenes_feat[i:i + 1], st, use_ref)
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for i in range(n):
+            one(i)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, range(n)))
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    if rank != 0:
+        return 0
+    from oracle import cpu, ref
+    from pcops_b200 import synth
+    cpu.lib()
+    use_ref = ref.available_cpu()
+    threads = host_threads()
+    per_step = max(threads, 8)              # scenes per step: a bounded sample of the B=16 x N-GPU batch
+    xyz, feat = synth.scannet_batch(0, per_step, NPOINTS)
+    for _ in range(min(args.warmup, 1)):
+        cpu_scenes_per_s(xyz[:threads], feat[:threads], threads, use_ref)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_scenes_per_s(xyz, feat, threads, use_ref)
+    dt = time.perf_counter() - t0
+    value = per_step * steps / dt
+    sample = "%d steps x %d scenes of the B=16 workload, %d host threads, one scene per thread" % (steps, per_step, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenes_per_step": per_step, "npoints": NPOINTS,
+                   "note": "host-only arm: the reference's geometry ops on the CPU (its interpolation ops are CPU-only; "
+                           "ball query / group_point from its standalone CPU programs; FPS, gather, attention contraction: "
+                           "C port of the reference CUDA / TF algorithm, the reference has no CPU code for them)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pcops_b200  # noqa: F401  (raises if libpcops.so is missing -- there is no fallback)
+    from pcops_b200 import sharding, synth
+    from pcops_b200.pipeline import ScanNetGeometry
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the geometry ops have no CPU implementation in the product")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, R, K, W = args.batch, max(1, args.ring), args.steps, max(args.warmup, 3)
+
+    # scene shards: rank r owns scenes [r*B*R, (r+1)*B*R) of the synthetic scene list
+    lo, _hi = sharding.shard_bounds(world * B * R, rank, world)
+    host_xyz, host_feat, dev_xyz, dev_feat = [], [], [], []
+    for i in range(R):
+        x, f = synth.scannet_batch(lo + i * B, B, NPOINTS)
+        hx, hf = torch.from_numpy(x).pin_memory(), torch.from_numpy(f).pin_memory()
+        host_xyz.append(hx)
+        host_feat.append(hf)
+        dev_xyz.append(hx.to(dev))
+        dev_feat.append(hf.to(dev))
+
+    pipe = ScanNetGeometry(B, NPOINTS, 6, dev, attention=True, seed=rank)
+    overlap = not args.no_overlap
+    main_stream = torch.cuda.current_stream(dev)
+
+    def step_resident(i, probes=None, graph=False):
+        pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+        if graph:
+            pipe.replay()
+        else:
+            pipe.forward(overlap, probes)
+
+    # warm-up (also sets per-device kernel attributes before any graph capture)
+    for i in range(W):
+        step_resident(i)
+    torch.cuda.synchronize(dev)
+    use_graph = bool(args.graph)
+    if use_graph:
+        pipe.capture(overlap)
+        for i in range(2):
+            step_resident(i, graph=True)
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region 1: inputs resident in HBM ----------------------------------------------------------------
+    work = pipe.algorithmic_work()
+    top_guess = "fps_sa1"
+    probes = {top_guess: []} if not use_graph else None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    sharding.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(main_stream)
+    for i in range(K):
+        step_resident(i, probes, use_graph)
+    e1.record(main_stream)
+    torch.cuda.synchronize(dev)
+    t_wall1 = time.time()
+    sharding.barrier()
+    ms_local = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_total = sharding.max_over_ranks(ms_local)
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- timed region 2: end to end through host buffers -------------------------------------------------------
+    results = pipe.result_tensors() + [fp["dist"] for fp in pipe.fps]
+    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in results]
+    h2d = pipe.input_bytes()
+    d2h = sum(t.numel() * t.element_size() for t in results)
+
+    def step_e2e(i):
+        pipe.set_inputs(host_xyz[i % R], host_feat[i % R], non_blocking=True)
+        pipe.forward(overlap)
+        for h, t in zip(host_out, results):
+            h.copy_(t, non_blocking=True)
+
+    for i in range(3):
+        step_e2e(i)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(main_stream)
+    for i in range(K):
+        step_e2e(i)
+    f1.record(main_stream)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    e2e_ms = sharding.max_over_ranks(f0.elapsed_time(f1))
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    checksum = int(sum(int(h.to(torch.int64).sum()) for h in host_out if h.dtype == torch.int32))
+
+    # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    nsm = pcops_b200._lib.lib().pc_num_sms()
+    fp32_peak_tops = nsm * 128 * sm_max * 1e6 / 1e12   # un-fused fp32 instructions/s (one op per lane per clock)
+
+    def roof(name, ms):
+        wk = work[name]
+        if wk["kind"] == "bytes":
+            ach = wk["amount"] / (ms * 1e-3) / 1e9
+            return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "ms": ms, "peak_source": peak_src}
+        ach = wk["amount"] / (ms * 1e-3) / 1e12
+        return {"kernel": name, "bound": "fp32", "achieved": ach, "peak": fp32_peak_tops, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms,
+                "peak_source": "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock)" % (nsm, sm_max)}
+
+    rooflines, op_ms = {}, {}
+    if not args.skip_probe:
+        allp = {n: [] for n in pipe.op_names()}
+        for i in range(min(K, 10)):
+            step_resident(i, allp, False)
+        torch.cuda.synchronize(dev)
+        for n, evs in allp.items():
+            d = sorted(a.elapsed_time(b) for a, b in evs)
+            op_ms[n] = d[len(d) // 2]
+            rooflines[n] = roof(n, op_ms[n])
+    if probes:
+        d = [a.elapsed_time(b) for a, b in probes[top_guess]]
+        top_ms = sum(d) / len(d)
+    else:
+        top_ms = op_ms.get(top_guess, float("nan"))
+    roofline = roof(top_guess, top_ms)
+    roofline["share_of_step"] = top_ms / (ms_local / K)
+    roofline["timed"] = "CUDA events around each launch on its stream, inside the value region (mean of %d)" % K \
+        if probes else "probed pass (graph replay hides single launches)"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline on this box (bounded sample) ------------------------------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.skip_cpu:
+        from oracle import cpu  # test infrastructure, used here only as the timed CPU baseline
+        cpu.lib()
+        threads = host_threads()
+        ns = args.cpu_scenes or max(threads, 8)
+        x = np.concatenate([t.numpy() for t in host_xyz])[:ns]
+        f = np.concatenate([t.numpy() for t in host_feat])[:ns]
+        v1, dt1 = cpu_scenes_per_s(x[:2], f[:2], 1, False)
+        vN, dtN = cpu_scenes_per_s(x, f, threads, False)
+        cpu_baseline = {"value": vN, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "%d scenes of the bench batches, %d host threads (one scene per thread), %.1f s"
+                                  % (x.shape[0], threads, dtN),
+                        "single_thread": {"value": v1, "cores": 1, "sample": "2 scenes, %.1f s" % dt1}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "npoints": NPOINTS, "feature_channels": 6,
+                   "parallelism": "scene-sharded x%d, no collective" % world, "streams": 2 if overlap else 1,
+                   "cuda_graph": use_graph, "input_ring": R,
+                   "l2": "inputs larger than L2: one step streams >500 MB (K/V/out tensors) through a 126 MB L2; "
+                         "each step reads a different batch of scenes"},
+        "fps_us_per_scene": {"sa1_batch_latency_us": top_ms * 1e3, "sa1_us_per_scene_throughput": top_ms * 1e3 / B},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K, "result_checksum": checksum},
+        "gpu_launches": pipe.launches_per_step * K,
+        "clocks": clocks,
+        "roofline": roofline,
+        "rooflines": rooflines,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

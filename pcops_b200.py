@@ -8,7 +8,7 @@ _root = os.path.dirname(os.path.abspath(__file__))
 if _root not in sys.path:
     sys.path.insert(0, _root)
 _pkg = importlib.import_module("pointcloud-segmentation-attention_b200")
-for _name in ("_lib", "tf_sampling", "tf_grouping", "tf_interpolate", "attention_layer", "pointnet_util", "pipeline",
+for _name in ("_lib", "tf_sampling", "tf_grouping", "tf_interpolate", "attention_layer", "pointnet_util", "pipeline", "synth",
               "sharding"):
     sys.modules[__name__ + "." + _name] = importlib.import_module("pointcloud-segmentation-attention_b200." + _name)
 sys.modules[__name__] = _pkg

@@ -35,12 +35,12 @@ class ScanNetGeometry:
         self.dev = torch.device(device)
         self.attention = attention
         self.L = _lib.lib()
-        g = torch.Generator(device="cpu").manual_seed(seed)
         f32, i32 = torch.float32, torch.int32
         dev = self.dev
+        g = torch.Generator(device=dev).manual_seed(seed)
 
         def rnd(*shape):
-            return torch.randn(*shape, generator=g, dtype=f32).to(dev)
+            return torch.randn(*shape, generator=g, dtype=f32, device=dev)
 
         self.xyz0 = torch.zeros((batch, npoints, 3), dtype=f32, device=dev)
         self.feat0 = torch.zeros((batch, npoints, feat_channels), dtype=f32, device=dev)
@@ -100,44 +100,100 @@ class ScanNetGeometry:
         return out
 
     # ---- one forward -----------------------------------------------------------------------------------------
-    def _sa_rest(self, lv, st):
+    def _sa_rest(self, lv, li, side, run):
         L, B, p = self.L, self.B, _lib.ptr
+        st = ctypes.c_void_p(side.cuda_stream)
         n, m, ns, cin = lv["n"], lv["m"], lv["ns"], lv["cin"]
-        _c(L.pc_query_ball(B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), st))
-        _c(L.pc_group_point(B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
-        _c(L.pc_group_point(B, n, cin, m, ns, p(lv["feat"]), p(lv["idx"]), p(lv["gfeat"]), st))
+        run("query_ball_sa%d" % (li + 1), side, lambda: L.pc_query_ball(
+            B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), st))
+        run("group_xyz_sa%d" % (li + 1), side, lambda: L.pc_group_point(
+            B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
+        run("group_feat_sa%d" % (li + 1), side, lambda: L.pc_group_point(
+            B, n, cin, m, ns, p(lv["feat"]), p(lv["idx"]), p(lv["gfeat"]), st))
         if self.attention:
-            _c(L.pc_attention_fwd(B * m, ns, lv["cout"] // KEY_DIM, KEY_DIM, p(lv["Q"]), p(lv["K"]), p(lv["V"]),
-                                  p(lv["att"]), st))
+            run("attention_sa%d" % (li + 1), side, lambda: L.pc_attention_fwd(
+                B * m, ns, lv["cout"] // KEY_DIM, KEY_DIM, p(lv["Q"]), p(lv["K"]), p(lv["V"]), p(lv["att"]), st))
 
-    def _fp(self, fp, st):
+    def _fp(self, fp, side, run):
         L, B, p = self.L, self.B, _lib.ptr
+        st = ctypes.c_void_p(side.cuda_stream)
         n, m, c = fp["n"], fp["m"], fp["c"]
-        _c(L.pc_three_nn(B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
-        _c(L.pc_three_weights(B * n, p(fp["dist"]), p(fp["w"]), st))
-        _c(L.pc_three_interpolate(B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
+        tag = "fp%d" % (4 - fp["level"])  # FP1 is the deepest level (pointnet2_sem_seg_attention.py:46-53)
+        run("three_nn_" + tag, side, lambda: L.pc_three_nn(
+            B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
+        run("three_weights_" + tag, side, lambda: L.pc_three_weights(B * n, p(fp["dist"]), p(fp["w"]), st))
+        run("three_interpolate_" + tag, side, lambda: L.pc_three_interpolate(
+            B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
 
-    def forward(self, overlap=True):
-        """Enqueue one forward on the current stream (plus the side stream when overlap=True)."""
+    def forward(self, overlap=True, probes=None):
+        """Enqueue one forward on the current stream (plus the side stream when overlap=True).
+
+        ``probes``: optional dict name -> list; for every op whose name is a key, a (start, end) pair of CUDA events
+        recorded on the op's own stream around its launch is appended (bench.py reads kernel durations from them)."""
         L, B, p = self.L, self.B, _lib.ptr
         main = torch.cuda.current_stream(self.dev)
         side = self.side if overlap else main
         s_main = ctypes.c_void_p(main.cuda_stream)
-        s_side = ctypes.c_void_p(side.cuda_stream)
         fp_of = {fp["level"]: fp for fp in self.fps}
+
+        def run(name, stream, call):
+            if probes is not None and name in probes:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                _c(call())
+                e1.record(stream)
+                probes[name].append((e0, e1))
+            else:
+                _c(call())
+
         if overlap:
             side.wait_stream(main)
         for li, lv in enumerate(self.levels):
-            _c(L.pc_fps(B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), s_main))
-            _c(L.pc_gather_point(B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
+            run("fps_sa%d" % (li + 1), main, lambda: L.pc_fps(
+                B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), s_main))
+            run("gather_sa%d" % (li + 1), main, lambda: L.pc_gather_point(
+                B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
             if overlap:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
-            self._sa_rest(lv, s_side)
-            self._fp(fp_of[li], s_side)
+            self._sa_rest(lv, li, side, run)
+            self._fp(fp_of[li], side, run)
         if overlap:
             main.wait_stream(side)
+
+    def op_names(self):
+        names = []
+        for li in range(len(self.levels)):
+            names += ["fps_sa%d" % (li + 1), "gather_sa%d" % (li + 1), "query_ball_sa%d" % (li + 1),
+                      "group_xyz_sa%d" % (li + 1), "group_feat_sa%d" % (li + 1)]
+            if self.attention:
+                names.append("attention_sa%d" % (li + 1))
+        for fp in self.fps:
+            tag = "fp%d" % (4 - fp["level"])
+            names += ["three_nn_" + tag, "three_weights_" + tag, "three_interpolate_" + tag]
+        return names
+
+    def algorithmic_work(self):
+        """Per-op algorithmic bytes (HBM-bound ops) or fp32 operations (compute-bound ops) of ONE forward over the
+        whole batch, from the formulas of SURVEY.md 8(d) / DESIGN.md.  name -> dict(kind, amount)."""
+        B, w = self.B, {}
+        for li, lv in enumerate(self.levels):
+            n, m, ns, cin, cout, t = lv["n"], lv["m"], lv["ns"], lv["cin"], lv["cout"], "_sa%d" % (li + 1)
+            w["fps" + t] = dict(kind="fp32_ops", amount=B * (m - 1) * n * 10, bytes=B * (12 * n + 4 * m))
+            w["gather" + t] = dict(kind="bytes", amount=B * (4 * m + 12 * m + 12 * m))
+            w["query_ball" + t] = dict(kind="fp32_ops", amount=B * m * n * 11,  # upper bound: every pair tested
+                                       bytes=B * (12 * n + 12 * m + 4 * m * ns + 4 * m))
+            for nm, c in (("group_xyz", 3), ("group_feat", cin)):
+                w[nm + t] = dict(kind="bytes", amount=B * (4 * m * ns + 4 * min(n, m * ns) * c + 4 * m * ns * c))
+            if self.attention:
+                w["attention" + t] = dict(kind="bytes", amount=B * m * (2 * 4 * ns * cout + 2 * 4 * cout))
+        for fp in self.fps:
+            n, m, c, t = fp["n"], fp["m"], fp["c"], "_fp%d" % (4 - fp["level"])
+            w["three_nn" + t] = dict(kind="fp32_ops", amount=B * n * m * 11, bytes=B * (12 * n + 12 * m + 24 * n))
+            w["three_weights" + t] = dict(kind="bytes", amount=B * n * 24)
+            w["three_interpolate" + t] = dict(kind="bytes", amount=B * (24 * n + 4 * m * c + 4 * n * c))
+        return w
 
     # ---- CUDA graph ------------------------------------------------------------------------------------------
     def capture(self, overlap=True):
