@@ -12,11 +12,13 @@ level three_nn -> weights -> three_interpolate (36 kernel launches; pointcloud-s
 Own arm (default).  One process per GPU, scenes sharded by rank, no data-path collective (weak scaling).  Prints ONE
 JSON line on rank 0:
   value         scenes/s, inputs resident in HBM, K steps timed with CUDA events, max over ranks.  Every step reads a
-                different input batch (ring of R batches); one step touches > 500 MB (> 126 MB L2).
-  e2e           same metric through host buffers: per step H2D of the batch from pinned memory, the forward, D2H of
-                the geometry results (FPS / ball / three_nn indices, counts, three_nn distances) into pinned memory.
-  roofline      the kernel with the largest share of the step, duration from CUDA events on its own stream inside
-                the timed region, against its own bound; `rooflines` lists every op from a separate probed pass.
+                different input batch (ring of R batches); one step touches > 500 MB (> 126 MB L2).  Steps are
+                independent batches, so --depth of them are in flight at once, each on its own streams and buffers
+                (FPS is a latency-bound chain on B SMs; the other SMs work on neighbouring batches meanwhile).
+  e2e           same metric through host buffers: per step H2D of the batch from pinned memory, the forward, ONE D2H
+                of the geometry results (FPS / ball / three_nn indices, counts, three_nn distances) to pinned memory.
+  roofline      the kernel with the largest share of a step, duration from CUDA events on its own stream, against
+                its own bound; `rooflines` lists every op (probed eager pass of one pipeline instance).
   cpu_baseline  the CPU oracle (C port of the reference algorithms) on this box's host cores, bounded sample.
 Reference arm (--impl reference): the reference's own CPU code (oracle/_ref, compiled from /root/reference sources)
 where the reference has CPU code for an op, the C port elsewhere, on all host threads, same metric.
@@ -47,7 +49,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="scenes per GPU per step (the config names 16)")
     ap.add_argument("--ring", type=int, default=4, help="distinct input batches cycled through")
-    ap.add_argument("--graph", type=int, default=0, help="1: replay the forward as a CUDA graph in the value region")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay each forward as a CUDA graph (default); 0: eager")
+    ap.add_argument("--depth", type=int, default=4, help="independent batches in flight (pipeline instances, own streams)")
     ap.add_argument("--no-overlap", action="store_true", help="single stream")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -263,25 +266,37 @@ def main():
         dev_xyz.append(hx.to(dev))
         dev_feat.append(hf.to(dev))
 
-    pipe = ScanNetGeometry(B, NPOINTS, 6, dev, attention=True, seed=rank)
+    D = max(1, args.depth)
+    pipes = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=True, seed=rank * 64 + d, own_streams=True) for d in range(D)]
+    pipe = pipes[0]
     overlap = not args.no_overlap
-    main_stream = torch.cuda.current_stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    use_graph = bool(args.graph)
 
     def step_resident(i, probes=None, graph=False):
-        pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+        pl = pipes[i % D]
+        pl.set_inputs(dev_xyz[i % R], dev_feat[i % R])
         if graph:
-            pipe.replay()
+            pl.replay()
         else:
-            pipe.forward(overlap, probes)
+            pl.forward(overlap, probes)
+
+    def fork():
+        for pl in pipes:
+            pl.main.wait_stream(cur)
+
+    def join():
+        for pl in pipes:
+            cur.wait_stream(pl.main)
 
     # warm-up (also sets per-device kernel attributes before any graph capture)
-    for i in range(W):
+    for i in range(max(W, D)):
         step_resident(i)
     torch.cuda.synchronize(dev)
-    use_graph = bool(args.graph)
     if use_graph:
-        pipe.capture(overlap)
-        for i in range(2):
+        for pl in pipes:
+            pl.capture(overlap)
+        for i in range(2 * D):
             step_resident(i, graph=True)
         torch.cuda.synchronize(dev)
 
@@ -297,10 +312,12 @@ def main():
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    e0.record(main_stream)
+    e0.record(cur)
+    fork()
     for i in range(K):
         step_resident(i, probes, use_graph)
-    e1.record(main_stream)
+    join()
+    e1.record(cur)
     torch.cuda.synchronize(dev)
     t_wall1 = time.time()
     sharding.barrier()
@@ -310,31 +327,36 @@ def main():
     value = world * B * K / (ms_total * 1e-3)
 
     # ---- timed region 2: end to end through host buffers -------------------------------------------------------
-    results = pipe.result_tensors() + [fp["dist"] for fp in pipe.fps]
-    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in results]
+    # per step: H2D of the batch from pinned memory, the forward, ONE D2H of the result arena into pinned memory
+    host_out = [torch.empty(pl.result_arena().shape, dtype=torch.int32).pin_memory() for pl in pipes]
     h2d = pipe.input_bytes()
-    d2h = sum(t.numel() * t.element_size() for t in results)
+    d2h = pipe.result_arena().numel() * 4
 
     def step_e2e(i):
-        pipe.set_inputs(host_xyz[i % R], host_feat[i % R], non_blocking=True)
-        pipe.forward(overlap)
-        for h, t in zip(host_out, results):
-            h.copy_(t, non_blocking=True)
+        pl = pipes[i % D]
+        pl.set_inputs(host_xyz[i % R], host_feat[i % R], non_blocking=True)
+        if use_graph:
+            pl.replay()
+        else:
+            pl.forward(overlap)
+        pl.read_results(host_out[i % D])
 
-    for i in range(3):
+    for i in range(max(3, D)):
         step_e2e(i)
     torch.cuda.synchronize(dev)
     sharding.barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(main_stream)
+    f0.record(cur)
+    fork()
     for i in range(K):
         step_e2e(i)
-    f1.record(main_stream)
+    join()
+    f1.record(cur)
     torch.cuda.synchronize(dev)
     sharding.barrier()
     e2e_ms = sharding.max_over_ranks(f0.elapsed_time(f1))
     e2e_value = world * B * K / (e2e_ms * 1e-3)
-    checksum = int(sum(int(h.to(torch.int64).sum()) for h in host_out if h.dtype == torch.int32))
+    checksum = int(sum(int(h.to(torch.int64).sum()) for h in host_out))
 
     # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
     peaks = {}
@@ -362,9 +384,10 @@ def main():
     rooflines, op_ms = {}, {}
     if not args.skip_probe:
         allp = {n: [] for n in pipe.op_names()}
-        for i in range(min(K, 10)):
-            step_resident(i, allp, False)
-        torch.cuda.synchronize(dev)
+        for i in range(min(K, 10)):      # one pipeline instance alone, eager: per-op durations without cross-step overlap
+            pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+            pipe.forward(overlap, allp)
+            torch.cuda.synchronize(dev)
         for n, evs in allp.items():
             d = sorted(a.elapsed_time(b) for a, b in evs)
             op_ms[n] = d[len(d) // 2]
@@ -375,9 +398,10 @@ def main():
     else:
         top_ms = op_ms.get(top_guess, float("nan"))
     roofline = roof(top_guess, top_ms)
-    roofline["share_of_step"] = top_ms / (ms_local / K)
+    roofline["share_of_step"] = top_ms / sum(op_ms.values()) if op_ms else None
     roofline["timed"] = "CUDA events around each launch on its stream, inside the value region (mean of %d)" % K \
-        if probes else "probed pass (graph replay hides single launches)"
+        if probes else "CUDA events around each launch on its stream in a probed eager pass right after the value " \
+                       "region (graph replay hides single launches); share = its time / sum of all op times"
 
     if rank != 0:
         if world > 1:
@@ -405,8 +429,8 @@ def main():
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "npoints": NPOINTS, "feature_channels": 6,
-                   "parallelism": "scene-sharded x%d, no collective" % world, "streams": 2 if overlap else 1,
-                   "cuda_graph": use_graph, "input_ring": R,
+                   "parallelism": "scene-sharded x%d, no collective" % world, "streams_per_batch": 5 if overlap else 1,
+                   "cuda_graph": use_graph, "input_ring": R, "batches_in_flight": D,
                    "l2": "inputs larger than L2: one step streams >500 MB (K/V/out tensors) through a 126 MB L2; "
                          "each step reads a different batch of scenes"},
         "fps_us_per_scene": {"sa1_batch_latency_us": top_ms * 1e3, "sa1_us_per_scene_throughput": top_ms * 1e3 / B},

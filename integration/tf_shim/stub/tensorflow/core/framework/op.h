@@ -1,0 +1,1 @@
+#include "tf_syntax_stub.h"

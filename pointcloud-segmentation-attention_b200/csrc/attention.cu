@@ -84,37 +84,113 @@ __device__ __forceinline__ void head_softmax(int S, const float *__restrict__ kh
   for (int i = 0; i < NS; ++i) a[i] *= inv;
 }
 
+// Sum of D per-lane values over the warp, result for component d valid in every lane.  For D == 4 the classic
+// halving exchange is used: 6 shuffles instead of 4 x 5.
+template <int D>
+__device__ __forceinline__ void warp_sum_vec(float (&o)[D]) {
+  if (D == 4) {
+    const int lane = threadIdx.x & 31;
+    // step 1 (xor 16): lanes 0-15 keep components 0,1; lanes 16-31 keep 2,3
+    const bool hi = lane & 16;
+    float s0 = hi ? o[0] : o[2], s1 = hi ? o[1] : o[3];          // what this lane gives away
+    float k0 = hi ? o[2] : o[0], k1 = hi ? o[3] : o[1];          // what it keeps
+    k0 += __shfl_xor_sync(PC_FULL_MASK, s0, 16);
+    k1 += __shfl_xor_sync(PC_FULL_MASK, s1, 16);
+    // step 2 (xor 8): keep one component
+    const bool hi8 = lane & 8;
+    float g = hi8 ? k0 : k1, k = hi8 ? k1 : k0;
+    k += __shfl_xor_sync(PC_FULL_MASK, g, 8);
+    k += __shfl_xor_sync(PC_FULL_MASK, k, 4);
+    k += __shfl_xor_sync(PC_FULL_MASK, k, 2);
+    k += __shfl_xor_sync(PC_FULL_MASK, k, 1);
+    // lane l now holds component c(l) = 2*(l>>4 & 1) + (l>>3 & 1); lanes 0, 8, 16, 24 hold components 0, 1, 2, 3
+    o[0] = __shfl_sync(PC_FULL_MASK, k, 0);
+    o[1] = __shfl_sync(PC_FULL_MASK, k, 8);
+    o[2] = __shfl_sync(PC_FULL_MASK, k, 16);
+    o[3] = __shfl_sync(PC_FULL_MASK, k, 24);
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = warp_sum(o[d]);
+  }
+}
+
+// One warp per (neighbourhood, head), warp-stride loop over heads.  When a head is at most one sample per lane
+// (S <= 32, the reference's nsample) the K and V rows of the NEXT head are requested before the current head's
+// softmax, so every lane keeps four 128-bit loads in flight: the kernel is a pure HBM stream of K and V.
 template <int D, int NS, bool VEC>
 __global__ void __launch_bounds__(kAttWarps * 32)
 attention_fwd_kernel(size_t heads_total, int S, int H, const float *__restrict__ Q, const float *__restrict__ K,
                      const float *__restrict__ V, float *__restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const size_t gh = (size_t)blockIdx.x * kAttWarps + (threadIdx.x >> 5);  // g*H + h
-  if (gh >= heads_total) return;
+  const size_t stride = (size_t)gridDim.x * kAttWarps;
+  size_t gh = (size_t)blockIdx.x * kAttWarps + (threadIdx.x >> 5);  // g*H + h
   const float rsd = 1.0f / sqrtf((float)D);
-  // (g,h) chunk: K + g*S*H*D + h*S*D == K + gh*S*D ;  Q + g*H*D + h*D == Q + gh*D
-  const float *kh = K + gh * (size_t)S * D;
-  const float *vh = V + gh * (size_t)S * D;
-  float q[D];
-  load_row<D, VEC>(Q + gh * D, q);
-  float a[NS];
-  head_softmax<D, NS, VEC>(S, kh, q, rsd, a);
-  float o[D];
+  if constexpr (NS == 1) {
+    // (g,h) chunk: K + g*S*H*D + h*S*D == K + gh*S*D ;  Q + g*H*D + h*D == Q + gh*D
+    const bool has = lane < S;
+    float kc[D], vc[D], qc[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int i = 0; i < NS; ++i) {
-    const int s = lane + 32 * i;
-    if (s < S) {
-      float v[D];
-      load_row<D, VEC>(vh + (size_t)s * D, v);
-#pragma unroll
-      for (int d = 0; d < D; ++d) o[d] = fmaf(a[i], v[d], o[d]);
+    for (int d = 0; d < D; ++d) kc[d] = vc[d] = qc[d] = 0.f;
+    if (gh < heads_total) {
+      if (has) {
+        load_row<D, VEC>(K + gh * (size_t)S * D + (size_t)lane * D, kc);
+        load_row<D, VEC>(V + gh * (size_t)S * D + (size_t)lane * D, vc);
+      }
+      load_row<D, VEC>(Q + gh * D, qc);
     }
-  }
+    for (; gh < heads_total; gh += stride) {
+      const size_t nx = gh + stride;
+      float kn[D], vn[D], qn[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) o[d] = warp_sum(o[d]);
-  if (lane == 0) store_row<D, VEC>(out + gh * D, o);
+      for (int d = 0; d < D; ++d) kn[d] = vn[d] = qn[d] = 0.f;
+      if (nx < heads_total) {  // prefetch the next head of this warp
+        if (has) {
+          load_row<D, VEC>(K + nx * (size_t)S * D + (size_t)lane * D, kn);
+          load_row<D, VEC>(V + nx * (size_t)S * D + (size_t)lane * D, vn);
+        }
+        load_row<D, VEC>(Q + nx * D, qn);
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc = fmaf(qc[d], kc[d], acc);
+      const float logit = has ? acc * rsd : -INFINITY;
+      const float mx = warp_max(logit);
+      const float e = has ? expf(logit - mx) : 0.f;
+      const float inv = 1.0f / warp_sum(e);
+      const float a = e * inv;
+      float o[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) o[d] = fmaf(a, vc[d], 0.f);
+      warp_sum_vec<D>(o);
+      if (lane == 0) store_row<D, VEC>(out + gh * D, o);
+#pragma unroll
+      for (int d = 0; d < D; ++d) { kc[d] = kn[d]; vc[d] = vn[d]; qc[d] = qn[d]; }
+    }
+  } else
+  for (; gh < heads_total; gh += stride) {
+    const float *kh = K + gh * (size_t)S * D;
+    const float *vh = V + gh * (size_t)S * D;
+    float q[D];
+    load_row<D, VEC>(Q + gh * D, q);
+    float a[NS];
+    head_softmax<D, NS, VEC>(S, kh, q, rsd, a);
+    float o[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int s = lane + 32 * i;
+      if (s < S) {
+        float v[D];
+        load_row<D, VEC>(vh + (size_t)s * D, v);
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] = fmaf(a[i], v[d], o[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = warp_sum(o[d]);
+    if (lane == 0) store_row<D, VEC>(out + gh * D, o);
+  }
 }
 
 template <int D, int NS, bool VEC>
@@ -179,7 +255,9 @@ attention_bwd_kernel(size_t heads_total, int S, int H, const float *__restrict__
 template <int D, int NS, bool VEC>
 int launch_fwd(size_t heads, int S, int H, const float *Q, const float *K, const float *V, float *out,
                cudaStream_t st) {
-  const size_t blocks = (heads + kAttWarps - 1) / kAttWarps;
+  size_t blocks = (heads + kAttWarps - 1) / kAttWarps;
+  const size_t cap = (size_t)num_sms() * 16;  // persistent-ish: 8 resident CTAs per SM, two waves
+  if (blocks > cap) blocks = cap;
   attention_fwd_kernel<D, NS, VEC><<<(unsigned)blocks, kAttWarps * 32, 0, st>>>(heads, S, H, Q, K, V, out);
   PC_RETURN_LAUNCH_STATUS();
 }

@@ -7,11 +7,18 @@
 // input; d2 < radius*radius would NOT, radius*radius rounds up for 0.1/0.2/0.4/0.8).  Unfilled slots repeat the
 // first hit, pts_cnt saturates at nsample, rows of empty balls are zero.
 //
-// Design: the dataset streams through shared memory in tiles shared by the whole CTA; a warp owns QW queries and
-// tests 32 candidates per step (one per lane) against all of them, so each candidate load is amortised over QW
-// distance evaluations; hits are appended in index order with ballot + popc prefix (order-preserving compaction),
-// and a warp stops evaluating a query once it has nsample hits.  The reference runs one thread per query streaming
-// global memory on b CTAs; this runs b * m / (8*QW) CTAs.
+// Design (FP32-pipe bound; the pair tests are the whole cost):
+//   * a CTA owns 32 queries of one scene (lane = query) and its 8 warps split the candidate range into 8 contiguous
+//     segments, so a level with few queries still spreads over the chip (B*m/32*8 warps);
+//   * each warp streams its segment through a private shared-memory stage, transposed to SoA so that one LDS.128
+//     broadcast feeds four candidates as two packed fp32x2 operands; a thread tests two candidates per FADD2/FMUL2/
+//     FFMA2 (every operation still rounded on its own, common.cuh);
+//   * the inner loop is branch-free: a hit sets one bit of a 32-candidate word (per query, per segment) kept in shared
+//     memory; ordering is free because bit position == candidate index;
+//   * after a chunk (<= 8192 candidates) the 8 segment counts of a query are exchanged through shared memory, each
+//     thread turns its own words into indices written at (hits in earlier segments) + rank -- "first nsample in
+//     ascending index" without any sort, ballot or atomics -- and the CTA stops as soon as all its queries are full.
+// The reference runs one thread per query streaming global memory on b CTAs with a divergent early exit.
 #include <math.h>
 #include <string.h>
 #include "common.cuh"
@@ -19,72 +26,125 @@
 namespace pc {
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kTile = 2048;  // candidates per shared-memory tile (24 KB)
+constexpr int kSeg = 8;           // warps per CTA = candidate segments
+constexpr int kStage = 256;       // candidates staged per warp per step (multiple of 32)
+constexpr int kStagePad = 12;     // row stride 268 floats: 16-byte aligned rows, x / y / z rows 12 banks apart for the transpose
+constexpr int kChunk = 8192;      // candidates per chunk (capacity of the hit bitmap)
+constexpr int kStageRow = kStage + kStagePad;
 
-template <int QW>
-__global__ void __launch_bounds__(kWarps * 32)
-ball_query_kernel(int n, int m, float s_star, int nsample, const float *__restrict__ xyz1,
+struct BallSmem {
+  float stage[kSeg][3][kStageRow];
+  unsigned bits[kChunk / 32][32];  // [word][query lane]: bank == lane, conflict-free for writer and reader
+  int seg_cnt[kSeg][32];
+  int seg_first[kSeg][32];
+};
+
+__global__ void __launch_bounds__(kSeg * 32, 3)
+ball_query_kernel(int n, int m, float s_star, int nsample, float one, const float *__restrict__ xyz1,
                   const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt) {
-  __shared__ float tile[kTile * 3];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BallSmem &sm = *reinterpret_cast<BallSmem *>(smem_raw);
   const int scene = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * 32 + lane;
+  const bool live = q < m;
   const float *data = xyz1 + (size_t)scene * n * 3;
-  const int q0 = (blockIdx.x * kWarps + warp) * QW;
-  const unsigned lt = lanemask_lt();
+  const float *qp = xyz2 + ((size_t)scene * m + (live ? q : 0)) * 3;
+  const float qx = qp[0], qy = qp[1], qz = qp[2];
+  const f32x2 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz), one2 = pack2(one, one);
+  int *row = idx + ((size_t)scene * m + (live ? q : 0)) * nsample;
+  const float inf = __int_as_float(0x7f800000);
+  const int thr = (s_star >= 0.0f) ? __float_as_int(s_star) + 1 : 0;  // s_star < 0: nothing can hit
 
-  float qx[QW], qy[QW], qz[QW];
-  int cnt[QW], first[QW];
-  int *row[QW];
-#pragma unroll
-  for (int i = 0; i < QW; ++i) {
-    const int q = q0 + i;
-    const bool live = q < m;
-    const float *qp = xyz2 + ((size_t)scene * m + (live ? q : 0)) * 3;
-    qx[i] = qp[0]; qy[i] = qp[1]; qz[i] = qp[2];
-    cnt[i] = live ? 0 : nsample;  // dead slots behave as already full
-    first[i] = 0;
-    row[i] = idx + ((size_t)scene * m + (live ? q : 0)) * nsample;
-  }
+  int total = live ? 0 : nsample;  // hits of this query in all earlier chunks (dead lanes count as full)
+  int first = INT_MAX;             // first hit of this query so far (absolute index)
+  float(*st)[kStageRow] = sm.stage[warp];
 
-  for (int t0 = 0; t0 < n; t0 += kTile) {
-    bool warp_full = true;
+  for (int c0 = 0; c0 < n; c0 += kChunk) {
+    const int cn = min(kChunk, n - c0);
+    const int seg_len = ((cn + kSeg - 1) / kSeg + 31) / 32 * 32;  // multiple of 32: segments own whole words
+    const int s_lo = min(cn, warp * seg_len), s_hi = min(cn, s_lo + seg_len);
+    int cnt = 0, sfirst = INT_MAX;
+    // The stage is double-buffered through registers: the 24 coalesced loads of the NEXT stage are in flight while
+    // the current one is being tested, so global latency never stalls the warp.
+    constexpr int kLoads = kStage * 3 / 32;
+    float pre[kLoads];
+    auto fetch = [&](int t0) {
+      const int tn = min(kStage, s_hi - t0);
+      const float *src = data + (size_t)(c0 + t0) * 3;
 #pragma unroll
-    for (int i = 0; i < QW; ++i) warp_full = warp_full && (cnt[i] >= nsample);
-    if (__syncthreads_and(warp_full)) break;  // also fences the previous tile's readers
-    const int tn = min(kTile, n - t0);
-    for (int i = threadIdx.x; i < tn * 3; i += kWarps * 32) tile[i] = data[(size_t)t0 * 3 + i];
+      for (int u = 0; u < kLoads; ++u) {
+        const int i = lane + 32 * u;
+        pre[u] = (i < tn * 3) ? __ldg(src + i) : inf;  // slots past tn become +inf (never hit)
+      }
+    };
+    if (s_lo < s_hi) fetch(s_lo);
+    for (int t0 = s_lo; t0 < s_hi; t0 += kStage) {
+      const int tn = min(kStage, s_hi - t0);
+      __syncwarp();
+      // AoS -> SoA transpose of the fetched candidates into this warp's stage
+#pragma unroll
+      for (int u = 0; u < kLoads; ++u) {
+        const int i = lane + 32 * u, k = i / 3, c = i - k * 3;
+        st[c][k] = pre[u];
+      }
+      __syncwarp();
+      if (t0 + kStage < s_hi) fetch(t0 + kStage);
+      const int nwords = (tn + 31) / 32;
+      for (int w = 0; w < nwords; ++w) {
+        unsigned word = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {  // 4 candidates per step
+          const int k = w * 32 + g * 4;
+          const float4 xs = *reinterpret_cast<const float4 *>(&st[0][k]);
+          const float4 ys = *reinterpret_cast<const float4 *>(&st[1][k]);
+          const float4 zs = *reinterpret_cast<const float4 *>(&st[2][k]);
+          float d0, d1, d2, d3;
+          unpack2(sqdist3_x2(qx2, qy2, qz2, pack2(xs.x, xs.y), pack2(ys.x, ys.y), pack2(zs.x, zs.y), one2), d0, d1);
+          unpack2(sqdist3_x2(qx2, qy2, qz2, pack2(xs.z, xs.w), pack2(ys.z, ys.w), pack2(zs.z, zs.w), one2), d2, d3);
+          // d <= s_star  <=>  bits(d) - thr < 0 (non-negative floats order like ints; NaN bits exceed every thr):
+          // the sign bit is shifted into the word, candidate j of the word lands in bit 31-j
+          word = __funnelshift_l(__float_as_int(d0) - thr, word, 1);
+          word = __funnelshift_l(__float_as_int(d1) - thr, word, 1);
+          word = __funnelshift_l(__float_as_int(d2) - thr, word, 1);
+          word = __funnelshift_l(__float_as_int(d3) - thr, word, 1);
+        }
+        word = __brev(word);           // bit j <-> candidate j
+        const int wi = (t0 >> 5) + w;  // word index inside the chunk
+        sm.bits[wi][lane] = word;
+        if (word && sfirst == INT_MAX) sfirst = c0 + wi * 32 + __ffs(word) - 1;
+        cnt += __popc(word);
+      }
+    }
+    sm.seg_cnt[warp][lane] = cnt;
+    sm.seg_first[warp][lane] = sfirst;
     __syncthreads();
-    if (warp_full) continue;
-    for (int k0 = 0; k0 < tn; k0 += 32) {
-      const int k = k0 + lane;
-      const bool valid = k < tn;
-      const int kk = valid ? k : 0;
-      const float x = tile[kk * 3 + 0], y = tile[kk * 3 + 1], z = tile[kk * 3 + 2];
+    int base = total, chunk_total = 0;
 #pragma unroll
-      for (int i = 0; i < QW; ++i) {
-        if (cnt[i] < nsample) {  // warp-uniform
-          const float s = sqdist3(qx[i], qy[i], qz[i], x, y, z);
-          const bool hit = valid && (s <= s_star);
-          const unsigned mask = __ballot_sync(PC_FULL_MASK, hit);
-          if (mask) {
-            if (cnt[i] == 0) first[i] = t0 + k0 + __ffs(mask) - 1;
-            const int pos = cnt[i] + __popc(mask & lt);
-            if (hit && pos < nsample) row[i][pos] = t0 + k;
-            cnt[i] = min(nsample, cnt[i] + __popc(mask));
-          }
+    for (int s = 0; s < kSeg; ++s) {
+      const int c = sm.seg_cnt[s][lane];
+      if (s < warp) base += c;
+      chunk_total += c;
+      first = min(first, sm.seg_first[s][lane]);
+    }
+    if (live && cnt > 0 && base < nsample) {  // this segment contributes slots [base, base + cnt) of the row
+      int pos = base;
+      for (int wi = s_lo >> 5; wi < (s_hi + 31) >> 5 && pos < nsample; ++wi) {
+        unsigned word = sm.bits[wi][lane];
+        while (word && pos < nsample) {
+          row[pos++] = c0 + wi * 32 + __ffs(word) - 1;
+          word &= word - 1;
         }
       }
     }
+    total = min(nsample, total + chunk_total);
+    if (__syncthreads_and(total >= nsample)) break;  // also protects bits / seg_* against the next chunk's writers
   }
 
-#pragma unroll
-  for (int i = 0; i < QW; ++i) {
-    if (q0 + i < m) {
-      const int fill = cnt[i] ? first[i] : 0;  // tf_grouping_g.cu:26-29; empty ball -> zero row
-      for (int l = cnt[i] + lane; l < nsample; l += 32) row[i][l] = fill;
-      if (lane == 0) pts_cnt[(size_t)scene * m + q0 + i] = cnt[i];
-    }
+  if (live) {
+    const int fill = (first == INT_MAX) ? 0 : first;  // tf_grouping_g.cu:26-29; empty ball -> zero row
+    for (int l = total + warp; l < nsample; l += kSeg) row[l] = fill;
+    if (warp == 0) pts_cnt[(size_t)scene * m + q] = total;
   }
 }
 
@@ -107,14 +167,6 @@ float ball_threshold(float radius) {
   return s;
 }
 
-template <int QW>
-int launch(int b, int n, int m, float s_star, int nsample, const float *xyz1, const float *xyz2, int *idx,
-           int *pts_cnt, cudaStream_t st) {
-  dim3 grid((m + kWarps * QW - 1) / (kWarps * QW), b);
-  ball_query_kernel<QW><<<grid, kWarps * 32, 0, st>>>(n, m, s_star, nsample, xyz1, xyz2, idx, pts_cnt);
-  PC_RETURN_LAUNCH_STATUS();
-}
-
 }  // namespace
 }  // namespace pc
 
@@ -127,10 +179,9 @@ extern "C" int pc_query_ball(int b, int n, int m, float radius, int nsample, con
   if (b > 65535) return PC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const float s_star = pc::ball_threshold(radius);
-  // Enough warps to cover the chip first, then amortise candidate loads over more queries per warp.
-  const long warps4 = (long)b * ((m + 3) / 4);
-  const long target = (long)pc::num_sms() * 16;
-  if (warps4 >= target) return pc::launch<4>(b, n, m, s_star, nsample, xyz1, xyz2, idx, pts_cnt, st);
-  if (warps4 * 2 >= target) return pc::launch<2>(b, n, m, s_star, nsample, xyz1, xyz2, idx, pts_cnt, st);
-  return pc::launch<1>(b, n, m, s_star, nsample, xyz1, xyz2, idx, pts_cnt, st);
+  const size_t smem = sizeof(pc::BallSmem);
+  PC_CUDA_TRY(pc::allow_smem(pc::ball_query_kernel, smem));
+  dim3 grid((m + 31) / 32, b);
+  pc::ball_query_kernel<<<grid, pc::kSeg * 32, smem, st>>>(n, m, s_star, nsample, 1.0f, xyz1, xyz2, idx, pts_cnt);
+  PC_RETURN_LAUNCH_STATUS();
 }

@@ -33,6 +33,43 @@ __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx,
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE fp32 results per lane per instruction) ----
+// Used by the pair-test-heavy kernels (FPS, ball query, three_nn, kNN) to halve their FP-pipe instruction count while
+// keeping every operation individually rounded.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// under --fmad=false, so the un-fused add is spelled fma(a, 1, b) with the 1 held in a register ptxas cannot see
+// through (a kernel argument): round(a*1 + b) == round(a + b) exactly, and a product can never be folded into the
+// multiplicand or the addend of an existing fma.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// Two squared distances at once, (dx*dx + dy*dy) + dz*dz per half, every step rounded on its own.
+// `one2` must be pack2(one, one) with `one` == 1.0f coming from a kernel argument.
+__device__ __forceinline__ f32x2 sqdist3_x2(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by, f32x2 bz, f32x2 one2) {
+  const f32x2 dx = sub2(ax, bx), dy = sub2(ay, by), dz = sub2(az, bz);
+  return fma2(fma2(mul2(dx, dx), one2, mul2(dy, dy)), one2, mul2(dz, dz));
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;

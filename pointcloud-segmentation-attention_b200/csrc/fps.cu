@@ -6,30 +6,57 @@
 // smallest (k mod 512, k) -- what the reference's 512-thread strided partition and left-biased tree produce.
 //
 // Design (not the reference's): one scene's whole state lives ON CHIP.  Each thread owns P points in registers
-// (xyz + running min-distance = 4P registers), a copy of xyz sits in shared memory only to broadcast the chosen
-// centre.  A round is: P distance updates per thread -> redux.sync max over the value bits (non-negative floats
+// (xyz as packed fp32x2 pairs + running min-distance = 4P registers), a copy of xyz sits in shared memory only to
+// broadcast the chosen centre.  A round is: P/2 packed distance updates per thread (FADD2/FMUL2/FFMA2, two points per
+// instruction, each operation still rounded on its own) -> redux.sync max over the value bits (non-negative floats
 // order like ints) -> one shared-memory hop across warps -> only threads holding the maximal value compute their
-// tie-break key and atomicMin it.  Two barriers per round instead of the reference's ten, no global traffic at all
-// inside the m-1 dependent rounds.
+// tie-break key and atomicMin it.  Two barriers per round instead of the reference's ten (none when the scene fits
+// one warp), no global traffic at all inside the m-1 dependent rounds.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace pc {
 namespace {
 
-constexpr int kMaxRegPoints = 8192;  // T=1024 threads x P=8 points
+constexpr int kMaxRegPoints = 8192;  // T=256 threads x P=32 points (4 registers per point)
 
 __device__ __forceinline__ int tie_key(int k) { return ((k & 511) << 22) | (k >> 9); }
 __device__ __forceinline__ int tie_key_to_index(int t) { return ((t & 0x3fffff) << 9) | (t >> 22); }
 
-// One CTA per scene (grid-stride over scenes), blockDim.x = T threads, thread owns points tid + i*T.
-template <int P>
-__global__ void __launch_bounds__(1024, 1)
-fps_onchip_kernel(int b, int n, int m, const float *__restrict__ xyz, int *__restrict__ out) {
+// One CTA of T threads per scene (grid-stride over scenes); a thread owns P points (P even) held as P/2 packed fp32x2
+// register pairs so that one FADD2/FMUL2/FFMA2 advances two points (common.cuh: sqdist3_x2 keeps every operation
+// individually rounded).  FEW, FAT threads: the fp32 pipe needs n*8/128 cycles per round whatever the shape, but the
+// per-round tail (two reductions, two barriers) is paid per warp, so 8192 points run as 8 warps x 32 points per thread.
+//
+// Point <-> thread mapping.  The reference's tie-break order is (k mod 512, k).  Thread `tid` owns the residues
+// tid, tid+T, ... (mod 512) -- R = 512/T of them -- and within a residue every 512th point:
+//     local slot i = r*A + a  <->  k = tid + T*r + 512*a      (A = P/R points per residue)
+// so a thread's slots are in ascending tie-break order and "first slot at the maximum" is its best candidate.  With
+// that, the winner scan after the block maximum is known costs 1 compare per group of 8 slots plus 8 compares
+// inside the first matching group, instead of P key computations.  (Scenes of at most 512 points: key order is k
+// order and the plain mapping k = tid + T*i is the same thing.)
+template <int P, int T>
+struct FpsMap {
+  static constexpr int R = (T >= 512) ? 1 : ((512 / T < P) ? 512 / T : P);  // residues per thread
+  static constexpr int A = P / R;
+  __device__ static __forceinline__ int k_of(int tid, int i) { return tid + T * (i / A) + (R * T) * (i % A); }
+};
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out) {
   extern __shared__ float s_xyz[];  // n*3
-  __shared__ int s_wmax[32];
-  __shared__ int s_tb[2];
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  __shared__ int s_wmax[2][32];     // per-warp maxima, double-buffered by round parity
+  __shared__ int s_tb[2];           // winning tie-break key, double-buffered by round parity
+  using Map = FpsMap<P, T>;
+  static_assert(P % 2 == 0 && T % 32 == 0 && (T >= 512 || P % Map::R == 0), "bad FPS shape");
+  constexpr int H = P / 2;
+  constexpr int G = (P < 8) ? P : 8;  // slots per group
+  constexpr int NG = P / G;
+  constexpr int nwarps = T / 32;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const f32x2 one2 = pack2(one, one);
 
   for (int scene = blockIdx.x; scene < b; scene += gridDim.x) {
     const float *p = xyz + (size_t)scene * n * 3;
@@ -39,46 +66,77 @@ fps_onchip_kernel(int b, int n, int m, const float *__restrict__ xyz, int *__res
     if (tid == 0) { s_tb[0] = INT_MAX; s_tb[1] = INT_MAX; o[0] = 0; }
     __syncthreads();
 
-    float px[P], py[P], pz[P], td[P];
+    f32x2 px[H], py[H], pz[H];
+    float td[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-      int k = tid + i * T;
-      if (k < n) {
-        px[i] = s_xyz[k * 3 + 0]; py[i] = s_xyz[k * 3 + 1]; pz[i] = s_xyz[k * 3 + 2];
-        td[i] = 1e38f;
-      } else {  // padding never wins: real values are >= 0
-        px[i] = py[i] = pz[i] = 0.0f;
-        td[i] = -1.0f;
+    for (int h = 0; h < H; ++h) {
+      float x[2], y[2], z[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * h + e, k = Map::k_of(tid, i);
+        if (k < n) {
+          x[e] = s_xyz[k * 3 + 0]; y[e] = s_xyz[k * 3 + 1]; z[e] = s_xyz[k * 3 + 2];
+          td[i] = 1e38f;
+        } else {  // padding never wins: real values are >= 0
+          x[e] = y[e] = z[e] = 0.0f;
+          td[i] = -1.0f;
+        }
       }
+      px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]);
     }
 
     int old = 0;
+    int *wslot = &s_wmax[1][warp];          // slot this warp's lane 0 writes in round j (parity j&1), j starts at 1
+    const int *rslot = &s_wmax[1][lane < nwarps ? lane : 0];
+    int par = 1;
     for (int j = 1; j < m; ++j) {
       const float cx = s_xyz[old * 3 + 0], cy = s_xyz[old * 3 + 1], cz = s_xyz[old * 3 + 2];
-      float vmax = -1.0f;
+      const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz);
+      float gm[NG];
 #pragma unroll
-      for (int i = 0; i < P; ++i) {
-        float d = sqdist3(px[i], py[i], pz[i], cx, cy, cz);
-        td[i] = fminf(d, td[i]);
-        vmax = fmaxf(vmax, td[i]);
+      for (int g = 0; g < NG; ++g) {
+        gm[g] = -1.0f;
+#pragma unroll
+        for (int h = g * G / 2; h < (g + 1) * G / 2; ++h) {
+          float d0, d1;
+          unpack2(sqdist3_x2(px[h], py[h], pz[h], cx2, cy2, cz2, one2), d0, d1);
+          td[2 * h] = fminf(d0, td[2 * h]);
+          td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+          gm[g] = fmaxf(gm[g], fmaxf(td[2 * h], td[2 * h + 1]));
+        }
       }
+      float vmax = gm[0];
+#pragma unroll
+      for (int g = 1; g < NG; ++g) vmax = fmaxf(vmax, gm[g]);
       const int vb = __float_as_int(vmax);
-      const int wmax = __reduce_max_sync(PC_FULL_MASK, vb);
-      if (lane == 0) s_wmax[warp] = wmax;
-      __syncthreads();
-      const int g = (lane < nwarps) ? s_wmax[lane] : INT_MIN;
-      const int gmax = __reduce_max_sync(PC_FULL_MASK, g);
-      const int slot = j & 1;
-      if (vb == gmax) {  // rare: this thread owns a point at the maximum
-        int tb = INT_MAX;
-#pragma unroll
-        for (int i = 0; i < P; ++i)
-          if (__float_as_int(td[i]) == gmax) tb = min(tb, tie_key(tid + i * T));
-        atomicMin(&s_tb[slot], tb);
+      int gmax = __reduce_max_sync(PC_FULL_MASK, vb);
+      if (nwarps > 1) {
+        if (lane == 0) *wslot = gmax;
+        __syncthreads();
+        gmax = __reduce_max_sync(PC_FULL_MASK, *rslot);  // lanes >= nwarps re-read slot 0: harmless for a max
       }
-      if (tid == 0) s_tb[slot ^ 1] = INT_MAX;
-      __syncthreads();
-      old = tie_key_to_index(s_tb[slot]);
+      int tb = INT_MAX;
+      if (vb == gmax) {  // rare: this thread owns a point at the maximum; its first such slot is its best candidate
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (tb == INT_MAX && __float_as_int(gm[g]) == gmax) {
+#pragma unroll
+            for (int e = G - 1; e >= 0; --e)
+              if (__float_as_int(td[g * G + e]) == gmax) tb = tie_key(Map::k_of(tid, g * G + e));
+          }
+        }
+      }
+      if (nwarps > 1) {
+        if (vb == gmax) atomicMin(&s_tb[par], tb);
+        if (tid == 0) s_tb[par ^ 1] = INT_MAX;  // next round's slot; nobody touches it before the next barrier pair
+        __syncthreads();
+        old = tie_key_to_index(s_tb[par]);
+        par ^= 1;
+        wslot += par ? 32 : -32;
+        rslot += par ? 32 : -32;
+      } else {  // a single warp: no shared-memory hop, no barrier
+        old = tie_key_to_index(__reduce_min_sync(PC_FULL_MASK, tb));
+      }
       if (tid == 0) o[j] = old;
     }
   }
@@ -133,12 +191,12 @@ fps_stream_kernel(int b, int n, int m, const float *__restrict__ xyz, float *__r
   }
 }
 
-template <int P>
-int launch_onchip(int b, int n, int m, int T, const float *xyz, int *out, cudaStream_t st) {
+template <int P, int T>
+int launch_onchip(int b, int n, int m, const float *xyz, int *out, cudaStream_t st) {
   size_t smem = (size_t)n * 3 * sizeof(float);
-  if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(fps_onchip_kernel<P>, smem));
+  if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(fps_onchip_kernel<P, T>, smem));
   int grid = b;  // one CTA per scene; more scenes than SMs simply queue (1 CTA/SM resident)
-  fps_onchip_kernel<P><<<grid, T, smem, st>>>(b, n, m, xyz, out);
+  fps_onchip_kernel<P, T><<<grid, T, smem, st>>>(b, n, m, 1.0f, xyz, out);
   PC_RETURN_LAUNCH_STATUS();
 }
 
@@ -158,14 +216,20 @@ extern "C" int pc_fps(int b, int n, int m, const float *xyz, void *workspace, in
   if (!xyz || !out_idx) return PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= pc::kMaxRegPoints) {
-    // ~4 points per thread until the CTA is full, then more points per thread.
-    int T = ((n + 3) / 4 + 31) / 32 * 32;
-    if (T > 1024) T = 1024;
-    int P = (n + T - 1) / T;
-    if (P <= 1) return pc::launch_onchip<1>(b, n, m, T, xyz, out_idx, st);
-    if (P <= 2) return pc::launch_onchip<2>(b, n, m, T, xyz, out_idx, st);
-    if (P <= 4) return pc::launch_onchip<4>(b, n, m, T, xyz, out_idx, st);
-    return pc::launch_onchip<8>(b, n, m, T, xyz, out_idx, st);
+    // Few, fat threads (see the kernel comment).  n <= 256 runs in ONE warp (no barrier at all); up to 4096 points
+    // take 4 warps (one per SM sub-partition); beyond that 8 warps x 32 points per thread.
+    if (n <= 64) return pc::launch_onchip<2, 32>(b, n, m, xyz, out_idx, st);
+    if (n <= 128) return pc::launch_onchip<4, 32>(b, n, m, xyz, out_idx, st);
+    if (n <= 256) return pc::launch_onchip<8, 32>(b, n, m, xyz, out_idx, st);
+    if (n <= 512) return pc::launch_onchip<4, 128>(b, n, m, xyz, out_idx, st);
+    if (n <= 1024) return pc::launch_onchip<8, 128>(b, n, m, xyz, out_idx, st);
+    if (n <= 2048) return pc::launch_onchip<16, 128>(b, n, m, xyz, out_idx, st);
+    if (n <= 4096) return pc::launch_onchip<32, 128>(b, n, m, xyz, out_idx, st);
+    static int shape = -1;  // development knob: PCOPS_FPS_SHAPE=512 selects 16 warps x 16 points
+    if (shape < 0) { const char *e = getenv("PCOPS_FPS_SHAPE"); shape = e ? atoi(e) : 256; }
+    if (shape == 512) return pc::launch_onchip<16, 512>(b, n, m, xyz, out_idx, st);
+    if (shape == 1024) return pc::launch_onchip<8, 1024>(b, n, m, xyz, out_idx, st);
+    return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, st);
   }
   if (!workspace) return PC_ERR_WORKSPACE;
   pc::fps_stream_kernel<<<b, 1024, 0, st>>>(b, n, m, xyz, (float *)workspace, out_idx);

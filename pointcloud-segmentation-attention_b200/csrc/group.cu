@@ -10,16 +10,34 @@
 namespace pc {
 namespace {
 
-// c % 4 == 0 and 16-byte aligned bases: one float4 per thread.
+// c % 4 == 0 and 16-byte aligned bases: one float4 per element, four independent gathers in flight per thread
+// (index loads first, then the four row loads, then the four coalesced 128-bit stores).
+constexpr int kGroupUnroll = 4;
 __global__ void __launch_bounds__(256)
 group_vec4_kernel(size_t total_vec, int c4, size_t rows_per_scene, size_t src_rows_per_scene,
                   const float4 *__restrict__ points, const int *__restrict__ idx, float4 *__restrict__ out) {
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total_vec; v += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = v / c4;
-    const int q = (int)(v - row * c4);
-    const size_t scene = row / rows_per_scene;
-    const int src = __ldg(idx + row);
-    out[v] = __ldg(points + (scene * src_rows_per_scene + src) * c4 + q);
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < total_vec; v0 += step * kGroupUnroll) {
+    const float4 *src[kGroupUnroll];
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u) {
+      const size_t v = v0 + u * step;
+      src[u] = points;
+      if (v < total_vec) {
+        const size_t row = v / c4;
+        const int q = (int)(v - row * c4);
+        const size_t scene = row / rows_per_scene;
+        src[u] = points + (scene * src_rows_per_scene + __ldg(idx + row)) * c4 + q;
+      }
+    }
+    float4 val[kGroupUnroll];
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u) val[u] = __ldg(src[u]);
+#pragma unroll
+    for (int u = 0; u < kGroupUnroll; ++u) {
+      const size_t v = v0 + u * step;
+      if (v < total_vec) __stcs(out + v, val[u]);  // streaming store: the grouped tensor is consumed by a later kernel
+    }
   }
 }
 
@@ -63,8 +81,8 @@ int gather_rows(size_t scenes, size_t src_rows, size_t rows, int c, const float 
   const int sms = num_sms();
   if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
     const size_t nv = total / 4;
-    size_t blocks = (nv + 255) / 256;
-    if (blocks > (size_t)sms * 64) blocks = (size_t)sms * 64;
+    size_t blocks = (nv + 256 * kGroupUnroll - 1) / (256 * kGroupUnroll);
+    if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
     group_vec4_kernel<<<(unsigned)blocks, 256, 0, st>>>(nv, c / 4, rows, src_rows, (const float4 *)points, idx,
                                                          (float4 *)out);
   } else {

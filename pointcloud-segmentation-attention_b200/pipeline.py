@@ -14,9 +14,14 @@ The shared MLPs / Dense projections between those calls are stock dense layers a
 would produce (per-level point features, and Q/K/V of each attention level) are fixed synthetic stand-ins of the
 right shape, resident in HBM.  Because of that, an FP level's ops are issued as soon as the xyz they depend on exists.
 
-Two streams: the four FPS calls form a strictly sequential chain (level l+1 samples level l's centroids) on the
-main stream; everything else runs on a side stream behind per-level events, so grouping / interpolation / attention of
-level l overlap FPS of level l+1.  The sequence is CUDA-graph capturable (no allocation, no host sync inside).
+Streams: the four FPS calls form a strictly sequential chain (level l+1 samples level l's centroids) on the main
+stream (high priority: FPS is latency-bound and occupies only B SMs); everything else of level l runs on side stream l
+behind a per-level event, so grouping / interpolation / attention of all levels overlap each other and the FPS chain.
+The sequence is CUDA-graph capturable (no allocation, no host sync inside).  Independent batches overlap further by
+running several ``ScanNetGeometry`` instances, each on its own streams (bench.py --depth).
+
+All integer / distance results a host consumer reads back (FPS, ball and three_nn indices, counts, three_nn distances)
+are views into ONE contiguous device buffer, so a step's result is a single device-to-host copy.
 """
 import ctypes
 
@@ -30,11 +35,26 @@ KEY_DIM = 4  # attention_layer.py:256-258: heads = C // 4, key_dim = output_dim 
 
 
 class ScanNetGeometry:
-    def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0):
+    def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0, own_streams=False):
         self.B, self.N, self.CF = batch, npoints, feat_channels
         self.dev = torch.device(device)
         self.attention = attention
         self.L = _lib.lib()
+        # result arena: every tensor of result_tensors() is a view into it (4-byte elements, 16-byte aligned slots)
+        sizes, n_ = [], npoints
+        for (m_, _r, ns_, _c) in SA_LEVELS:
+            sizes += [batch * m_, batch * m_ * ns_, batch * m_, batch * n_ * 3, batch * n_ * 3]
+            n_ = m_
+        self._arena = torch.empty(sum((x + 3) // 4 * 4 for x in sizes), dtype=torch.int32, device=self.dev)
+        self._arena_off = 0
+
+        def res(shape, dtype):
+            numel = 1
+            for d in shape:
+                numel *= d
+            v = self._arena[self._arena_off:self._arena_off + numel]
+            self._arena_off += (numel + 3) // 4 * 4
+            return v.view(dtype).view(*shape)
         f32, i32 = torch.float32, torch.int32
         dev = self.dev
         g = torch.Generator(device=dev).manual_seed(seed)
@@ -50,10 +70,10 @@ class ScanNetGeometry:
         for (m, r, ns, cout) in SA_LEVELS:
             lv = dict(n=n, m=m, r=r, ns=ns, cin=cin, cout=cout, xyz=xyz)
             lv["feat"] = self.feat0 if n == npoints else rnd(batch, n, cin)  # stand-in for the previous level's MLP output
-            lv["fps_idx"] = torch.empty((batch, m), dtype=i32, device=dev)
+            lv["fps_idx"] = res((batch, m), i32)
             lv["new_xyz"] = torch.empty((batch, m, 3), dtype=f32, device=dev)
-            lv["idx"] = torch.empty((batch, m, ns), dtype=i32, device=dev)
-            lv["cnt"] = torch.empty((batch, m), dtype=i32, device=dev)
+            lv["idx"] = res((batch, m, ns), i32)
+            lv["cnt"] = res((batch, m), i32)
             lv["gxyz"] = torch.empty((batch, m, ns, 3), dtype=f32, device=dev)
             lv["gfeat"] = torch.empty((batch, m, ns, cin), dtype=f32, device=dev)
             if attention:  # stand-ins for the Dense projections of the level's (B,m,ns,cout) activations
@@ -72,32 +92,48 @@ class ScanNetGeometry:
             lv = self.levels[li]
             fp = dict(n=lv["n"], m=lv["m"], c=c, xyz1=lv["xyz"], xyz2=lv["new_xyz"], level=li)
             fp["points2"] = rnd(batch, lv["m"], c)  # stand-in for the deeper level's features
-            fp["dist"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
-            fp["idx"] = torch.empty((batch, lv["n"], 3), dtype=i32, device=dev)
+            fp["dist"] = res((batch, lv["n"], 3), f32)
+            fp["idx"] = res((batch, lv["n"], 3), i32)
             fp["w"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
             fp["out"] = torch.empty((batch, lv["n"], c), dtype=f32, device=dev)
             self.fps.append(fp)
-        self.side = torch.cuda.Stream(device=dev)
+        self.main = torch.cuda.Stream(device=dev, priority=-1) if own_streams else None
+        self.sides = [torch.cuda.Stream(device=dev) for _ in self.levels]
+        self.side = self.sides[0]
         self.launches_per_step = len(self.levels) * (6 if attention else 5) + len(self.fps) * 3
         self._graph = None
 
     # ---- inputs / outputs ----------------------------------------------------------------------------------
     def set_inputs(self, xyz, feats, non_blocking=True):
-        self.xyz0.copy_(xyz, non_blocking=non_blocking)
-        self.feat0.copy_(feats, non_blocking=non_blocking)
+        """Copy a batch (device or pinned host tensors) into the input buffers, on this pipeline's stream."""
+        with torch.cuda.stream(self.stream()):
+            self.xyz0.copy_(xyz, non_blocking=non_blocking)
+            self.feat0.copy_(feats, non_blocking=non_blocking)
+
+    def read_results(self, host_arena, non_blocking=True):
+        """One device-to-host copy of the result arena into a pinned int32 host tensor, on this pipeline's stream."""
+        with torch.cuda.stream(self.stream()):
+            host_arena.copy_(self.result_arena(), non_blocking=non_blocking)
 
     def input_bytes(self):
         return self.xyz0.numel() * 4 + self.feat0.numel() * 4
 
     def result_tensors(self):
-        """The integer geometry decisions of a forward (what a host-side consumer can check): FPS indices, ball
-        indices and counts per SA level, three_nn indices per FP level."""
+        """The geometry decisions of a forward (what a host-side consumer reads back): FPS indices, ball indices and
+        counts per SA level, three_nn indices and squared distances per FP level."""
         out = []
         for lv in self.levels:
             out += [lv["fps_idx"], lv["idx"], lv["cnt"]]
         for fp in self.fps:
-            out.append(fp["idx"])
+            out += [fp["idx"], fp["dist"]]
         return out
+
+    def result_arena(self):
+        """The one contiguous int32 device buffer all result_tensors() live in (floats are bit-views)."""
+        return self._arena[:self._arena_off]
+
+    def stream(self):
+        return self.main if self.main is not None else torch.cuda.current_stream(self.dev)
 
     # ---- one forward -----------------------------------------------------------------------------------------
     def _sa_rest(self, lv, li, side, run):
@@ -131,8 +167,7 @@ class ScanNetGeometry:
         ``probes``: optional dict name -> list; for every op whose name is a key, a (start, end) pair of CUDA events
         recorded on the op's own stream around its launch is appended (bench.py reads kernel durations from them)."""
         L, B, p = self.L, self.B, _lib.ptr
-        main = torch.cuda.current_stream(self.dev)
-        side = self.side if overlap else main
+        main = self.stream()
         s_main = ctypes.c_void_p(main.cuda_stream)
         fp_of = {fp["level"]: fp for fp in self.fps}
 
@@ -146,21 +181,19 @@ class ScanNetGeometry:
             else:
                 _c(call())
 
-        if overlap:
-            side.wait_stream(main)
         for li, lv in enumerate(self.levels):
+            side = self.sides[li] if overlap else main
             run("fps_sa%d" % (li + 1), main, lambda: L.pc_fps(
                 B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), s_main))
             run("gather_sa%d" % (li + 1), main, lambda: L.pc_gather_point(
                 B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
             if overlap:
-                ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
+                side.wait_stream(main)  # also orders this step's side work after the previous step's join
             self._sa_rest(lv, li, side, run)
             self._fp(fp_of[li], side, run)
         if overlap:
-            main.wait_stream(side)
+            for side in self.sides:
+                main.wait_stream(side)
 
     def op_names(self):
         names = []
@@ -201,13 +234,19 @@ class ScanNetGeometry:
         self.forward(overlap)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.forward(overlap)
+        saved, self.main = self.main, None  # inside the capture the capture stream plays the role of main
+        try:
+            with torch.cuda.graph(g, stream=saved):
+                self.forward(overlap)
+        finally:
+            self.main = saved
         self._graph = g
         return g
 
     def replay(self):
-        self._graph.replay()
+        """Launch the captured forward on this pipeline's stream."""
+        with torch.cuda.stream(self.stream()):
+            self._graph.replay()
 
 
 def _c(rc):

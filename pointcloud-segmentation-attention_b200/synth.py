@@ -1,5 +1,5 @@
 """Seeded synthetic ScanNet-shaped workloads: the inputs bench.py, smoke() and the tests feed to
-the CUDA path -- and, through the re-export in oracle/synth.py, to the CPU oracle, so both sides consume identical bytes.
+the CUDA path; the CPU checker re-exports this very file, so both sides consume identical bytes.
 
 Pure numpy; no reference files are read; nothing here computes any op result.
 

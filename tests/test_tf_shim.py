@@ -1,0 +1,57 @@
+"""The TensorFlow op shim (integration/tf_shim) must parse as C++ against the C ABI and re-register exactly the op
+names / attrs / inputs / outputs of the reference's three custom-op libraries (tf_sampling.cpp:14-63,
+tf_grouping.cpp:13-63, tf_interpolate.cpp:12-46), so the reference's Python wrappers load it unchanged."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "integration", "tf_shim")
+
+# op -> (attrs, inputs, outputs) as registered by the reference
+REFERENCE_REGISTRY = {
+    "FarthestPointSample": (["npoint: int"], ["inp: float32"], ["out: int32"]),
+    "GatherPoint": ([], ["inp: float32", "idx: int32"], ["out: float32"]),
+    "GatherPointGrad": ([], ["inp: float32", "idx: int32", "out_g: float32"], ["inp_g: float32"]),
+    "QueryBallPoint": (["radius: float", "nsample: int"], ["xyz1: float32", "xyz2: float32"],
+                       ["idx: int32", "pts_cnt: int32"]),
+    "SelectionSort": (["k: int"], ["dist: float32"], ["outi: int32", "out: float32"]),
+    "GroupPoint": ([], ["points: float32", "idx: int32"], ["out: float32"]),
+    "GroupPointGrad": ([], ["points: float32", "idx: int32", "grad_out: float32"], ["grad_points: float32"]),
+    "ThreeNN": ([], ["xyz1: float32", "xyz2: float32"], ["dist: float32", "idx: int32"]),
+    "ThreeInterpolate": ([], ["points: float32", "idx: int32", "weight: float32"], ["out: float32"]),
+    "ThreeInterpolateGrad": ([], ["points: float32", "idx: int32", "weight: float32", "grad_out: float32"],
+                             ["grad_points: float32"]),
+}
+
+
+def parse_registry():
+    reg = {}
+    for f in ("sampling_ops.cc", "grouping_ops.cc", "interpolation_ops.cc"):
+        text = open(os.path.join(SHIM, f)).read()
+        for m in re.finditer(r'REGISTER_OP\("(\w+)"\)(.*?)\.SetShapeFn', text, re.S):
+            body = m.group(2)
+            reg[m.group(1)] = (re.findall(r'\.Attr\("([^"]+)"\)', body), re.findall(r'\.Input\("([^"]+)"\)', body),
+                               re.findall(r'\.Output\("([^"]+)"\)', body))
+        for op in re.findall(r'REGISTER_KERNEL_BUILDER\(Name\("(\w+)"\)\.Device\(DEVICE_GPU\)', text):
+            assert op in reg, op
+    return reg
+
+
+def test_shim_registers_the_reference_ops_exactly():
+    assert parse_registry() == REFERENCE_REGISTRY
+
+
+def test_every_registered_op_has_a_gpu_kernel_calling_the_c_abi():
+    text = "".join(open(os.path.join(SHIM, f)).read() for f in ("sampling_ops.cc", "grouping_ops.cc", "interpolation_ops.cc"))
+    kernels = set(re.findall(r'REGISTER_KERNEL_BUILDER\(Name\("(\w+)"\)\.Device\(DEVICE_GPU\)', text))
+    assert kernels == set(REFERENCE_REGISTRY)
+    for fn in ("pc_fps", "pc_gather_point", "pc_gather_point_grad", "pc_query_ball", "pc_selection_sort", "pc_group_point",
+               "pc_group_point_grad", "pc_three_nn", "pc_three_interpolate", "pc_three_interpolate_grad"):
+        assert re.search(r"\b%s\(" % fn, text), fn
+
+
+def test_shim_parses_against_the_c_abi_header():
+    out = subprocess.run(["sh", os.path.join(SHIM, "check.sh")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.count("ok:") == 3
