@@ -384,9 +384,9 @@ def main():
     rooflines, op_ms = {}, {}
     if not args.skip_probe:
         allp = {n: [] for n in pipe.op_names()}
-        for i in range(min(K, 10)):      # one pipeline instance alone, eager: per-op durations without cross-step overlap
+        for i in range(min(K, 10)):      # one pipeline instance alone, eager, ONE stream: every op's stand-alone duration
             pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
-            pipe.forward(overlap, allp)
+            pipe.forward(False, allp)
             torch.cuda.synchronize(dev)
         for n, evs in allp.items():
             d = sorted(a.elapsed_time(b) for a, b in evs)
@@ -400,7 +400,7 @@ def main():
     roofline = roof(top_guess, top_ms)
     roofline["share_of_step"] = top_ms / sum(op_ms.values()) if op_ms else None
     roofline["timed"] = "CUDA events around each launch on its stream, inside the value region (mean of %d)" % K \
-        if probes else "CUDA events around each launch on its stream in a probed eager pass right after the value " \
+        if probes else "CUDA events around each launch in a probed single-stream eager pass right after the value " \
                        "region (graph replay hides single launches); share = its time / sum of all op times"
 
     if rank != 0:

@@ -18,7 +18,6 @@
 namespace pc {
 namespace {
 
-constexpr int kNNThreads = 256;
 constexpr int kNNTile = 2048;  // known points per tile: 3 SoA rows of 2048 floats = 24 KB
 
 // 3-slot insertion of tf_interpolate.cpp:74-89 (strict '<': equal distances keep ascending index order).
@@ -35,31 +34,46 @@ __device__ __forceinline__ void nn_insert(float d, int kk, float &b1, float &b2,
 }
 
 // One thread per dense point.  The known cloud is staged SoA in shared memory so one LDS.128 broadcast feeds four
-// candidates as two packed fp32x2 operands; four distances cost 16 packed FP instructions, and only when the smallest
-// of the four beats the current third-best does the thread enter the (in-order, exact) insertion cascade.
+// candidates as two packed fp32x2 operands.  The scan is a branch-free FILTER: for every word of 32 candidates a thread
+// only records, as one bit per candidate, whether the distance beats its third-best AT THE START of the word (sign of
+// an integer subtract funnel-shifted into the word -- non-negative floats order like their bit patterns).  The exact
+// 3-slot insertion then runs only for the recorded candidates, in ascending index, recomputing the distance with the
+// same un-fused arithmetic.  A candidate that fails the stale test can never enter the list (the third-best only
+// shrinks), so the result is the reference's sequential scan exactly, while 32 lanes no longer serialise on a branch
+// that some lane takes at almost every step (a top-3 list changes ~3 ln m times per lane).
+// Q dense points per thread: one broadcast LDS.128 then feeds 4 candidates x Q queries (a broadcast LDS.128 still
+// occupies the shared-memory crossbar for 4 cycles per warp, which bounds a Q = 1 scan before the fp32 pipe does).
+template <int Q, int kNNThreads>
 __global__ void __launch_bounds__(kNNThreads)
 three_nn_kernel(int n, int m, float one, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                 float *__restrict__ dist, int *__restrict__ idx) {
   __shared__ __align__(16) float tile[3][kNNTile];
   const int scene = blockIdx.y;
-  const int j = blockIdx.x * kNNThreads + threadIdx.x;
-  const bool live = j < n;
-  const float *qp = xyz1 + ((size_t)scene * n + (live ? j : 0)) * 3;
-  const float x1 = qp[0], y1 = qp[1], z1 = qp[2];
-  const f32x2 qx2 = pack2(x1, x1), qy2 = pack2(y1, y1), qz2 = pack2(z1, z1), one2 = pack2(one, one);
   const float *known = xyz2 + (size_t)scene * m * 3;
   const float inf = __int_as_float(0x7f800000);
-  float b1 = inf, b2 = inf, b3 = inf;
-  int i1 = 0, i2 = 0, i3 = 0;
+  const f32x2 one2 = pack2(one, one);
+  int j[Q];
+  float x1[Q], y1[Q], z1[Q], b1[Q], b2[Q], b3[Q];
+  int i1[Q], i2[Q], i3[Q];
+  f32x2 qx2[Q], qy2[Q], qz2[Q];
+#pragma unroll
+  for (int u = 0; u < Q; ++u) {
+    j[u] = (blockIdx.x * Q + u) * kNNThreads + threadIdx.x;
+    const float *qp = xyz1 + ((size_t)scene * n + (j[u] < n ? j[u] : 0)) * 3;
+    x1[u] = qp[0]; y1[u] = qp[1]; z1[u] = qp[2];
+    qx2[u] = pack2(x1[u], x1[u]); qy2[u] = pack2(y1[u], y1[u]); qz2[u] = pack2(z1[u], z1[u]);
+    b1[u] = b2[u] = b3[u] = inf;
+    i1[u] = i2[u] = i3[u] = 0;
+  }
   constexpr int kLoads = kNNTile * 3 / kNNThreads;  // 24 coalesced loads per thread, all issued before the first store
   for (int t0 = 0; t0 < m; t0 += kNNTile) {
     const int tn = min(kNNTile, m - t0);
-    const int tn4 = (tn + 3) & ~3;
+    const int tn32 = (tn + 31) & ~31;
     float pre[kLoads];
 #pragma unroll
     for (int u = 0; u < kLoads; ++u) {
       const int i = threadIdx.x + kNNThreads * u;
-      pre[u] = (i < tn * 3) ? __ldg(known + (size_t)t0 * 3 + i) : inf;  // slots past tn: +inf, never inserted
+      pre[u] = (i < tn * 3) ? __ldg(known + (size_t)t0 * 3 + i) : inf;  // slots past tn: +inf, never below any b3
     }
     __syncthreads();
 #pragma unroll
@@ -68,29 +82,55 @@ three_nn_kernel(int n, int m, float one, const float *__restrict__ xyz1, const f
       tile[c][k] = pre[u];
     }
     __syncthreads();
-#pragma unroll 2
-    for (int k = 0; k < tn4; k += 4) {
-      const float4 xs = *reinterpret_cast<const float4 *>(&tile[0][k]);
-      const float4 ys = *reinterpret_cast<const float4 *>(&tile[1][k]);
-      const float4 zs = *reinterpret_cast<const float4 *>(&tile[2][k]);
-      float d0, d1, d2, d3;
-      // candidate minus query, as tf_interpolate.cpp:73 writes it
-      unpack2(sqdist3_x2(pack2(xs.x, xs.y), pack2(ys.x, ys.y), pack2(zs.x, zs.y), qx2, qy2, qz2, one2), d0, d1);
-      unpack2(sqdist3_x2(pack2(xs.z, xs.w), pack2(ys.z, ys.w), pack2(zs.z, zs.w), qx2, qy2, qz2, one2), d2, d3);
-      if (fminf(fminf(d0, d1), fminf(d2, d3)) < b3) {
-        const int kk = t0 + k;
-        nn_insert(d0, kk, b1, b2, b3, i1, i2, i3);
-        nn_insert(d1, kk + 1, b1, b2, b3, i1, i2, i3);
-        nn_insert(d2, kk + 2, b1, b2, b3, i1, i2, i3);
-        nn_insert(d3, kk + 3, b1, b2, b3, i1, i2, i3);
+    for (int w0 = 0; w0 < tn32; w0 += 32) {
+      int thr[Q];
+      unsigned word[Q];
+#pragma unroll
+      for (int u = 0; u < Q; ++u) {
+        thr[u] = __float_as_int(b3[u]);  // stale third-best for this word; +inf admits every finite distance
+        word[u] = 0;
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int k = w0 + g * 4;
+        const float4 xs = *reinterpret_cast<const float4 *>(&tile[0][k]);
+        const float4 ys = *reinterpret_cast<const float4 *>(&tile[1][k]);
+        const float4 zs = *reinterpret_cast<const float4 *>(&tile[2][k]);
+        const f32x2 xa = pack2(xs.x, xs.y), ya = pack2(ys.x, ys.y), za = pack2(zs.x, zs.y);
+        const f32x2 xb = pack2(xs.z, xs.w), yb = pack2(ys.z, ys.w), zb = pack2(zs.z, zs.w);
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+          float d0, d1, d2, d3;
+          // candidate minus query, as tf_interpolate.cpp:73 writes it
+          unpack2(sqdist3_x2(xa, ya, za, qx2[u], qy2[u], qz2[u], one2), d0, d1);
+          unpack2(sqdist3_x2(xb, yb, zb, qx2[u], qy2[u], qz2[u], one2), d2, d3);
+          word[u] = __funnelshift_l(__float_as_int(d0) - thr[u], word[u], 1);  // d < b3 <=> bits(d) - bits(b3) < 0
+          word[u] = __funnelshift_l(__float_as_int(d1) - thr[u], word[u], 1);
+          word[u] = __funnelshift_l(__float_as_int(d2) - thr[u], word[u], 1);
+          word[u] = __funnelshift_l(__float_as_int(d3) - thr[u], word[u], 1);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < Q; ++u) {
+        unsigned wd = __brev(word[u]);  // bit e <-> candidate w0 + e
+        while (wd) {                    // exact insertion of the few admitted candidates, ascending index
+          const int e = __ffs(wd) - 1;
+          wd &= wd - 1;
+          const int k = w0 + e;
+          const float d = sqdist3(tile[0][k], tile[1][k], tile[2][k], x1[u], y1[u], z1[u]);
+          nn_insert(d, t0 + k, b1[u], b2[u], b3[u], i1[u], i2[u], i3[u]);
+        }
       }
     }
   }
-  if (live) {
-    float *dp = dist + ((size_t)scene * n + j) * 3;
-    int *ip = idx + ((size_t)scene * n + j) * 3;
-    dp[0] = b1; dp[1] = b2; dp[2] = b3;
-    ip[0] = i1; ip[1] = i2; ip[2] = i3;
+#pragma unroll
+  for (int u = 0; u < Q; ++u) {
+    if (j[u] < n) {
+      float *dp = dist + ((size_t)scene * n + j[u]) * 3;
+      int *ip = idx + ((size_t)scene * n + j[u]) * 3;
+      dp[0] = b1[u]; dp[1] = b2[u]; dp[2] = b3[u];
+      ip[0] = i1[u]; ip[1] = i2[u]; ip[2] = i3[u];
+    }
   }
 }
 
@@ -165,8 +205,13 @@ extern "C" int pc_three_nn(int b, int n, int m, const float *xyz1, const float *
   if (b == 0 || n == 0) return PC_OK;
   if (!xyz1 || !dist || !idx || (m > 0 && !xyz2)) return PC_ERR_INVALID_ARGUMENT;
   if (b > 65535) return PC_ERR_UNSUPPORTED;
-  dim3 grid((n + pc::kNNThreads - 1) / pc::kNNThreads, b);
-  pc::three_nn_kernel<<<grid, pc::kNNThreads, 0, (cudaStream_t)stream>>>(n, m, 1.0f, xyz1, xyz2, dist, idx);
+  // a CTA owns 256 dense points: as 128 threads x 2 points when that still gives >= 2 CTAs per SM (halves the
+  // shared-memory broadcasts per pair test), else as 256 threads x 1 point
+  dim3 grid((n + 255) / 256, b);
+  if ((long)grid.x * b >= 2L * pc::num_sms())
+    pc::three_nn_kernel<2, 128><<<grid, 128, 0, (cudaStream_t)stream>>>(n, m, 1.0f, xyz1, xyz2, dist, idx);
+  else
+    pc::three_nn_kernel<1, 256><<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, 1.0f, xyz1, xyz2, dist, idx);
   PC_RETURN_LAUNCH_STATUS();
 }
 
