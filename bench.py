@@ -50,7 +50,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="scenes per GPU per step (the config names 16)")
     ap.add_argument("--ring", type=int, default=4, help="distinct input batches cycled through")
     ap.add_argument("--graph", type=int, default=1, help="1: replay each forward as a CUDA graph (default); 0: eager")
-    ap.add_argument("--depth", type=int, default=4, help="independent batches in flight (pipeline instances, own streams)")
+    ap.add_argument("--depth", type=int, default=8, help="independent batches in flight (pipeline instances, own streams)")
+    ap.add_argument("--attention", type=int, default=1, help="0: leave the attention contraction out (diagnostics only)")
+    ap.add_argument("--grid", type=int, default=1, help="1: cell-grid ball query / three_nn; 0: all-pairs kernels")
     ap.add_argument("--no-overlap", action="store_true", help="single stream")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -267,7 +269,8 @@ def main():
         dev_feat.append(hf.to(dev))
 
     D = max(1, args.depth)
-    pipes = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=True, seed=rank * 64 + d, own_streams=True) for d in range(D)]
+    pipes = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=bool(args.attention), seed=rank * 64 + d, own_streams=True, grid=bool(args.grid))
+             for d in range(D)]
     pipe = pipes[0]
     overlap = not args.no_overlap
     cur = torch.cuda.current_stream(dev)
@@ -318,6 +321,7 @@ def main():
         step_resident(i, probes, use_graph)
     join()
     e1.record(cur)
+    t_enq = time.time()
     torch.cuda.synchronize(dev)
     t_wall1 = time.time()
     sharding.barrier()
@@ -395,9 +399,27 @@ def main():
     if probes:
         d = [a.elapsed_time(b) for a, b in probes[top_guess]]
         top_ms = sum(d) / len(d)
-    else:
-        top_ms = op_ms.get(top_guess, float("nan"))
+    elif top_guess in op_ms:
+        top_ms = op_ms[top_guess]
+    else:                                 # --skip-probe under graph replay: time the dominant kernel alone
+        solo = {top_guess: []}
+        for i in range(5):
+            pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+            pipe.forward(False, solo)
+        torch.cuda.synchronize(dev)
+        d = sorted(a.elapsed_time(b) for a, b in solo[top_guess]) or [float("inf")]
+        top_ms = d[len(d) // 2]
     roofline = roof(top_guess, top_ms)
+    try:  # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top_guess, {})
+        if B == 16 and tr.get("bytes") is not None:
+            roofline["traffic"] = tr["bytes"]
+            roofline["traffic_source"] = tr.get("capture")
+    except Exception:
+        pass
+    roofline["algorithmic_bytes"] = work[top_guess].get("bytes")
+    roofline["occupied_sms"] = min(B, nsm)
+    roofline["frac_of_occupied_sms"] = roofline["frac"] * nsm / min(B, nsm)   # FPS runs one scene per SM
     roofline["share_of_step"] = top_ms / sum(op_ms.values()) if op_ms else None
     roofline["timed"] = "CUDA events around each launch on its stream, inside the value region (mean of %d)" % K \
         if probes else "CUDA events around each launch in a probed single-stream eager pass right after the value " \
@@ -426,17 +448,18 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / K, "host_enqueue_ms_per_step": 1e3 * (t_enq - t_wall0) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "npoints": NPOINTS, "feature_channels": 6,
                    "parallelism": "scene-sharded x%d, no collective" % world, "streams_per_batch": 5 if overlap else 1,
                    "cuda_graph": use_graph, "input_ring": R, "batches_in_flight": D,
+                   "neighbour_search": "cell grid" if args.grid else "all pairs",
                    "l2": "inputs larger than L2: one step streams >500 MB (K/V/out tensors) through a 126 MB L2; "
                          "each step reads a different batch of scenes"},
         "fps_us_per_scene": {"sa1_batch_latency_us": top_ms * 1e3, "sa1_us_per_scene_throughput": top_ms * 1e3 / B},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "result_checksum": checksum},
-        "gpu_launches": pipe.launches_per_step * K,
+        "gpu_launches": pipe.launches_per_step * K * world,
         "clocks": clocks,
         "roofline": roofline,
         "rooflines": rooflines,

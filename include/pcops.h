@@ -65,6 +65,11 @@ PC_API int pc_num_sms(void);                   /* SM count of the current device
 PC_API size_t pc_fps_workspace_bytes(int b, int n, int m);
 PC_API int pc_fps(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, pc_stream_t stream);
 
+/* farthest_point_sample + gather_point in one launch (the pair pointnet_util.py:34 always issues together):
+ * additionally writes out_xyz (b,m,3) = xyz[b, out_idx[b,j], :] when out_xyz is not NULL.  Same indices as pc_fps. */
+PC_API int pc_fps_gather(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, float *out_xyz,
+                  pc_stream_t stream);
+
 /* gather_point.  Replaces gatherpointLauncher(b,n,m,inp,idx,out) (tf_sampling_g.cu:206-208, prototype
  * tf_sampling.cpp:125; op GatherPoint tf_sampling.cpp:41-54,126-148).
  *   inp (b,n,3), idx (b,m) -> out (b,m,3);  out[b,j,:] = inp[b,idx[b,j],:] */
@@ -91,6 +96,14 @@ PC_API int pc_gather_point_grad(int b, int n, int m, const float *out_g, const i
  *   (tf_grouping.cpp:70-74). */
 PC_API int pc_query_ball(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
                   int *pts_cnt, pc_stream_t stream);
+
+/* Ball query through a per-scene cell grid: SAME outputs as pc_query_ball, bit for bit, but a query only meets the
+ * candidates of its 3x3x3 cell neighbourhood (cell edge >= radius) instead of all n.  The TF shim / wrappers call this
+ * one; it forwards to pc_query_ball for shapes the grid path does not cover (n > ~15000 points per scene).
+ * workspace: pc_query_ball_grid_workspace_bytes(b,n,m) bytes, 16-byte aligned, contents scratch. */
+PC_API size_t pc_query_ball_grid_workspace_bytes(int b, int n, int m);
+PC_API int pc_query_ball_grid(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                       int *idx, int *pts_cnt, void *workspace, pc_stream_t stream);
 
 /* group_point.  Replaces groupPointLauncher(b,n,c,m,nsample,points,idx,out) (tf_grouping_g.cu:133-136, prototype
  * tf_grouping.cpp:142; op GroupPoint tf_grouping.cpp:41-54,143-171).
@@ -129,6 +142,13 @@ PC_API int pc_knn(int b, int n, int m, int k, int c, const float *xyz1, const fl
  *   idx (b,n,3) i32; equal distances keep ascending index order; missing neighbours (m < 3) are (+inf, 0). */
 PC_API int pc_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
                 pc_stream_t stream);
+
+/* three_nn through a per-scene cell grid over the known cloud xyz2: SAME outputs as pc_three_nn, bit for bit (ties by
+ * ascending index), scanning cell rings around the query until the third-best distance is certified.
+ * workspace: pc_three_nn_grid_workspace_bytes(b,n,m) bytes, 16-byte aligned, contents scratch. */
+PC_API size_t pc_three_nn_grid_workspace_bytes(int b, int n, int m);
+PC_API int pc_three_nn_grid(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                     void *workspace, pc_stream_t stream);
 
 /* Inverse-distance weights of pointnet_fp_module (utils/pointnet_util.py:219-222, stock TF ops in the reference):
  *   d = max(dist,1e-10); w_t = (1/d_t) / ((1/d_0 + 1/d_1) + 1/d_2).   dist, weight: (rows,3). */

@@ -73,8 +73,12 @@ class QueryBallPointGpuOp : public OpKernel {
     Tensor *idx = nullptr, *cnt = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape{b, m, nsample_}, &idx));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape{b, m}, &cnt));
-    PCSHIM_CHECK_RC(ctx, pc_query_ball(b, n, m, radius_, nsample_, F(xyz1), F(xyz2), I(idx), I(cnt), PCSHIM_STREAM(ctx)),
-                    "pc_query_ball");
+    Tensor ws_t;  // per-scene cell grid (same outputs as pc_query_ball, far fewer pair tests)
+    void *ws = nullptr;
+    OP_REQUIRES_OK(ctx, scratch(ctx, pc_query_ball_grid_workspace_bytes(b, n, m), &ws_t, &ws));
+    PCSHIM_CHECK_RC(ctx,
+                    pc_query_ball_grid(b, n, m, radius_, nsample_, F(xyz1), F(xyz2), I(idx), I(cnt), ws, PCSHIM_STREAM(ctx)),
+                    "pc_query_ball_grid");
   }
 
  private:

@@ -53,7 +53,11 @@ class ThreeNNGpuOp : public OpKernel {
     Tensor *dist = nullptr, *idx = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape{b, n, 3}, &dist));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape{b, n, 3}, &idx));
-    PCSHIM_CHECK_RC(ctx, pc_three_nn(b, n, m, F(xyz1), F(xyz2), F(dist), I(idx), PCSHIM_STREAM(ctx)), "pc_three_nn");
+    Tensor ws_t;  // per-scene cell grid over the known cloud (same outputs as pc_three_nn)
+    void *ws = nullptr;
+    OP_REQUIRES_OK(ctx, scratch(ctx, pc_three_nn_grid_workspace_bytes(b, n, m), &ws_t, &ws));
+    PCSHIM_CHECK_RC(ctx, pc_three_nn_grid(b, n, m, F(xyz1), F(xyz2), F(dist), I(idx), ws, PCSHIM_STREAM(ctx)),
+                    "pc_three_nn_grid");
   }
 };
 REGISTER_KERNEL_BUILDER(Name("ThreeNN").Device(DEVICE_GPU), ThreeNNGpuOp);

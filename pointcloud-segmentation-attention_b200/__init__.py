@@ -12,7 +12,8 @@ Import with ``importlib.import_module("pointcloud-segmentation-attention_b200")`
 Everything computes in libpcops.so (include/pcops.h); there is no CPU or eager fallback.
 """
 from . import _lib  # noqa: F401
-from .tf_sampling import farthest_point_sample, gather_point, gather_point_grad, prob_sample  # noqa: F401
+from .tf_sampling import (farthest_point_sample, farthest_point_sample_and_gather, gather_point,  # noqa: F401
+                          gather_point_grad, prob_sample)
 from .tf_grouping import (group_point, group_point_grad, knn_point, query_ball_point,  # noqa: F401
                           select_top_k)
 from .tf_interpolate import (three_interpolate, three_interpolate_grad, three_nn,  # noqa: F401

@@ -26,16 +26,21 @@ SIGNATURES = {
     "pc_num_sms": (_i, []),
     "pc_fps_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_fps": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pc_fps_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_gather_point_grad_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_query_ball": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_query_ball_grid_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pc_query_ball_grid": (_i, [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_group_point": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_group_point_grad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pc_group_point_grad": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_selection_sort": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_knn": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_three_nn": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_three_nn_grid_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pc_three_nn_grid": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_three_weights": (_i, [_sz, _vp, _vp, _vp]),
     "pc_three_interpolate": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_three_interpolate_grad_workspace_bytes": (_sz, [_i, _i, _i, _i]),

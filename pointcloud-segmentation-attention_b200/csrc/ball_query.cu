@@ -180,6 +180,8 @@ ball_query_kernel(int n, int m, float s_star, int nsample, float one, const floa
   }
 }
 
+}  // namespace
+
 // Largest float s with max(sqrtf(s), 1e-20f) < radius, or -1 if there is none.
 float ball_threshold(float radius) {
   if (!(radius > 1e-20f)) return -1.0f;  // d is clamped to 1e-20f from below, so nothing can hit
@@ -199,7 +201,6 @@ float ball_threshold(float radius) {
   return s;
 }
 
-}  // namespace
 }  // namespace pc
 
 extern "C" int pc_query_ball(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,

@@ -87,6 +87,10 @@ inline cudaError_t allow_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Largest float s with max(sqrtf(s), 1e-20f) < radius, or -1 if there is none (ball_query.cu): the exact form of the
+// reference's hit test max(sqrtf(d2),1e-20f) < radius (tf_grouping_g.cu:24-25) as a compare on d2.
+float ball_threshold(float radius);
+
 // ---- CSR inverse of an index tensor + deterministic segmented reductions (segreduce.cu) ----
 // Workspace per call: b * (nkeys + 1 + npos) int32.
 size_t csr_workspace_bytes(int b, int nkeys, int npos);

@@ -9,9 +9,15 @@
 // (xyz as packed fp32x2 pairs + running min-distance = 4P registers), a copy of xyz sits in shared memory only to
 // broadcast the chosen centre.  A round is: P/2 packed distance updates per thread (FADD2/FMUL2/FFMA2, two points per
 // instruction, each operation still rounded on its own) -> redux.sync max over the value bits (non-negative floats
-// order like ints) -> one shared-memory hop across warps -> only threads holding the maximal value compute their
-// tie-break key and atomicMin it.  Two barriers per round instead of the reference's ten (none when the scene fits
-// one warp), no global traffic at all inside the m-1 dependent rounds.
+// order like ints) -> the lane at the warp maximum resolves its tie-break key, redux.sync min -> each warp publishes
+// (value, key) in shared memory -> ONE barrier -> every warp re-reduces the published pairs.  One barrier per round
+// instead of the reference's ten (none when the scene fits one warp), no global traffic inside the m-1 dependent
+// rounds, and the sampled coordinates can be written by the same kernel (pc_fps_gather).
+//
+// Measured anatomy of a round at n = 8192 on B200 (scripts/ubench/fps_rounds.cu): distance updates 620-660 cycles (the
+// fp32 pipe needs 512: 8192 points x 8 un-fused flops / 128 lanes), winner resolution + barrier + broadcast ~300-450.
+// A scene cannot go faster on one SM, and splitting it over a cluster buys less than the DSMEM exchange costs at this
+// size -- so throughput comes from running scenes, and batches, side by side.
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -42,12 +48,16 @@ struct FpsMap {
   __device__ static __forceinline__ int k_of(int tid, int i) { return tid + T * (i / A) + (R * T) * (i % A); }
 };
 
-template <int P, int T>
-__global__ void __launch_bounds__(T, 1)
-fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out) {
+// Register cap: the state itself is 4 registers per point; capping the rest leaves register file and warp slots on an
+// FPS SM for CTAs of other kernels (a scene's FPS keeps the fp32 pipe < 50 % busy), which matters when several
+// batches are in flight.
+template <int P, int T, bool kOneBarrier, int kRegs>
+__global__ void __launch_bounds__(T, 1) __maxnreg__(kRegs)
+fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out,
+                  float *__restrict__ out_xyz) {
   extern __shared__ float s_xyz[];  // n*3
-  __shared__ int s_wmax[2][32];     // per-warp maxima, double-buffered by round parity
-  __shared__ int s_tb[2];           // winning tie-break key, double-buffered by round parity
+  __shared__ int2 s_pair[2][32];    // per-warp (max value bits, tie-break key), double-buffered by round parity
+  __shared__ int s_tb[2];           // two-barrier variant: winning tie-break key, double-buffered by round parity
   using Map = FpsMap<P, T>;
   static_assert(P % 2 == 0 && T % 32 == 0 && (T >= 512 || P % Map::R == 0), "bad FPS shape");
   constexpr int H = P / 2;
@@ -61,9 +71,14 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
   for (int scene = blockIdx.x; scene < b; scene += gridDim.x) {
     const float *p = xyz + (size_t)scene * n * 3;
     int *o = out + (size_t)scene * m;
-    __syncthreads();  // previous scene fully done with s_xyz / s_tb
+    __syncthreads();  // previous scene fully done with s_xyz / s_pair
     for (int i = tid; i < n * 3; i += T) s_xyz[i] = p[i];
-    if (tid == 0) { s_tb[0] = INT_MAX; s_tb[1] = INT_MAX; o[0] = 0; }
+    float *oxyz = out_xyz ? out_xyz + (size_t)scene * m * 3 : nullptr;
+    if (tid == 0) {
+      o[0] = 0;
+      s_tb[0] = INT_MAX; s_tb[1] = INT_MAX;
+      if (oxyz) { oxyz[0] = p[0]; oxyz[1] = p[1]; oxyz[2] = p[2]; }
+    }
     __syncthreads();
 
     f32x2 px[H], py[H], pz[H];
@@ -86,8 +101,8 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
     }
 
     int old = 0;
-    int *wslot = &s_wmax[1][warp];          // slot this warp's lane 0 writes in round j (parity j&1), j starts at 1
-    const int *rslot = &s_wmax[1][lane < nwarps ? lane : 0];
+    int2 *wslot = &s_pair[1][warp];         // slot this warp's lane 0 writes in round j (parity j&1), j starts at 1
+    const int2 *rslot = &s_pair[1][lane < nwarps ? lane : 0];
     int par = 1;
     for (int j = 1; j < m; ++j) {
       const float cx = s_xyz[old * 3 + 0], cy = s_xyz[old * 3 + 1], cz = s_xyz[old * 3 + 2];
@@ -108,36 +123,66 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
       float vmax = gm[0];
 #pragma unroll
       for (int g = 1; g < NG; ++g) vmax = fmaxf(vmax, gm[g]);
-      const int vb = __float_as_int(vmax);
-      int gmax = __reduce_max_sync(PC_FULL_MASK, vb);
-      if (nwarps > 1) {
-        if (lane == 0) *wslot = gmax;
+      if constexpr (!kOneBarrier && nwarps > 1) {
+        // Two-barrier variant: block maximum first, then only the thread(s) at the block maximum resolve a key.
+        const int vb = __float_as_int(vmax);
+        const int wmax = __reduce_max_sync(PC_FULL_MASK, vb);
+        if (lane == 0) wslot->x = wmax;
         __syncthreads();
-        gmax = __reduce_max_sync(PC_FULL_MASK, *rslot);  // lanes >= nwarps re-read slot 0: harmless for a max
-      }
-      int tb = INT_MAX;
-      if (vb == gmax) {  // rare: this thread owns a point at the maximum; its first such slot is its best candidate
+        const int gmax = __reduce_max_sync(PC_FULL_MASK, rslot->x);
+        if (vb == gmax) {
+          int tb = INT_MAX;
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if (tb == INT_MAX && __float_as_int(gm[g]) == gmax) {
+          for (int g = 0; g < NG; ++g) {
+            if (tb == INT_MAX && __float_as_int(gm[g]) == gmax) {
 #pragma unroll
-            for (int e = G - 1; e >= 0; --e)
-              if (__float_as_int(td[g * G + e]) == gmax) tb = tie_key(Map::k_of(tid, g * G + e));
+              for (int e = G - 1; e >= 0; --e)
+                if (__float_as_int(td[g * G + e]) == gmax) tb = tie_key(Map::k_of(tid, g * G + e));
+            }
           }
+          atomicMin(&s_tb[par], tb);
         }
-      }
-      if (nwarps > 1) {
-        if (vb == gmax) atomicMin(&s_tb[par], tb);
-        if (tid == 0) s_tb[par ^ 1] = INT_MAX;  // next round's slot; nobody touches it before the next barrier pair
+        if (tid == 0) s_tb[par ^ 1] = INT_MAX;
         __syncthreads();
         old = tie_key_to_index(s_tb[par]);
         par ^= 1;
         wslot += par ? 32 : -32;
         rslot += par ? 32 : -32;
-      } else {  // a single warp: no shared-memory hop, no barrier
-        old = tie_key_to_index(__reduce_min_sync(PC_FULL_MASK, tb));
+      } else {
+      // Warp winner: value by redux, then the lane(s) at the warp maximum resolve their first slot at that value (slots
+      // are in tie-break order) and a second redux picks the smallest key.  ONE barrier per round: every warp publishes
+      // (value, key) in a parity-double-buffered slot and re-reduces all warps' pairs after the barrier.
+      const int vb = __float_as_int(vmax);
+      const int wmax = __reduce_max_sync(PC_FULL_MASK, vb);
+      int tb = INT_MAX;
+      if (vb == wmax) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (tb == INT_MAX && __float_as_int(gm[g]) == wmax) {
+#pragma unroll
+            for (int e = G - 1; e >= 0; --e)
+              if (__float_as_int(td[g * G + e]) == wmax) tb = tie_key(Map::k_of(tid, g * G + e));
+          }
+        }
       }
-      if (tid == 0) o[j] = old;
+      const int wkey = __reduce_min_sync(PC_FULL_MASK, tb);
+      if (nwarps > 1) {
+        if (lane == 0) *wslot = make_int2(wmax, wkey);
+        __syncthreads();
+        const int2 pr = *rslot;  // lanes >= nwarps re-read slot 0: harmless for max / min
+        const int gmax = __reduce_max_sync(PC_FULL_MASK, pr.x);
+        old = tie_key_to_index(__reduce_min_sync(PC_FULL_MASK, pr.x == gmax ? pr.y : INT_MAX));
+        par ^= 1;
+        wslot += par ? 32 : -32;
+        rslot += par ? 32 : -32;
+      } else {  // a single warp: no shared-memory hop, no barrier
+        old = tie_key_to_index(wkey);
+      }
+      }
+      if (tid == 0) {
+        o[j] = old;
+        if (oxyz) { oxyz[j * 3 + 0] = s_xyz[old * 3 + 0]; oxyz[j * 3 + 1] = s_xyz[old * 3 + 1]; oxyz[j * 3 + 2] = s_xyz[old * 3 + 2]; }
+      }
     }
   }
 }
@@ -191,12 +236,12 @@ fps_stream_kernel(int b, int n, int m, const float *__restrict__ xyz, float *__r
   }
 }
 
-template <int P, int T>
-int launch_onchip(int b, int n, int m, const float *xyz, int *out, cudaStream_t st) {
+template <int P, int T, bool kOneBarrier = true, int kRegs = (P >= 32 ? 168 : 128)>
+int launch_onchip(int b, int n, int m, const float *xyz, int *out, float *out_xyz, cudaStream_t st) {
   size_t smem = (size_t)n * 3 * sizeof(float);
-  if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(fps_onchip_kernel<P, T>, smem));
+  if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(fps_onchip_kernel<P, T, kOneBarrier, kRegs>, smem));
   int grid = b;  // one CTA per scene; more scenes than SMs simply queue (1 CTA/SM resident)
-  fps_onchip_kernel<P, T><<<grid, T, smem, st>>>(b, n, m, 1.0f, xyz, out);
+  fps_onchip_kernel<P, T, kOneBarrier, kRegs><<<grid, T, smem, st>>>(b, n, m, 1.0f, xyz, out, out_xyz);
   PC_RETURN_LAUNCH_STATUS();
 }
 
@@ -209,7 +254,10 @@ extern "C" size_t pc_fps_workspace_bytes(int b, int n, int m) {
   return (size_t)b * n * sizeof(float);
 }
 
-extern "C" int pc_fps(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, pc_stream_t stream) {
+// FPS that also writes the sampled coordinates: out_xyz (b,m,3) = xyz[b, out_idx[b,j], :], i.e. the
+// farthest_point_sample + gather_point pair every caller issues back to back (utils/pointnet_util.py:34), in one launch.
+extern "C" int pc_fps_gather(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, float *out_xyz,
+                             pc_stream_t stream) {
   if (b < 0 || n < 0) return PC_ERR_INVALID_ARGUMENT;
   if (m <= 0 || b == 0) return PC_OK;  // tf_sampling_g.cu:106-107
   if (n == 0) return PC_ERR_INVALID_ARGUMENT;
@@ -218,20 +266,30 @@ extern "C" int pc_fps(int b, int n, int m, const float *xyz, void *workspace, in
   if (n <= pc::kMaxRegPoints) {
     // Few, fat threads (see the kernel comment).  n <= 256 runs in ONE warp (no barrier at all); up to 4096 points
     // take 4 warps (one per SM sub-partition); beyond that 8 warps x 32 points per thread.
-    if (n <= 64) return pc::launch_onchip<2, 32>(b, n, m, xyz, out_idx, st);
-    if (n <= 128) return pc::launch_onchip<4, 32>(b, n, m, xyz, out_idx, st);
-    if (n <= 256) return pc::launch_onchip<8, 32>(b, n, m, xyz, out_idx, st);
-    if (n <= 512) return pc::launch_onchip<4, 128>(b, n, m, xyz, out_idx, st);
-    if (n <= 1024) return pc::launch_onchip<8, 128>(b, n, m, xyz, out_idx, st);
-    if (n <= 2048) return pc::launch_onchip<16, 128>(b, n, m, xyz, out_idx, st);
-    if (n <= 4096) return pc::launch_onchip<32, 128>(b, n, m, xyz, out_idx, st);
-    static int shape = -1;  // development knob: PCOPS_FPS_SHAPE=512 selects 16 warps x 16 points
+    if (n <= 64) return pc::launch_onchip<2, 32>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (n <= 128) return pc::launch_onchip<4, 32>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (n <= 256) return pc::launch_onchip<8, 32>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (n <= 512) return pc::launch_onchip<4, 128>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (n <= 1024) return pc::launch_onchip<8, 128>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (n <= 2048) return pc::launch_onchip<16, 128>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (n <= 4096) return pc::launch_onchip<32, 128>(b, n, m, xyz, out_idx, out_xyz, st);
+    // Two shapes for 4097..8192 points (measured on B200, 16 scenes x 8192 -> 1024):
+    //   default  8 warps x 32 points, one barrier per round, 168 registers: 645 us alone, but leaves a quarter of the
+    //            register file to CTAs of other kernels -- best whole-pipeline throughput with several batches in flight;
+    //   PCOPS_FPS_SHAPE=512  16 warps x 16 points, two-barrier tail: 584 us alone (lowest single-launch latency).
+    static int shape = -1;
     if (shape < 0) { const char *e = getenv("PCOPS_FPS_SHAPE"); shape = e ? atoi(e) : 256; }
-    if (shape == 512) return pc::launch_onchip<16, 512>(b, n, m, xyz, out_idx, st);
-    if (shape == 1024) return pc::launch_onchip<8, 1024>(b, n, m, xyz, out_idx, st);
-    return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, st);
+    if (shape == 512) return pc::launch_onchip<16, 512, false, 128>(b, n, m, xyz, out_idx, out_xyz, st);
+    return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
   }
   if (!workspace) return PC_ERR_WORKSPACE;
   pc::fps_stream_kernel<<<b, 1024, 0, st>>>(b, n, m, xyz, (float *)workspace, out_idx);
-  PC_RETURN_LAUNCH_STATUS();
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  if (out_xyz) return pc_gather_point(b, n, m, xyz, out_idx, out_xyz, stream);
+  return PC_OK;
+}
+
+extern "C" int pc_fps(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, pc_stream_t stream) {
+  return pc_fps_gather(b, n, m, xyz, workspace, out_idx, nullptr, stream);
 }

@@ -1,0 +1,521 @@
+// Cell-grid accelerated ball query and three_nn for sm_100a.
+//
+// pc_query_ball / pc_three_nn test every (query, candidate) pair like the reference kernels do
+// (tf_ops/grouping/tf_grouping_g.cu:3-36, tf_ops/interpolation_3d/tf_interpolate.cpp:60-103).  The *_grid entry points
+// return the SAME outputs, bit for bit, from far fewer pair tests:
+//   1. grid_build_kernel bins the candidate cloud of every scene into a uniform cell grid (one CTA per scene:
+//      bounding box -> shared-memory histogram -> scan -> scatter into a cell-sorted float4 array that carries the
+//      original index), and bins the QUERY cloud by the same cells, so 32 consecutive sorted queries are neighbours;
+//   2. a warp owns such a tile of 32 queries, stages the union of their cell neighbourhoods once, and runs the
+//      branch-free packed all-pairs filter on that local candidate set only.
+//   ball query   cell edge >= r * (1 + 1e-4): every point inside a ball lies in the 3x3x3 neighbourhood of the query's
+//                cell.  The cell filter is only a conservative superset -- the hit test on the survivors is the
+//                reference's exact un-fused arithmetic -- and hits are recorded as bits at their ORIGINAL index in a
+//                per-query shared-memory bitmap, so "first nsample in ascending index", first-hit padding and pts_cnt
+//                come out unchanged.
+//   three_nn     after scanning (a superset of) the 3x3x3 neighbourhood every unvisited point is farther than one
+//                cell edge h, so a lane whose third-best squared distance is below (0.999 h)^2 is certified; the few
+//                that are not get a warp-cooperative scan of the whole cloud.  Visiting order is no longer ascending
+//                index, so the 3-slot insertion orders by (distance, index) -- exactly what the reference's strict-'<'
+//                scan over ascending indices keeps.
+#include <math.h>
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int kMaxCells = 16384;  // 64 KB shared-memory histogram in the build kernel
+constexpr int kBuildThreads = 1024;
+constexpr int kHdrInts = 16;
+
+struct GridHdr {  // 16 x 4 bytes, first thing in a scene's workspace
+  float ox, oy, oz, inv_h, h;
+  int nx, ny, nz, ncells;
+  int pad[7];
+};
+static_assert(sizeof(GridHdr) == kHdrInts * 4, "GridHdr layout");
+
+// per-scene workspace: GridHdr | cell_start[kMaxCells + 1] | (16-byte aligned) sorted float4[n]
+__host__ __device__ inline size_t grid_sorted_offset_ints() { return (size_t)((kHdrInts + kMaxCells + 1 + 3) / 4 * 4); }
+__host__ __device__ inline size_t grid_scene_ints(int n) { return grid_sorted_offset_ints() + (size_t)n * 4; }
+
+__device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int dim) {
+  // monotone in x (fp32 subtract of a constant, multiply by a positive constant, floor): the conservative cell range
+  // of an interval is the range of its end points
+  const int c = (int)floorf((x - o) * inv_h);
+  return min(max(c, 0), dim - 1);
+}
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float *s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(PC_FULL_MASK, v, o);
+    v = is_max ? fmaxf(v, w) : fminf(v, w);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = is_max ? fmaxf(r, s_red[i]) : fminf(r, s_red[i]);
+  return r;
+}
+
+// mode 0: cell edge = min_edge (ball query, min_edge = r'); mode 1: cell edge from the point density (three_nn);
+// mode 2: bin with the header of another grid (hdr_ws, hdr_n points per scene): the QUERY cloud sorted by the cells
+// of the candidate grid, so that 32 consecutive sorted queries are spatial neighbours.
+__global__ void __launch_bounds__(kBuildThreads, 1)
+grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz, int *__restrict__ ws,
+                  const int *__restrict__ hdr_ws, int hdr_n) {
+  extern __shared__ int s_cnt[];  // kMaxCells
+  __shared__ float s_red[32];
+  __shared__ GridHdr s_hdr;
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *p = xyz + (size_t)scene * n * 3;
+  int *base = ws + (size_t)scene * grid_scene_ints(n);
+  int *cell_start = base + kHdrInts;
+  float4 *sorted = reinterpret_cast<float4 *>(base + grid_sorted_offset_ints());
+
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (mode == 2) {
+    if (tid == 0) {
+      s_hdr = *reinterpret_cast<const GridHdr *>(hdr_ws + (size_t)scene * grid_scene_ints(hdr_n));
+      *reinterpret_cast<GridHdr *>(base) = s_hdr;
+      s_carry = 0;
+    }
+  } else {
+  for (int k = tid; k < n; k += kBuildThreads) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __ldg(p + k * 3 + c);
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    lo[c] = block_reduce(lo[c], false, s_red);
+    hi[c] = block_reduce(hi[c], true, s_red);
+  }
+  if (tid == 0) {
+    const float ex = fmaxf(hi[0] - lo[0], 0.f), ey = fmaxf(hi[1] - lo[1], 0.f), ez = fmaxf(hi[2] - lo[2], 0.f);
+    float h = min_edge;
+    if (mode == 1) {  // ~1 point per cell in volume terms, never finer than the surface / line density suggests
+      const float vol = ex * ey * ez, area = fmaxf(ex * ey, fmaxf(ex * ez, ey * ez)), len = fmaxf(ex, fmaxf(ey, ez));
+      h = fmaxf(fmaxf(cbrtf(vol / n), 0.7f * sqrtf(area / n)), fmaxf(len / n, 1e-12f));
+      h = fmaxf(h, min_edge);
+    }
+    if (!(h > 0.f) || !isfinite(h)) h = 1.0f;
+    int nx, ny, nz;
+    for (;;) {  // coarsen until the grid fits the histogram
+      const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
+      if (fx * fy * fz <= (float)kMaxCells) { nx = (int)fx; ny = (int)fy; nz = (int)fz; break; }
+      h *= 1.25f;
+    }
+    s_hdr.ox = lo[0]; s_hdr.oy = lo[1]; s_hdr.oz = lo[2];
+    s_hdr.h = h; s_hdr.inv_h = 1.0f / h;
+    s_hdr.nx = nx; s_hdr.ny = ny; s_hdr.nz = nz; s_hdr.ncells = nx * ny * nz;
+    *reinterpret_cast<GridHdr *>(base) = s_hdr;
+    s_carry = 0;
+  }
+  }
+  __syncthreads();
+  const GridHdr g = s_hdr;
+  for (int i = tid; i < g.ncells; i += kBuildThreads) s_cnt[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < n; k += kBuildThreads) {
+    const int c = (cell_coord(__ldg(p + k * 3 + 2), g.oz, g.inv_h, g.nz) * g.ny +
+                   cell_coord(__ldg(p + k * 3 + 1), g.oy, g.inv_h, g.ny)) * g.nx +
+                  cell_coord(__ldg(p + k * 3 + 0), g.ox, g.inv_h, g.nx);
+    atomicAdd(&s_cnt[c], 1);
+  }
+  __syncthreads();
+  // exclusive scan of s_cnt[0..ncells) in chunks of kBuildThreads; s_cnt becomes the scatter cursor
+  for (int b0 = 0; b0 < g.ncells; b0 += kBuildThreads) {
+    const int i = b0 + tid;
+    const int v = i < g.ncells ? s_cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(PC_FULL_MASK, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = s_warp[lane];
+      int iw = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(PC_FULL_MASK, iw, o);
+        if (lane >= o) iw += u;
+      }
+      s_warp[lane] = iw - w;
+    }
+    __syncthreads();
+    const int excl = s_carry + s_warp[warp] + incl - v;
+    if (i < g.ncells) { s_cnt[i] = excl; cell_start[i] = excl; }
+    __syncthreads();
+    if (tid == kBuildThreads - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) cell_start[g.ncells] = n;
+  for (int k = tid; k < n; k += kBuildThreads) {
+    const float x = __ldg(p + k * 3 + 0), y = __ldg(p + k * 3 + 1), z = __ldg(p + k * 3 + 2);
+    const int c = (cell_coord(z, g.oz, g.inv_h, g.nz) * g.ny + cell_coord(y, g.oy, g.inv_h, g.ny)) * g.nx +
+                  cell_coord(x, g.ox, g.inv_h, g.nx);
+    const int pos = atomicAdd(&s_cnt[c], 1);  // order inside a cell is arbitrary; no result depends on it
+    sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ three_nn
+// (distance, index) ordered 3-slot insertion: the reference visits ascending indices with strict '<'
+// (tf_interpolate.cpp:74-89), i.e. keeps the 3 smallest by (distance, index); here the visiting order is arbitrary.
+__device__ __forceinline__ bool before(float d, int k, float bd, int bi) { return d < bd || (d == bd && k < bi); }
+__device__ __forceinline__ void nn_insert_lex(float d, int k, float &b1, float &b2, float &b3, int &i1, int &i2, int &i3) {
+  if (before(d, k, b3, i3)) {
+    if (before(d, k, b1, i1)) {
+      b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
+    } else if (before(d, k, b2, i2)) {
+      b3 = b2; i3 = i2; b2 = d; i2 = k;
+    } else {
+      b3 = d; i3 = k;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tile kernels
+// Thread-per-query traversal of the grid (kernels above) is latency- and divergence-bound: every lane chases its own
+// cell runs.  The tile kernels sort the QUERIES by cell as well (grid_build_kernel mode 2), so a warp owns 32
+// spatial neighbours, whose cell neighbourhoods overlap almost completely.  The warp stages the UNION of those
+// neighbourhoods once (coalesced cell-run copies into an SoA shared-memory stage) and then runs the branch-free packed
+// all-pairs filter of ball_query.cu / interpolate.cu on that local candidate set only -- a few hundred candidates per
+// warp instead of the whole scene.
+constexpr int kMaxRows = 256;  // (z, y) cell rows of the union box handled per pass
+constexpr int kCap = 512;      // staged candidates per batch
+constexpr int kTileWarpInts = 3 * kMaxRows + 4 * kCap;  // per-warp shared memory: rows (start, len, offset) + stage
+
+struct TileSmem {
+  int *rs, *rl, *ro;
+  float *x, *y, *z;
+  int *i;
+  __device__ explicit TileSmem(int *base)
+      : rs(base), rl(base + kMaxRows), ro(base + 2 * kMaxRows), x(reinterpret_cast<float *>(base + 3 * kMaxRows)),
+        y(x + kCap), z(y + kCap), i(base + 3 * kMaxRows + 3 * kCap) {}
+};
+
+// Stages the candidates of the cell box [X0..X1] x [Y0..Y1] x [Z0..Z1] batch by batch and calls process(count) with
+// `count` (a multiple of 32, padded with +inf points) candidates in the stage.  Warp-collective.
+template <class F>
+__device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__restrict__ cell_start,
+                                               const float4 *__restrict__ sorted, int X0, int X1, int Y0, int Y1, int Z0,
+                                               int Z1, TileSmem &st, F &&process) {
+  const int lane = threadIdx.x & 31;
+  const float inf = __int_as_float(0x7f800000);
+  const int nyu = Y1 - Y0 + 1, nrows = nyu * (Z1 - Z0 + 1);
+  for (int r0 = 0; r0 < nrows; r0 += kMaxRows) {
+    const int nr = min(kMaxRows, nrows - r0);
+    for (int r = lane; r < kMaxRows; r += 32) {
+      int s = 0, len = 0;
+      if (r < nr) {
+        const int rr = r0 + r, z = Z0 + rr / nyu, y = Y0 + rr % nyu, row = (z * g.ny + y) * g.nx;
+        s = __ldg(cell_start + row + X0);  // cells X0..X1 of a row are contiguous in the sorted array
+        len = __ldg(cell_start + row + X1 + 1) - s;
+      }
+      st.rs[r] = s;
+      st.rl[r] = len;
+    }
+    __syncwarp();
+    // exclusive prefix of the row lengths: lane owns rows [8*lane, 8*lane+8)
+    int mine = 0;
+#pragma unroll
+    for (int t = 0; t < kMaxRows / 32; ++t) mine += st.rl[lane * (kMaxRows / 32) + t];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(PC_FULL_MASK, incl, o);
+      if (lane >= o) incl += u;
+    }
+    const int total = __shfl_sync(PC_FULL_MASK, incl, 31);
+    int run = incl - mine;
+#pragma unroll
+    for (int t = 0; t < kMaxRows / 32; ++t) {
+      st.ro[lane * (kMaxRows / 32) + t] = run;
+      run += st.rl[lane * (kMaxRows / 32) + t];
+    }
+    __syncwarp();
+    for (int b0 = 0; b0 < total; b0 += kCap) {
+      const int bn = min(kCap, total - b0);
+      for (int r = lane; r < nr; r += 32) {  // a lane copies whole cell runs (contiguous float4s)
+        const int off = st.ro[r], s = st.rs[r];
+        const int lo = max(off, b0), hi = min(off + st.rl[r], b0 + bn);
+        for (int f = lo; f < hi; ++f) {
+          const float4 v = __ldg(sorted + s + (f - off));
+          st.x[f - b0] = v.x; st.y[f - b0] = v.y; st.z[f - b0] = v.z; st.i[f - b0] = __float_as_int(v.w);
+        }
+      }
+      const int bp = (bn + 31) & ~31;
+      for (int f = bn + lane; f < bp; f += 32) { st.x[f] = inf; st.y[f] = inf; st.z[f] = inf; st.i[f] = 0; }
+      __syncwarp();
+      process(bp);
+      __syncwarp();
+    }
+  }
+}
+
+// 32 hit bits (bit e <-> staged candidate w0 + e) of `d(query, candidate) - thr < 0` for one word of the stage.
+__device__ __forceinline__ unsigned filter_word(const TileSmem &st, int w0, f32x2 qx2, f32x2 qy2, f32x2 qz2, f32x2 one2,
+                                                int thr, bool query_minus_candidate) {
+  unsigned word = 0;
+#pragma unroll
+  for (int gq = 0; gq < 8; ++gq) {
+    const int k = w0 + gq * 4;
+    const float4 xs = *reinterpret_cast<const float4 *>(st.x + k);
+    const float4 ys = *reinterpret_cast<const float4 *>(st.y + k);
+    const float4 zs = *reinterpret_cast<const float4 *>(st.z + k);
+    const f32x2 xa = pack2(xs.x, xs.y), ya = pack2(ys.x, ys.y), za = pack2(zs.x, zs.y);
+    const f32x2 xb = pack2(xs.z, xs.w), yb = pack2(ys.z, ys.w), zb = pack2(zs.z, zs.w);
+    float d0, d1, d2, d3;
+    if (query_minus_candidate) {
+      unpack2(sqdist3_x2(qx2, qy2, qz2, xa, ya, za, one2), d0, d1);
+      unpack2(sqdist3_x2(qx2, qy2, qz2, xb, yb, zb, one2), d2, d3);
+    } else {
+      unpack2(sqdist3_x2(xa, ya, za, qx2, qy2, qz2, one2), d0, d1);
+      unpack2(sqdist3_x2(xb, yb, zb, qx2, qy2, qz2, one2), d2, d3);
+    }
+    word = __funnelshift_l(__float_as_int(d0) - thr, word, 1);
+    word = __funnelshift_l(__float_as_int(d1) - thr, word, 1);
+    word = __funnelshift_l(__float_as_int(d2) - thr, word, 1);
+    word = __funnelshift_l(__float_as_int(d3) - thr, word, 1);
+  }
+  return __brev(word);
+}
+
+// Ball query, one warp per CTA, a tile = 32 consecutive cell-sorted queries.
+__global__ void __launch_bounds__(32)
+ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, float one, const int *__restrict__ ws_c,
+                       const int *__restrict__ ws_q, int *__restrict__ idx, int *__restrict__ pts_cnt) {
+  extern __shared__ __align__(16) int s_tile[];  // TileSmem | bitmap (nwords + nsumm) * 32
+  TileSmem st(s_tile);
+  const int nwords = (n + 31) >> 5, nsumm = (nwords + 31) >> 5;
+  unsigned *s_bits = reinterpret_cast<unsigned *>(s_tile + kTileWarpInts);
+  unsigned *s_summ = s_bits + (size_t)nwords * 32;
+  const int scene = blockIdx.y, lane = threadIdx.x;
+  const int *cbase = ws_c + (size_t)scene * grid_scene_ints(n);
+  const GridHdr g = *reinterpret_cast<const GridHdr *>(cbase);
+  const int *cell_start = cbase + kHdrInts;
+  const float4 *sorted = reinterpret_cast<const float4 *>(cbase + grid_sorted_offset_ints());
+  const float4 *qsorted =
+      reinterpret_cast<const float4 *>(ws_q + (size_t)scene * grid_scene_ints(m) + grid_sorted_offset_ints());
+  const f32x2 one2 = pack2(one, one);
+  const int thr = (s_star >= 0.0f) ? __float_as_int(s_star) + 1 : 0;
+  for (int i = lane; i < (nwords + nsumm) * 32; i += 32) s_bits[i] = 0;
+  __syncwarp();
+  const int ntiles = (m + 31) >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int qs = tile * 32 + lane;
+    const bool live = qs < m;
+    const float4 qv = __ldg(qsorted + (live ? qs : tile * 32));
+    const int qi = __float_as_int(qv.w);
+    const f32x2 qx2 = pack2(qv.x, qv.x), qy2 = pack2(qv.y, qv.y), qz2 = pack2(qv.z, qv.z);
+    // cell box of this lane's ball (dead lanes copy the tile's first query) and the warp's union box
+    const int X0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.x - reach, g.ox, g.inv_h, g.nx));
+    const int X1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.x + reach, g.ox, g.inv_h, g.nx));
+    const int Y0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.y - reach, g.oy, g.inv_h, g.ny));
+    const int Y1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.y + reach, g.oy, g.inv_h, g.ny));
+    const int Z0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.z - reach, g.oz, g.inv_h, g.nz));
+    const int Z1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.z + reach, g.oz, g.inv_h, g.nz));
+    for_each_batch(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
+      for (int w0 = 0; w0 < count; w0 += 32) {
+        unsigned word = filter_word(st, w0, qx2, qy2, qz2, one2, thr, true);
+        while (word) {  // record each hit at its ORIGINAL index
+          const int k = st.i[w0 + __ffs(word) - 1], w = k >> 5;
+          word &= word - 1;
+          s_bits[w * 32 + lane] |= 1u << (k & 31);
+          s_summ[(w >> 5) * 32 + lane] |= 1u << (w & 31);
+        }
+      }
+    });
+    // ascending extraction; every touched word is cleared on the way so the bitmap is clean for the next tile
+    int *row_out = idx + ((size_t)scene * m + (live ? qi : 0)) * nsample;
+    int cnt = 0, first = 0;
+    for (int sidx = 0; sidx < nsumm; ++sidx) {
+      unsigned sw = s_summ[sidx * 32 + lane];
+      if (sw) s_summ[sidx * 32 + lane] = 0;
+      while (sw) {
+        const int w = sidx * 32 + __ffs(sw) - 1;
+        sw &= sw - 1;
+        unsigned word = s_bits[w * 32 + lane];
+        s_bits[w * 32 + lane] = 0;
+        while (word && cnt < nsample) {
+          const int k = w * 32 + __ffs(word) - 1;
+          word &= word - 1;
+          if (cnt == 0) first = k;
+          if (live) row_out[cnt] = k;
+          ++cnt;
+        }
+      }
+    }
+    if (live) {
+      for (int l = cnt; l < nsample; ++l) row_out[l] = first;  // tf_grouping_g.cu:26-29; empty ball -> zero row
+      pts_cnt[(size_t)scene * m + qi] = cnt;
+    }
+    __syncwarp();
+  }
+}
+
+// three_nn over tiles of 32 cell-sorted dense points; kWarps independent warps per CTA.
+constexpr int kNNTileWarps = 4;
+__global__ void __launch_bounds__(kNNTileWarps * 32)
+three_nn_tile_kernel(int n, int m, float one, const int *__restrict__ ws_c, const int *__restrict__ ws_q,
+                     float *__restrict__ dist, int *__restrict__ idx) {
+  extern __shared__ __align__(16) int s_tile[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TileSmem st(s_tile + warp * kTileWarpInts);
+  const int scene = blockIdx.y;
+  const int *cbase = ws_c + (size_t)scene * grid_scene_ints(m);
+  const GridHdr g = *reinterpret_cast<const GridHdr *>(cbase);
+  const int *cell_start = cbase + kHdrInts;
+  const float4 *sorted = reinterpret_cast<const float4 *>(cbase + grid_sorted_offset_ints());
+  const float4 *qsorted =
+      reinterpret_cast<const float4 *>(ws_q + (size_t)scene * grid_scene_ints(n) + grid_sorted_offset_ints());
+  const f32x2 one2 = pack2(one, one);
+  const float inf = __int_as_float(0x7f800000);
+  const int ntiles = (n + 31) >> 5;
+  for (int tile = blockIdx.x * kNNTileWarps + warp; tile < ntiles; tile += gridDim.x * kNNTileWarps) {
+    const int qs = tile * 32 + lane;
+    const bool live = qs < n;
+    const float4 qv = __ldg(qsorted + (live ? qs : tile * 32));
+    const int qi = __float_as_int(qv.w);
+    const f32x2 qx2 = pack2(qv.x, qv.x), qy2 = pack2(qv.y, qv.y), qz2 = pack2(qv.z, qv.z);
+    const int cx = cell_coord(qv.x, g.ox, g.inv_h, g.nx), cy = cell_coord(qv.y, g.oy, g.inv_h, g.ny),
+              cz = cell_coord(qv.z, g.oz, g.inv_h, g.nz);
+    // union of the lanes' ring-1 neighbourhoods (a superset for every lane: more candidates never hurt)
+    const int X0 = max(__reduce_min_sync(PC_FULL_MASK, cx) - 1, 0), X1 = min(__reduce_max_sync(PC_FULL_MASK, cx) + 1, g.nx - 1);
+    const int Y0 = max(__reduce_min_sync(PC_FULL_MASK, cy) - 1, 0), Y1 = min(__reduce_max_sync(PC_FULL_MASK, cy) + 1, g.ny - 1);
+    const int Z0 = max(__reduce_min_sync(PC_FULL_MASK, cz) - 1, 0), Z1 = min(__reduce_max_sync(PC_FULL_MASK, cz) + 1, g.nz - 1);
+    float b1 = inf, b2 = inf, b3 = inf;
+    int i1 = INT_MAX, i2 = INT_MAX, i3 = INT_MAX;
+    for_each_batch(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
+      for (int w0 = 0; w0 < count; w0 += 32) {
+        // stale filter d <= b3 (ties on the distance may still win on the index); exact replay of the survivors
+        const int thr = (b3 == inf) ? 0x7f800000 : __float_as_int(b3) + 1;
+        unsigned word = filter_word(st, w0, qx2, qy2, qz2, one2, thr, false);
+        while (word) {
+          const int e = w0 + __ffs(word) - 1;
+          word &= word - 1;
+          nn_insert_lex(sqdist3(st.x[e], st.y[e], st.z[e], qv.x, qv.y, qv.z), st.i[e], b1, b2, b3, i1, i2, i3);
+        }
+      }
+    });
+    // certified when the third-best lies strictly inside the lane's own ring-1 box (see three_nn_grid_kernel)
+    const float bound = 0.999f * g.h;
+    unsigned todo = __ballot_sync(PC_FULL_MASK, live && !(b3 < bound * bound));
+    while (todo) {  // rare: the whole warp scans the cloud for that lane, then merges its 32 partial lists
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float fx = __shfl_sync(PC_FULL_MASK, qv.x, src), fy = __shfl_sync(PC_FULL_MASK, qv.y, src),
+                  fz = __shfl_sync(PC_FULL_MASK, qv.z, src);
+      float c1 = inf, c2 = inf, c3 = inf;
+      int j1 = INT_MAX, j2 = INT_MAX, j3 = INT_MAX;
+      for (int p = lane; p < m; p += 32) {
+        const float4 v = __ldg(sorted + p);
+        nn_insert_lex(sqdist3(v.x, v.y, v.z, fx, fy, fz), __float_as_int(v.w), c1, c2, c3, j1, j2, j3);
+      }
+      float r1 = inf, r2 = inf, r3 = inf;
+      int k1 = INT_MAX, k2 = INT_MAX, k3 = INT_MAX;
+#pragma unroll
+      for (int round = 0; round < 3; ++round) {  // pop the warp-wide (distance, index) minimum three times
+        float bd = c1;
+        int bi = j1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(PC_FULL_MASK, bd, o);
+          const int oi = __shfl_xor_sync(PC_FULL_MASK, bi, o);
+          if (before(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        if (round == 0) { r1 = bd; k1 = bi; } else if (round == 1) { r2 = bd; k2 = bi; } else { r3 = bd; k3 = bi; }
+        if (c1 == bd && j1 == bi) { c1 = c2; j1 = j2; c2 = c3; j2 = j3; c3 = inf; j3 = INT_MAX; }  // owner pops
+      }
+      if (lane == src) { b1 = r1; b2 = r2; b3 = r3; i1 = k1; i2 = k2; i3 = k3; }
+    }
+    if (live) {
+      float *dp = dist + ((size_t)scene * n + qi) * 3;
+      int *ip = idx + ((size_t)scene * n + qi) * 3;
+      dp[0] = b1; dp[1] = b2; dp[2] = b3;
+      ip[0] = (i1 == INT_MAX) ? 0 : i1; ip[1] = (i2 == INT_MAX) ? 0 : i2; ip[2] = (i3 == INT_MAX) ? 0 : i3;
+    }
+  }
+}
+
+int build(int b, int n, float min_edge, int mode, const float *xyz, int *ws, const int *hdr_ws, int hdr_n,
+          cudaStream_t st) {
+  const size_t smem = (size_t)kMaxCells * sizeof(int);
+  PC_CUDA_TRY(allow_smem(grid_build_kernel, smem));
+  grid_build_kernel<<<b, kBuildThreads, smem, st>>>(n, min_edge, mode, xyz, ws, hdr_ws, hdr_n);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace
+
+}  // namespace pc
+
+extern "C" size_t pc_query_ball_grid_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 0;
+  return (size_t)b * (pc::grid_scene_ints(n) + pc::grid_scene_ints(m)) * sizeof(int);
+}
+
+extern "C" int pc_query_ball_grid(int b, int n, int m, float radius, int nsample, const float *xyz1,
+                                  const float *xyz2, int *idx, int *pts_cnt, void *workspace, pc_stream_t stream) {
+  if (!(radius > 0.0f) || nsample <= 0) return PC_ERR_INVALID_ARGUMENT;  // tf_grouping.cpp:70-74
+  if (b < 0 || n < 0 || m < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || m == 0) return PC_OK;
+  if (!xyz2 || !idx || !pts_cnt || (n > 0 && !xyz1)) return PC_ERR_INVALID_ARGUMENT;
+  // shapes the bitmap does not cover (or nothing to bin): the all-pairs kernel gives the same outputs
+  const int nwords = (n + 31) / 32, nsumm = (nwords + 31) / 32;
+  const size_t smem = ((size_t)pc::kTileWarpInts + (size_t)(nwords + nsumm) * 32) * sizeof(int);
+  if (n == 0 || smem > 96 * 1024 || b > 65535 || !isfinite(radius))
+    return pc_query_ball(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+  if (!workspace) return PC_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float s_star = pc::ball_threshold(radius);
+  const float reach = radius * 1.0001f + 1e-30f;  // conservative: fp32 rounding of the distance is ~1e-7 relative
+  int *ws_c = (int *)workspace, *ws_q = ws_c + (size_t)b * pc::grid_scene_ints(n);
+  int rc = pc::build(b, n, reach, 0, xyz1, ws_c, nullptr, 0, st);
+  if (rc) return rc;
+  rc = pc::build(b, m, 0.0f, 2, xyz2, ws_q, ws_c, n, st);  // queries sorted by the candidates' cells
+  if (rc) return rc;
+  PC_CUDA_TRY(pc::allow_smem(pc::ball_query_tile_kernel, smem));
+  const int ntiles = (m + 31) / 32;
+  dim3 grid(ntiles < 64 ? ntiles : 64, b);
+  pc::ball_query_tile_kernel<<<grid, 32, smem, st>>>(n, m, s_star, reach, nsample, 1.0f, ws_c, ws_q, idx, pts_cnt);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" size_t pc_three_nn_grid_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || m <= 0 || n <= 0) return 0;
+  return (size_t)b * (pc::grid_scene_ints(m) + pc::grid_scene_ints(n)) * sizeof(int);
+}
+
+extern "C" int pc_three_nn_grid(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx,
+                                void *workspace, pc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0) return PC_OK;
+  if (!xyz1 || !dist || !idx || (m > 0 && !xyz2)) return PC_ERR_INVALID_ARGUMENT;
+  if (m < 64 || b > 65535) return pc_three_nn(b, n, m, xyz1, xyz2, dist, idx, stream);  // nothing to gain from binning
+  if (!workspace) return PC_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int *ws_c = (int *)workspace, *ws_q = ws_c + (size_t)b * pc::grid_scene_ints(m);
+  int rc = pc::build(b, m, 0.0f, 1, xyz2, ws_c, nullptr, 0, st);
+  if (rc) return rc;
+  rc = pc::build(b, n, 0.0f, 2, xyz1, ws_q, ws_c, m, st);  // dense points sorted by the known cloud's cells
+  if (rc) return rc;
+  const size_t smem = (size_t)pc::kNNTileWarps * pc::kTileWarpInts * sizeof(int);
+  PC_CUDA_TRY(pc::allow_smem(pc::three_nn_tile_kernel, smem));
+  const int ntiles = (n + 31) / 32, ctas = (ntiles + pc::kNNTileWarps - 1) / pc::kNNTileWarps;
+  dim3 grid(ctas < 256 ? ctas : 256, b);
+  pc::three_nn_tile_kernel<<<grid, pc::kNNTileWarps * 32, smem, st>>>(n, m, 1.0f, ws_c, ws_q, dist, idx);
+  PC_RETURN_LAUNCH_STATUS();
+}

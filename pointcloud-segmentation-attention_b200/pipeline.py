@@ -35,8 +35,14 @@ KEY_DIM = 4  # attention_layer.py:256-258: heads = C // 4, key_dim = output_dim 
 
 
 class ScanNetGeometry:
-    def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0, own_streams=False):
+    def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0, own_streams=False,
+                 grid=True, fuse_gather=True):
         self.B, self.N, self.CF = batch, npoints, feat_channels
+        # development knob (scripts only): which parts of the forward to enqueue, e.g. PCOPS_PIPE_PARTS=fps
+        import os
+        self.parts = os.environ.get("PCOPS_PIPE_PARTS", "fps,side").split(",")
+        self.fuse_gather = fuse_gather  # pc_fps_gather instead of pc_fps + pc_gather_point
+        self.grid = grid  # cell-grid ball query / three_nn (same outputs as the all-pairs kernels, far fewer pair tests)
         self.dev = torch.device(device)
         self.attention = attention
         self.L = _lib.lib()
@@ -83,6 +89,7 @@ class ScanNetGeometry:
                 lv["att"] = torch.empty((batch * m, cout), dtype=f32, device=dev)
             ws = self.L.pc_fps_workspace_bytes(batch, n, m)
             lv["fps_ws"] = _lib.workspace(ws, dev)
+            lv["ball_ws"] = _lib.workspace(self.L.pc_query_ball_grid_workspace_bytes(batch, n, m), dev)
             self.levels.append(lv)
             xyz, n, cin = lv["new_xyz"], m, cout
         # FP levels: dense xyz = level input, sparse xyz = level output; channels of the sparse features
@@ -96,11 +103,16 @@ class ScanNetGeometry:
             fp["idx"] = res((batch, lv["n"], 3), i32)
             fp["w"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
             fp["out"] = torch.empty((batch, lv["n"], c), dtype=f32, device=dev)
+            fp["nn_ws"] = _lib.workspace(self.L.pc_three_nn_grid_workspace_bytes(batch, lv["n"], lv["m"]), dev)
             self.fps.append(fp)
         self.main = torch.cuda.Stream(device=dev, priority=-1) if own_streams else None
         self.sides = [torch.cuda.Stream(device=dev) for _ in self.levels]
         self.side = self.sides[0]
-        self.launches_per_step = len(self.levels) * (6 if attention else 5) + len(self.fps) * 3
+        # kernels per forward: FPS, gather, ball (+ grid build), group x2, attention per SA level; three_nn (+ grid build
+        # when the known cloud has >= 64 points), weights, interpolate per FP level
+        self.launches_per_step = len(self.levels) * ((6 if attention else 5) + (2 if grid else 0) -
+                                                     (1 if fuse_gather else 0)) + \
+            sum(3 + (2 if grid and fp["m"] >= 64 else 0) for fp in self.fps)
         self._graph = None
 
     # ---- inputs / outputs ----------------------------------------------------------------------------------
@@ -140,8 +152,12 @@ class ScanNetGeometry:
         L, B, p = self.L, self.B, _lib.ptr
         st = ctypes.c_void_p(side.cuda_stream)
         n, m, ns, cin = lv["n"], lv["m"], lv["ns"], lv["cin"]
-        run("query_ball_sa%d" % (li + 1), side, lambda: L.pc_query_ball(
-            B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), st))
+        if self.grid:
+            run("query_ball_sa%d" % (li + 1), side, lambda: L.pc_query_ball_grid(
+                B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), p(lv["ball_ws"]), st))
+        else:
+            run("query_ball_sa%d" % (li + 1), side, lambda: L.pc_query_ball(
+                B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), st))
         run("group_xyz_sa%d" % (li + 1), side, lambda: L.pc_group_point(
             B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
         run("group_feat_sa%d" % (li + 1), side, lambda: L.pc_group_point(
@@ -155,8 +171,12 @@ class ScanNetGeometry:
         st = ctypes.c_void_p(side.cuda_stream)
         n, m, c = fp["n"], fp["m"], fp["c"]
         tag = "fp%d" % (4 - fp["level"])  # FP1 is the deepest level (pointnet2_sem_seg_attention.py:46-53)
-        run("three_nn_" + tag, side, lambda: L.pc_three_nn(
-            B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
+        if self.grid:
+            run("three_nn_" + tag, side, lambda: L.pc_three_nn_grid(
+                B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), p(fp["nn_ws"]), st))
+        else:
+            run("three_nn_" + tag, side, lambda: L.pc_three_nn(
+                B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
         run("three_weights_" + tag, side, lambda: L.pc_three_weights(B * n, p(fp["dist"]), p(fp["w"]), st))
         run("three_interpolate_" + tag, side, lambda: L.pc_three_interpolate(
             B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
@@ -181,16 +201,22 @@ class ScanNetGeometry:
             else:
                 _c(call())
 
+        parts = self.parts
         for li, lv in enumerate(self.levels):
             side = self.sides[li] if overlap else main
-            run("fps_sa%d" % (li + 1), main, lambda: L.pc_fps(
-                B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), s_main))
-            run("gather_sa%d" % (li + 1), main, lambda: L.pc_gather_point(
-                B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
+            if "fps" in parts and self.fuse_gather:   # FPS writes the sampled coordinates itself: one launch, not two
+                run("fps_sa%d" % (li + 1), main, lambda: L.pc_fps_gather(
+                    B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
+            elif "fps" in parts:
+                run("fps_sa%d" % (li + 1), main, lambda: L.pc_fps(
+                    B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_ws"]), p(lv["fps_idx"]), s_main))
+                run("gather_sa%d" % (li + 1), main, lambda: L.pc_gather_point(
+                    B, lv["n"], lv["m"], p(lv["xyz"]), p(lv["fps_idx"]), p(lv["new_xyz"]), s_main))
             if overlap:
                 side.wait_stream(main)  # also orders this step's side work after the previous step's join
-            self._sa_rest(lv, li, side, run)
-            self._fp(fp_of[li], side, run)
+            if "side" in parts:
+                self._sa_rest(lv, li, side, run)
+                self._fp(fp_of[li], side, run)
         if overlap:
             for side in self.sides:
                 main.wait_stream(side)
@@ -198,8 +224,8 @@ class ScanNetGeometry:
     def op_names(self):
         names = []
         for li in range(len(self.levels)):
-            names += ["fps_sa%d" % (li + 1), "gather_sa%d" % (li + 1), "query_ball_sa%d" % (li + 1),
-                      "group_xyz_sa%d" % (li + 1), "group_feat_sa%d" % (li + 1)]
+            names += ["fps_sa%d" % (li + 1)] + ([] if self.fuse_gather else ["gather_sa%d" % (li + 1)]) + \
+                     ["query_ball_sa%d" % (li + 1), "group_xyz_sa%d" % (li + 1), "group_feat_sa%d" % (li + 1)]
             if self.attention:
                 names.append("attention_sa%d" % (li + 1))
         for fp in self.fps:

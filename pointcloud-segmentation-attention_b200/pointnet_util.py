@@ -9,13 +9,16 @@ import torch
 
 from .tf_grouping import group_point, knn_point, query_ball_point
 from .tf_interpolate import three_interpolate, three_nn, three_weights
-from .tf_sampling import farthest_point_sample, gather_point
+from .tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True):
     """Same inputs / outputs as pointnet_util.py:16-58:
     returns new_xyz (B,npoint,3), new_points (B,npoint,nsample,3+C), idx (B,npoint,nsample), grouped_xyz."""
-    new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+    if xyz.requires_grad:  # keep GatherPoint's registered gradient in the graph (tf_sampling.py:44-48)
+        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+    else:                  # one launch for the pair
+        _, new_xyz = farthest_point_sample_and_gather(npoint, xyz)
     if knn:
         _, idx = knn_point(nsample, xyz, new_xyz)
     else:

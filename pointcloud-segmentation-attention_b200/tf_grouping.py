@@ -11,6 +11,9 @@ import torch
 from . import _lib
 
 
+USE_GRID = True  # module switch: cell-grid ball query (default) vs the all-pairs kernel; outputs are identical
+
+
 def query_ball_point(radius, nsample, xyz1, xyz2):
     """xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32."""
     if not float(radius) > 0:
@@ -27,8 +30,14 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     m = xyz2.shape[1]
     idx = torch.empty((b, m, int(nsample)), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
-    rc = _lib.lib().pc_query_ball(b, n, m, float(radius), int(nsample), _lib.ptr(xyz1), _lib.ptr(xyz2),
-                                  _lib.ptr(idx), _lib.ptr(cnt), _lib.stream())
+    L = _lib.lib()
+    if USE_GRID:  # same outputs bit for bit; a query only meets its 3x3x3 cell neighbourhood (csrc/grid.cu)
+        ws = _lib.workspace(L.pc_query_ball_grid_workspace_bytes(b, n, m), xyz1.device)
+        rc = L.pc_query_ball_grid(b, n, m, float(radius), int(nsample), _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx),
+                                  _lib.ptr(cnt), _lib.ptr(ws), _lib.stream())
+    else:         # all-pairs kernel, the reference launcher's exact signature (csrc/ball_query.cu)
+        rc = L.pc_query_ball(b, n, m, float(radius), int(nsample), _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(idx),
+                             _lib.ptr(cnt), _lib.stream())
     _lib.check(rc, "pc_query_ball")
     return idx, cnt
 

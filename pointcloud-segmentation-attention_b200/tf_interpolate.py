@@ -12,6 +12,9 @@ import torch
 from . import _lib
 
 
+USE_GRID = True  # module switch: cell-grid three_nn (default) vs the all-pairs kernel; outputs are identical
+
+
 def three_nn(xyz1, xyz2):
     """xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) f32 squared, idx (b,n,3) i32."""
     if xyz1.dim() != 3 or xyz1.shape[2] != 3:
@@ -24,7 +27,13 @@ def three_nn(xyz1, xyz2):
     m = xyz2.shape[1]
     dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
     idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
-    rc = _lib.lib().pc_three_nn(b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist), _lib.ptr(idx), _lib.stream())
+    L = _lib.lib()
+    if USE_GRID:  # same outputs bit for bit; cell rings around the query instead of all m known points (csrc/grid.cu)
+        ws = _lib.workspace(L.pc_three_nn_grid_workspace_bytes(b, n, m), xyz1.device)
+        rc = L.pc_three_nn_grid(b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist), _lib.ptr(idx), _lib.ptr(ws),
+                                _lib.stream())
+    else:         # all-pairs kernel (csrc/interpolate.cu)
+        rc = L.pc_three_nn(b, n, m, _lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist), _lib.ptr(idx), _lib.stream())
     _lib.check(rc, "pc_three_nn")
     return dist, idx
 

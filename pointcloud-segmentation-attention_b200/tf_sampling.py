@@ -26,6 +26,24 @@ def farthest_point_sample(npoint, inp):
     return out
 
 
+def farthest_point_sample_and_gather(npoint, inp):
+    """farthest_point_sample followed by gather_point on the same cloud (pointnet_util.py:34) in ONE kernel launch:
+    inp (b,n,3) -> (idx (b,npoint) i32, new_xyz (b,npoint,3) f32).  No gradient flows to inp (as for FPS)."""
+    if int(npoint) <= 0:
+        raise ValueError("FarthestPointSample expects positive npoint")
+    if inp.dim() != 3 or inp.shape[2] != 3:
+        raise ValueError("FarthestPointSample expects (batch_size,num_points,3) inp shape")
+    inp = _lib.cuda_f32(inp.detach(), "inp")
+    b, n, _ = inp.shape
+    out = torch.empty((b, int(npoint)), dtype=torch.int32, device=inp.device)
+    new_xyz = torch.empty((b, int(npoint), 3), dtype=torch.float32, device=inp.device)
+    L = _lib.lib()
+    ws = _lib.workspace(L.pc_fps_workspace_bytes(b, n, int(npoint)), inp.device)
+    rc = L.pc_fps_gather(b, n, int(npoint), _lib.ptr(inp), _lib.ptr(ws), _lib.ptr(out), _lib.ptr(new_xyz), _lib.stream())
+    _lib.check(rc, "pc_fps_gather", "FarthestPointSample expects (batch_size,num_points,3) inp shape")
+    return out, new_xyz
+
+
 class _GatherPoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, idx):

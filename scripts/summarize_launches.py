@@ -16,8 +16,15 @@ for r in rows:
     d = dict(zip(hdr, r))
     if d.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    v = float(d["Metric Value"].replace(",", ""))
+    try:
+        v = float(d["Metric Value"].replace(",", ""))
+    except ValueError:
+        continue
+    if v != v:
+        continue
     v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}[d["Metric Unit"]]
+    if "pc::" not in d["Kernel Name"]:  # torch fill / randn launches of the bench set-up are not part of a step
+        continue
     key = (d["Kernel Name"][:90], d["Block Size"], d["Grid Size"])
     a = agg.setdefault(key, [0, 0.0])
     a[0] += 1

@@ -26,6 +26,17 @@ def same(t, a):
     return np.array_equal(npy(t), a)
 
 
+@pytest.fixture(autouse=True, params=["grid", "allpairs"])
+def neighbour_search_mode(request):
+    """Every test runs twice: with the cell-grid ball query / three_nn (the default path) and with the all-pairs
+    kernels behind the reference launchers' exact signatures.  Both must match the oracle bit for bit."""
+    from pcops_b200 import tf_grouping, tf_interpolate
+    saved = tf_grouping.USE_GRID, tf_interpolate.USE_GRID
+    tf_grouping.USE_GRID = tf_interpolate.USE_GRID = (request.param == "grid")
+    yield request.param
+    tf_grouping.USE_GRID, tf_interpolate.USE_GRID = saved
+
+
 @pytest.fixture(scope="module")
 def refgpu():
     if not ref.available_gpu(True):
@@ -39,6 +50,16 @@ def refgpu():
 def test_fps_matches_oracle(n, m):
     xyz, _ = synth.scannet_batch(n + m, 3, n)
     assert same(ops.farthest_point_sample(m, cu(xyz)), cpu.farthest_point_sample(m, xyz))
+
+
+def test_fps_gather_fused_equals_the_pair():
+    for n, m in ((8192, 1024), (1024, 256), (200, 64), (20000, 50)):
+        xyz, _ = synth.scannet_batch(n, 2, n)
+        x = cu(xyz)
+        idx, new_xyz = ops.farthest_point_sample_and_gather(m, x)
+        assert torch.equal(idx, ops.farthest_point_sample(m, x))
+        assert torch.equal(new_xyz, ops.gather_point(x, idx))
+        assert same(idx, cpu.farthest_point_sample(m, xyz))
 
 
 def test_fps_ties_duplicates_and_big_batches():
@@ -347,3 +368,49 @@ def test_sample_and_group_and_fp_front_end():
     assert same(out, want)
     _, npk, idxk, _ = ops.sample_and_group(256, 0.2, 16, xyz, None, knn=True)
     assert same(idxk, cpu.knn_point(16, xyz_np, nx)[1])
+
+
+# -------------------------------------------------------------------- cell-grid paths: adversarial geometry
+def _check_ball_and_nn(xyz1, xyz2, r, ns):
+    idx, cnt = ops.query_ball_point(r, ns, cu(xyz1), cu(xyz2))
+    oi, oc = cpu.query_ball_point(r, ns, xyz1, xyz2)
+    assert same(idx, oi) and same(cnt, oc)
+    d, i3 = ops.three_nn(cu(xyz2), cu(xyz1))      # xyz2 as the dense cloud, xyz1 as the known one
+    od, o3 = cpu.three_nn(xyz2, xyz1)
+    assert same(d, od) and same(i3, o3)
+    d, i3 = ops.three_nn(cu(xyz1), cu(xyz2))      # and the other way round (queries may leave the known box)
+    od, o3 = cpu.three_nn(xyz1, xyz2)
+    assert same(d, od) and same(i3, o3)
+
+
+def test_grid_paths_on_adversarial_clouds():
+    rng = np.random.default_rng(5)
+    # (a) heavy duplicates + exact ties: points on a coarse lattice, queries on lattice points
+    lat = rng.integers(0, 6, size=(2, 700, 3)).astype(np.float32) * 0.125
+    _check_ball_and_nn(lat, lat[:, :90].copy(), 0.25, 16)
+    # (b) planar cloud (zero extent along z) and a line (zero extent along two axes)
+    plane = rng.random((2, 600, 3)).astype(np.float32)
+    plane[..., 2] = 0.5
+    _check_ball_and_nn(plane, rng.random((2, 70, 3)).astype(np.float32), 0.2, 32)
+    line = np.zeros((1, 300, 3), np.float32)
+    line[..., 0] = rng.random((1, 300)).astype(np.float32)
+    _check_ball_and_nn(line, line[:, ::4].copy(), 0.05, 8)
+    # (c) two far-apart clusters: rings run out for queries between them -> whole-cloud scan
+    a = rng.normal(0, 0.01, size=(1, 400, 3)).astype(np.float32)
+    b = rng.normal(0, 0.01, size=(1, 400, 3)).astype(np.float32) + 5.0
+    both = np.concatenate([a, b], 1)
+    q = np.concatenate([rng.random((1, 64, 3)).astype(np.float32) * 5.0, both[:, ::10]], 1)
+    _check_ball_and_nn(both, q, 0.02, 32)
+    # (d) radius larger than the scene (one cell), radius smaller than any spacing (empty balls), n % 32 != 0
+    u = rng.random((2, 333, 3)).astype(np.float32)
+    _check_ball_and_nn(u, u[:, :50].copy(), 10.0, 32)
+    _check_ball_and_nn(u, rng.random((2, 50, 3)).astype(np.float32), 1e-4, 4)
+    # (e) all points identical
+    same_pt = np.full((1, 200, 3), 0.3, np.float32)
+    _check_ball_and_nn(same_pt, same_pt[:, :70].copy(), 0.1, 32)
+    # (f) ScanNet-shaped chunk, every SA radius
+    xyz, _ = synth.scannet_batch(77, 2, 4096)
+    fi = cpu.farthest_point_sample(512, xyz)
+    nx = cpu.gather_point(xyz, fi)
+    for r in (0.1, 0.2, 0.4, 0.8):
+        _check_ball_and_nn(xyz, nx, r, 32)

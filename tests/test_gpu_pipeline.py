@@ -36,15 +36,16 @@ def check_against_oracle(pipe, xyz_np, feat_np):
         assert np.array_equal(npy(fp["out"]), cpu.three_interpolate(npy(fp["points2"]), i3, w))
 
 
-def test_pipeline_matches_oracle_eager_and_graph():
+@pytest.mark.parametrize("grid,fuse", [(True, True), (False, False)])
+def test_pipeline_matches_oracle_eager_and_graph(grid, fuse):
     B = 2
     xyz_np, feat_np = synth.scannet_batch(300, B, 8192)
-    pipe = ScanNetGeometry(B)
+    pipe = ScanNetGeometry(B, grid=grid, fuse_gather=fuse)
     pipe.set_inputs(torch.from_numpy(xyz_np), torch.from_numpy(feat_np))
     pipe.forward(overlap=False)
     torch.cuda.synchronize()
     check_against_oracle(pipe, xyz_np, feat_np)
-    assert pipe.launches_per_step == 36
+    assert pipe.launches_per_step == (46 if grid else 36)   # grid: +2 builds per binned op, -1 per fused gather
 
     eager = [t.clone() for t in pipe.result_tensors()] + [fp["out"].clone() for fp in pipe.fps]
     pipe.capture(overlap=True)
