@@ -19,7 +19,10 @@
 // A scene cannot go faster on one SM, and splitting it over a cluster buys less than the DSMEM exchange costs at this
 // size -- so throughput comes from running scenes, and batches, side by side.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pc {
 namespace {
@@ -187,6 +190,152 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 8192 < n <= 16 * 8192: one THREAD-BLOCK CLUSTER per scene.  CTA r of the cluster keeps points [8192 r, 8192 (r+1))
+// on chip exactly as the single-CTA kernel does (8 warps x 32 points, same slot order, same one-barrier CTA-level
+// winner); the CTA winners then meet through distributed shared memory: every CTA writes its (value, key, x, y, z)
+// record into slot [parity][r] of EVERY CTA of the cluster (st.shared::cluster), one cluster barrier, and every CTA
+// reduces the C records locally -- the record carries the winner's coordinates, so the next round starts without
+// another remote read.  No global-memory traffic inside the m-1 rounds; the alternative for these sizes (running
+// minima streamed through L2, fps_stream_kernel) moves 16 n bytes per round.
+constexpr int kSlice = 8192;
+struct __align__(16) FpsRec { int value, key; float x, y; float z; int pad[3]; };
+
+template <int CL>
+__global__ void __maxnreg__(200)
+fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out,
+                   float *__restrict__ out_xyz) {
+  constexpr int P = 32, T = 256, H = P / 2, G = 8, NG = P / G, nwarps = T / 32;
+  using Map = FpsMap<P, T>;
+  extern __shared__ float s_xyz[];  // this CTA's slice, up to kSlice * 3
+  __shared__ int2 s_pair[2][32];
+  __shared__ FpsRec s_rec[2][16];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int scene = blockIdx.x / CL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const f32x2 one2 = pack2(one, one);
+  const float *p = xyz + (size_t)scene * n * 3;
+  int *o = out + (size_t)scene * m;
+  float *oxyz = out_xyz ? out_xyz + (size_t)scene * m * 3 : nullptr;
+  const int base = rank * kSlice, sn = max(0, min(kSlice, n - base));  // this CTA's points [base, base + sn)
+  for (int i = tid; i < sn * 3; i += T) s_xyz[i] = p[(size_t)base * 3 + i];
+  float cx = p[0], cy = p[1], cz = p[2];  // first centre = point 0 (tf_sampling_g.cu:114-116)
+  if (rank == 0 && tid == 0) {
+    o[0] = 0;
+    if (oxyz) { oxyz[0] = cx; oxyz[1] = cy; oxyz[2] = cz; }
+  }
+  __syncthreads();
+
+  f32x2 px[H], py[H], pz[H];
+  float td[P];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    float x[2], y[2], z[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * h + e, k = Map::k_of(tid, i);  // local index; global index = base + k, same (k mod 512)
+      if (k < sn) {
+        x[e] = s_xyz[k * 3 + 0]; y[e] = s_xyz[k * 3 + 1]; z[e] = s_xyz[k * 3 + 2];
+        td[i] = 1e38f;
+      } else {
+        x[e] = y[e] = z[e] = 0.0f;
+        td[i] = -1.0f;
+      }
+    }
+    px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]);
+  }
+  cluster.sync();  // every CTA's s_rec is addressable before the first remote store
+
+  int par = 1;
+  for (int j = 1; j < m; ++j) {
+    const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz);
+    float gm[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      gm[g] = -1.0f;
+#pragma unroll
+      for (int h = g * G / 2; h < (g + 1) * G / 2; ++h) {
+        float d0, d1;
+        unpack2(sqdist3_x2(px[h], py[h], pz[h], cx2, cy2, cz2, one2), d0, d1);
+        td[2 * h] = fminf(d0, td[2 * h]);
+        td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+        gm[g] = fmaxf(gm[g], fmaxf(td[2 * h], td[2 * h + 1]));
+      }
+    }
+    float vmax = gm[0];
+#pragma unroll
+    for (int g = 1; g < NG; ++g) vmax = fmaxf(vmax, gm[g]);
+    const int vb = __float_as_int(vmax);
+    const int wmax = __reduce_max_sync(PC_FULL_MASK, vb);
+    int tb = INT_MAX;
+    if (vb == wmax) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (tb == INT_MAX && __float_as_int(gm[g]) == wmax) {
+#pragma unroll
+          for (int e = G - 1; e >= 0; --e)
+            if (__float_as_int(td[g * G + e]) == wmax) tb = tie_key(base + Map::k_of(tid, g * G + e));
+        }
+      }
+    }
+    const int wkey = __reduce_min_sync(PC_FULL_MASK, tb);
+    if (lane == 0) s_pair[par][warp] = make_int2(wmax, wkey);
+    __syncthreads();
+    const int2 pr = s_pair[par][lane < nwarps ? lane : 0];
+    const int cmax = __reduce_max_sync(PC_FULL_MASK, pr.x);
+    const int ckey = __reduce_min_sync(PC_FULL_MASK, pr.x == cmax ? pr.y : INT_MAX);
+    if (tid < CL) {  // thread i delivers this CTA's record to CTA i
+      FpsRec r;
+      r.value = cmax; r.key = ckey;
+      r.x = r.y = r.z = 0.0f;
+      if (cmax >= 0) {  // a CTA without live points reports (-1.0f bits): never the cluster winner
+        const int kl = tie_key_to_index(ckey) - base;
+        r.x = s_xyz[kl * 3 + 0]; r.y = s_xyz[kl * 3 + 1]; r.z = s_xyz[kl * 3 + 2];
+      }
+      FpsRec *dst = cluster.map_shared_rank(&s_rec[par][rank], tid);
+      *reinterpret_cast<int4 *>(dst) = make_int4(r.value, r.key, __float_as_int(r.x), __float_as_int(r.y));
+      dst->z = r.z;
+    }
+    cluster.sync();  // release the remote stores / acquire everyone else's
+    const FpsRec *rr = &s_rec[par][lane < CL ? lane : 0];
+    const int rv = rr->value, rk = rr->key;
+    const float rx = rr->x, ry = rr->y, rz = rr->z;
+    const int gmax = __reduce_max_sync(PC_FULL_MASK, rv);
+    const int gkey = __reduce_min_sync(PC_FULL_MASK, rv == gmax ? rk : INT_MAX);
+    const int src = __ffs(__ballot_sync(PC_FULL_MASK, rv == gmax && rk == gkey)) - 1;
+    cx = __shfl_sync(PC_FULL_MASK, rx, src);
+    cy = __shfl_sync(PC_FULL_MASK, ry, src);
+    cz = __shfl_sync(PC_FULL_MASK, rz, src);
+    par ^= 1;
+    if (rank == 0 && tid == 0) {
+      o[j] = tie_key_to_index(gkey);
+      if (oxyz) { oxyz[j * 3 + 0] = cx; oxyz[j * 3 + 1] = cy; oxyz[j * 3 + 2] = cz; }
+    }
+  }
+  cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
+}
+
+template <int CL>
+int launch_cluster(int b, int n, int m, const float *xyz, int *out, float *out_xyz, cudaStream_t st) {
+  const int sn = n < kSlice ? n : kSlice;
+  const size_t smem = (size_t)sn * 3 * sizeof(float);
+  PC_CUDA_TRY(allow_smem(fps_cluster_kernel<CL>, smem));
+  if (CL > 8) PC_CUDA_TRY(cudaFuncSetAttribute(fps_cluster_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)b * CL);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CL>, n, m, 1.0f, xyz, out, out_xyz));
+  return PC_OK;
+}
+
 // General sizes (n > 8192): running min-distances stream through a global workspace (b*n floats),
 // xyz is read through L1/L2.  Same reduction protocol as above.
 __global__ void __launch_bounds__(1024, 1)
@@ -250,7 +399,7 @@ int launch_onchip(int b, int n, int m, const float *xyz, int *out, float *out_xy
 
 extern "C" size_t pc_fps_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 0;
-  if (n <= pc::kMaxRegPoints) return 0;
+  if (n <= 16 * pc::kMaxRegPoints) return 0;  // single CTA or one thread-block cluster per scene: all state on chip
   return (size_t)b * n * sizeof(float);
 }
 
@@ -281,6 +430,13 @@ extern "C" int pc_fps_gather(int b, int n, int m, const float *xyz, void *worksp
     if (shape < 0) { const char *e = getenv("PCOPS_FPS_SHAPE"); shape = e ? atoi(e) : 256; }
     if (shape == 512) return pc::launch_onchip<16, 512, false, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
+  }
+  if (n <= 16 * pc::kSlice && (long long)b * 16 < 0x7fffffffLL) {  // one cluster of 2 / 4 / 8 / 16 CTAs per scene
+    const int slices = (n + pc::kSlice - 1) / pc::kSlice;
+    if (slices <= 2) return pc::launch_cluster<2>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (slices <= 4) return pc::launch_cluster<4>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (slices <= 8) return pc::launch_cluster<8>(b, n, m, xyz, out_idx, out_xyz, st);
+    return pc::launch_cluster<16>(b, n, m, xyz, out_idx, out_xyz, st);
   }
   if (!workspace) return PC_ERR_WORKSPACE;
   pc::fps_stream_kernel<<<b, 1024, 0, st>>>(b, n, m, xyz, (float *)workspace, out_idx);

@@ -72,9 +72,23 @@ def test_fps_ties_duplicates_and_big_batches():
     assert same(ops.farthest_point_sample(16, cu(small)), cpu.farthest_point_sample(16, small))   # m > n
 
 
-def test_fps_streaming_path_above_8192_points():
-    xyz, _ = synth.scannet_batch(77, 2, 20000)
-    assert same(ops.farthest_point_sample(96, cu(xyz)), cpu.farthest_point_sample(96, xyz))
+@pytest.mark.parametrize("n,m,b", [(8193, 64, 2), (16384, 80, 3), (16385, 80, 1), (20000, 96, 2), (40000, 64, 2),
+                                   (70000, 48, 1), (131072, 40, 1), (140000, 24, 1)])
+def test_fps_cluster_and_streaming_paths_above_8192_points(n, m, b):
+    """8192 < n <= 131072: one thread-block cluster (2/4/8/16 CTAs, DSMEM exchange) per scene; beyond: streaming."""
+    xyz, _ = synth.scannet_batch(n % 1000, b, n)
+    x = cu(xyz)
+    idx, new_xyz = ops.farthest_point_sample_and_gather(m, x)
+    assert same(idx, cpu.farthest_point_sample(m, xyz))
+    assert torch.equal(new_xyz, ops.gather_point(x, idx))
+
+
+def test_fps_cluster_ties_across_ctas():
+    """Exact duplicates placed in different 8192-point slices: the (k mod 512, k) tie-break must hold cluster-wide."""
+    rng = np.random.default_rng(3)
+    base = rng.random((1, 600, 3)).astype(np.float32)
+    xyz = np.tile(base, (1, 30, 1))[:, :17000]          # every point repeated ~28 times across slices
+    assert same(ops.farthest_point_sample(300, cu(xyz)), cpu.farthest_point_sample(300, xyz))
 
 
 def test_fps_matches_reference_cuda_kernel(refgpu):
