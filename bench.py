@@ -385,17 +385,32 @@ def main():
                 "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms,
                 "peak_source": "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock)" % (nsm, sm_max)}
 
-    rooflines, op_ms = {}, {}
+    rooflines, op_ms, grid_ms = {}, {}, {}
     if not args.skip_probe:
-        allp = {n: [] for n in pipe.op_names()}
-        for i in range(min(K, 10)):      # one pipeline instance alone, eager, ONE stream: every op's stand-alone duration
-            pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
-            pipe.forward(False, allp)
-            torch.cuda.synchronize(dev)
-        for n, evs in allp.items():
-            d = sorted(a.elapsed_time(b) for a, b in evs)
-            op_ms[n] = d[len(d) // 2]
-            rooflines[n] = roof(n, op_ms[n])
+        # Every op's stand-alone duration: one pipeline instance alone, eager, ONE stream.  The table is taken with the
+        # reference-signature ops (all-pairs ball query / three_nn, separate gather), whose algorithmic op counts the
+        # fractions are computed from; the durations of the cell-grid variants the timed pipeline uses are listed
+        # beside them in `grid_variants_ms`.
+        def probe(pl):
+            allp = {n: [] for n in pl.op_names()}
+            for i in range(min(K, 10)):
+                pl.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+                pl.forward(False, allp)
+                torch.cuda.synchronize(dev)
+            return {n: sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2] for n, evs in allp.items()}
+        ref_pipe = ScanNetGeometry(B, NPOINTS, 6, dev, attention=bool(args.attention), seed=999, own_streams=True,
+                                   grid=False, fuse_gather=False)
+        for i in range(3):
+            ref_pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+            ref_pipe.forward(False)
+        torch.cuda.synchronize(dev)
+        op_ms = probe(ref_pipe)
+        for n, ms in op_ms.items():
+            rooflines[n] = roof(n, ms)
+        del ref_pipe
+        if args.grid:
+            g = probe(pipe)
+            grid_ms = {n: ms for n, ms in g.items() if n.startswith(("query_ball", "three_nn", "fps"))}
     if probes:
         d = [a.elapsed_time(b) for a, b in probes[top_guess]]
         top_ms = sum(d) / len(d)
@@ -463,6 +478,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "rooflines": rooflines,
+        "grid_variants_ms": grid_ms,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

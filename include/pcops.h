@@ -170,6 +170,26 @@ PC_API int pc_three_interpolate_grad(int b, int n, int c, int m, const float *gr
                               const float *weight, float *grad_points, void *workspace, pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Fused layer front ends (reference: the stock-TF glue around the ops in utils/pointnet_util.py)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* The grouping half of sample_and_group (pointnet_util.py:39-52, use_xyz=True) in one pass:
+ *   new_points (b,m,nsample,3+c) = concat(xyz[idx] - new_xyz[:, :, None, :], points[idx])
+ *   grouped_xyz (b,m,nsample,3)  = xyz[idx] - new_xyz[:, :, None, :]            (optional, may be NULL)
+ * xyz (b,n,3), points (b,n,c) or NULL with c = 0, idx (b,m,nsample), new_xyz (b,m,3).  Bit-identical to
+ * pc_group_point x2 + an fp32 subtract + a concat. */
+PC_API int pc_sa_group(int b, int n, int c, int m, int nsample, const float *xyz, const float *points, const int *idx,
+                const float *new_xyz, float *new_points, float *grouped_xyz, pc_stream_t stream);
+
+/* The interpolation half of pointnet_fp_module (pointnet_util.py:219-226) in one pass:
+ *   weight = inverse-distance weights of dist (as pc_three_weights);  interpolated = three_interpolate(points2, idx, weight)
+ *   out (b,n,c2+c1) = concat(interpolated, points1);  weight (b,n,3) is also written when not NULL (the backward needs it)
+ * dist, idx (b,n,3) from three_nn; points2 (b,m,c2); points1 (b,n,c1) or NULL with c1 = 0.  Bit-identical to the
+ * op-by-op composition. */
+PC_API int pc_fp_interpolate(int b, int n, int m, int c2, int c1, const float *dist, const int *idx, const float *points2,
+                      const float *points1, float *out, float *weight, pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Per-neighbourhood attention contraction (reference: attention_points/attention_scannet/attention_layer.py:35-42,
  * i.e. AttentionLayer.call after its three Dense projections)
  * ------------------------------------------------------------------------------------------------------------- */

@@ -1,0 +1,148 @@
+// Fused front ends of the two PointNet++ layer types: what sample_and_group / pointnet_fp_module build around the
+// geometry ops with stock TF elementwise ops and concats (reference pointnet2_tensorflow/utils/pointnet_util.py).
+//
+// pc_sa_group      = group_point(xyz, idx) - tile(new_xyz)  (+)  group_point(points, idx)  -> concat   (:39-52)
+//                    one pass writes new_points (b,m,ns,3+c) and the centred grouped_xyz (b,m,ns,3); the reference
+//                    runs two GroupPoint ops, a tile, a subtract and a concat over five intermediate tensors.
+// pc_fp_interpolate = inverse-distance weights (:219-222) -> three_interpolate (:223) -> concat with the skip features
+//                    (:226); one pass writes (b,n,c2+c1) and, optionally, the (b,n,3) weights the backward needs.
+// Both are HBM-write bound gathers: consecutive threads produce consecutive output floats (4 per thread, one 128-bit
+// store when the base allows), the gathered rows come out of L2.  Values are bit-identical to the op-by-op
+// composition: the subtraction and the weight arithmetic are the same single un-fused fp32 operations.
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+__global__ void __launch_bounds__(256)
+sa_group_kernel(size_t total, int n, int c, int m, int ns, bool vec_store, const float *__restrict__ xyz,
+                const float *__restrict__ points, const int *__restrict__ idx, const float *__restrict__ new_xyz,
+                float *__restrict__ out, float *__restrict__ gxyz) {
+  const int W = 3 + c;
+  const size_t nchunks = (total + 3) / 4;
+  for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = ch * 4;
+    size_t row = e0 / W;  // (scene*m + j)*ns + k
+    int col = (int)(e0 - row * W);
+    float v[4];
+    int src = -1;
+    size_t scene = 0, q = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v[t] = 0.0f;
+      if (e0 + t < total) {
+        if (src < 0) {
+          src = __ldg(idx + row);
+          q = row / ns;        // scene*m + j
+          scene = q / m;
+        }
+        if (col < 3) {
+          const float g = __fsub_rn(__ldg(xyz + (scene * n + src) * 3 + col), __ldg(new_xyz + q * 3 + col));
+          v[t] = g;
+          if (gxyz) gxyz[row * 3 + col] = g;
+        } else {
+          v[t] = __ldg(points + (scene * n + src) * (size_t)c + (col - 3));
+        }
+      }
+      if (++col == W) { col = 0; ++row; src = -1; }
+    }
+    if (vec_store && e0 + 3 < total) {
+      __stcs(reinterpret_cast<float4 *>(out + e0), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (e0 + t < total) out[e0 + t] = v[t];
+    }
+  }
+}
+
+__device__ __forceinline__ void fp_weights(const float *__restrict__ dist, size_t row, float &w1, float &w2, float &w3) {
+  // pointnet_util.py:219-222, same operation order as three_weights_kernel (interpolate.cu)
+  const float d0 = fmaxf(__ldg(dist + row * 3 + 0), 1e-10f), d1 = fmaxf(__ldg(dist + row * 3 + 1), 1e-10f),
+              d2 = fmaxf(__ldg(dist + row * 3 + 2), 1e-10f);
+  const float r0 = __fdiv_rn(1.0f, d0), r1 = __fdiv_rn(1.0f, d1), r2 = __fdiv_rn(1.0f, d2);
+  const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+  w1 = __fdiv_rn(r0, norm); w2 = __fdiv_rn(r1, norm); w3 = __fdiv_rn(r2, norm);
+}
+
+__global__ void __launch_bounds__(256)
+fp_interp_kernel(size_t total, int n, int m, int c2, int c1, bool vec_store, const float *__restrict__ dist,
+                 const int *__restrict__ idx, const float *__restrict__ points2, const float *__restrict__ points1,
+                 float *__restrict__ out, float *__restrict__ weight) {
+  const int W = c2 + c1;
+  const size_t nchunks = (total + 3) / 4;
+  for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = ch * 4;
+    size_t row = e0 / W;  // scene*n + j
+    int col = (int)(e0 - row * W);
+    float v[4];
+    bool have = false;
+    float w1 = 0.f, w2 = 0.f, w3 = 0.f;
+    const float *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      v[t] = 0.0f;
+      if (e0 + t < total) {
+        if (col < c2) {
+          if (!have) {
+            have = true;
+            fp_weights(dist, row, w1, w2, w3);
+            const size_t scene = row / n;
+            const float *base = points2 + scene * (size_t)m * c2;
+            p1 = base + (size_t)__ldg(idx + row * 3 + 0) * c2;
+            p2 = base + (size_t)__ldg(idx + row * 3 + 1) * c2;
+            p3 = base + (size_t)__ldg(idx + row * 3 + 2) * c2;
+            if (weight && col == 0) { weight[row * 3 + 0] = w1; weight[row * 3 + 1] = w2; weight[row * 3 + 2] = w3; }
+          }
+          // tf_interpolate.cpp:119: p1*w1 + p2*w2 + p3*w3, left to right, un-fused
+          v[t] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(p1 + col), w1), __fmul_rn(__ldg(p2 + col), w2)),
+                           __fmul_rn(__ldg(p3 + col), w3));
+        } else {
+          v[t] = __ldg(points1 + row * (size_t)c1 + (col - c2));
+        }
+      }
+      if (++col == W) { col = 0; ++row; have = false; }
+    }
+    if (vec_store && e0 + 3 < total) {
+      __stcs(reinterpret_cast<float4 *>(out + e0), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (e0 + t < total) out[e0 + t] = v[t];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace pc
+
+extern "C" int pc_sa_group(int b, int n, int c, int m, int nsample, const float *xyz, const float *points,
+                           const int *idx, const float *new_xyz, float *new_points, float *grouped_xyz,
+                           pc_stream_t stream) {
+  if (b < 0 || n < 0 || c < 0 || m < 0 || nsample < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || m == 0 || nsample == 0) return PC_OK;
+  if (n == 0 || !xyz || !idx || !new_xyz || !new_points || (c > 0 && !points)) return PC_ERR_INVALID_ARGUMENT;
+  const size_t total = (size_t)b * m * nsample * (3 + c);
+  size_t blocks = ((total + 3) / 4 + 255) / 256;
+  const size_t cap = (size_t)pc::num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  pc::sa_group_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, n, c, m, nsample, pc::aligned16(new_points),
+                                                                        xyz, points, idx, new_xyz, new_points,
+                                                                        grouped_xyz);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int pc_fp_interpolate(int b, int n, int m, int c2, int c1, const float *dist, const int *idx,
+                                 const float *points2, const float *points1, float *out, float *weight,
+                                 pc_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c2 < 0 || c1 < 0) return PC_ERR_INVALID_ARGUMENT;
+  if (b == 0 || n == 0 || c2 + c1 == 0) return PC_OK;
+  if (!out || (c2 > 0 && (m == 0 || !dist || !idx || !points2)) || (c1 > 0 && !points1)) return PC_ERR_INVALID_ARGUMENT;
+  const size_t total = (size_t)b * n * (c2 + c1);
+  size_t blocks = ((total + 3) / 4 + 255) / 256;
+  const size_t cap = (size_t)pc::num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  pc::fp_interp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, n, m, c2, c1, pc::aligned16(out), dist,
+                                                                         idx, points2, points1, out, weight);
+  PC_RETURN_LAUNCH_STATUS();
+}

@@ -428,3 +428,68 @@ def test_grid_paths_on_adversarial_clouds():
     nx = cpu.gather_point(xyz, fi)
     for r in (0.1, 0.2, 0.4, 0.8):
         _check_ball_and_nn(xyz, nx, r, 32)
+
+
+# -------------------------------------------------------------------- fused layer front ends (csrc/fused.cu)
+@pytest.mark.parametrize("c", [0, 6, 64, 5])
+def test_fused_sa_group_equals_composition_and_oracle(c):
+    from pcops_b200 import pointnet_util
+    xyz_np, _ = synth.scannet_batch(21 + c, 2, 2048)
+    feat_np = synth.features(c, 2, 2048, c) if c else None
+    xyz = cu(xyz_np)
+    feat = cu(feat_np).requires_grad_(True) if c else None
+    pointnet_util.FUSED = True
+    new_xyz, new_points, idx, gxyz = ops.sample_and_group(256, 0.2, 32, xyz, feat)
+    pointnet_util.FUSED = False
+    try:
+        feat2 = cu(feat_np).requires_grad_(True) if c else None
+        r_xyz, r_points, r_idx, r_gxyz = ops.sample_and_group(256, 0.2, 32, xyz, feat2)
+    finally:
+        pointnet_util.FUSED = True
+    assert torch.equal(new_xyz, r_xyz) and torch.equal(idx, r_idx)
+    assert torch.equal(new_points, r_points) and torch.equal(gxyz, r_gxyz)
+    oi = npy(idx)
+    want = cpu.group_point(xyz_np, oi) - npy(new_xyz)[:, :, None, :]
+    if c:
+        want = np.concatenate([want, cpu.group_point(feat_np, oi)], -1)
+    assert same(new_points, want)
+    if c:  # gradient to the features only, identical to GroupPointGrad on the feature slice
+        go = torch.randn_like(new_points)
+        new_points.backward(go)
+        r_points.backward(go)
+        assert torch.equal(feat.grad, feat2.grad)
+        assert same(feat.grad, cpu.group_point_grad(feat_np, oi, npy(go)[..., 3:]))
+
+
+@pytest.mark.parametrize("c2,c1", [(32, 6), (128, 0), (7, 3), (256, 128)])
+def test_fused_fp_interpolate_equals_composition_and_oracle(c2, c1):
+    from pcops_b200 import pointnet_util
+    xyz_np, _ = synth.scannet_batch(31 + c2, 2, 2048)
+    nx = cpu.gather_point(xyz_np, cpu.farthest_point_sample(256, xyz_np))
+    p2_np = synth.features(c2, 2, 256, c2)
+    p1_np = synth.features(c1 + 1, 2, 2048, c1) if c1 else None
+    xyz, new_xyz = cu(xyz_np), cu(nx)
+    p2 = cu(p2_np).requires_grad_(True)
+    p1 = cu(p1_np).requires_grad_(True) if c1 else None
+    out = ops.fp_interpolate(xyz, new_xyz, p1, p2)
+    pointnet_util.FUSED = False
+    try:
+        q2 = cu(p2_np).requires_grad_(True)
+        q1 = cu(p1_np).requires_grad_(True) if c1 else None
+        ref_out = ops.fp_interpolate(xyz, new_xyz, q1, q2)
+    finally:
+        pointnet_util.FUSED = True
+    assert torch.equal(out, ref_out)
+    od, o3 = cpu.three_nn(xyz_np, nx)
+    w = cpu.three_weights(od)
+    want = cpu.three_interpolate(p2_np, o3, w)
+    if c1:
+        want = np.concatenate([want, p1_np], 2)
+    assert same(out, want)
+    go = torch.randn_like(out)
+    out.backward(go)
+    ref_out.backward(go)
+    assert torch.equal(p2.grad, q2.grad)
+    assert same(p2.grad, cpu.three_interpolate_grad(p2_np, o3, w, npy(go)[..., :c2]))
+    if c1:
+        assert torch.equal(p1.grad, q1.grad)
