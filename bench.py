@@ -399,7 +399,7 @@ def main():
                 torch.cuda.synchronize(dev)
             return {n: sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2] for n, evs in allp.items()}
         ref_pipe = ScanNetGeometry(B, NPOINTS, 6, dev, attention=bool(args.attention), seed=999, own_streams=True,
-                                   grid=False, fuse_gather=False)
+                                   grid=False, fuse_gather=False, fuse_layers=False)
         for i in range(3):
             ref_pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
             ref_pipe.forward(False)

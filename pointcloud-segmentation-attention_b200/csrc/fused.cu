@@ -65,50 +65,58 @@ __device__ __forceinline__ void fp_weights(const float *__restrict__ dist, size_
   w1 = __fdiv_rn(r0, norm); w2 = __fdiv_rn(r1, norm); w3 = __fdiv_rn(r2, norm);
 }
 
+// A warp owns 32 consecutive dense points: lane r computes the weights and fetches the indices of point r ONCE (they
+// are shared by all c2 channels), then the warp walks the 32 rows, broadcasting (i1,i2,i3,w1,w2,w3) by shuffle while
+// its lanes cover the row's channels -- 128-bit loads / stores when the channel counts and bases allow.
 __global__ void __launch_bounds__(256)
-fp_interp_kernel(size_t total, int n, int m, int c2, int c1, bool vec_store, const float *__restrict__ dist,
+fp_interp_kernel(size_t rows, int n, int m, int c2, int c1, bool vec, const float *__restrict__ dist,
                  const int *__restrict__ idx, const float *__restrict__ points2, const float *__restrict__ points1,
                  float *__restrict__ out, float *__restrict__ weight) {
+  const int lane = threadIdx.x & 31;
   const int W = c2 + c1;
-  const size_t nchunks = (total + 3) / 4;
-  for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
-    const size_t e0 = ch * 4;
-    size_t row = e0 / W;  // scene*n + j
-    int col = (int)(e0 - row * W);
-    float v[4];
-    bool have = false;
+  const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t r0 = warp_global * 32; r0 < rows; r0 += nwarps * 32) {
+    const size_t my = r0 + lane;
     float w1 = 0.f, w2 = 0.f, w3 = 0.f;
-    const float *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      v[t] = 0.0f;
-      if (e0 + t < total) {
-        if (col < c2) {
-          if (!have) {
-            have = true;
-            fp_weights(dist, row, w1, w2, w3);
-            const size_t scene = row / n;
-            const float *base = points2 + scene * (size_t)m * c2;
-            p1 = base + (size_t)__ldg(idx + row * 3 + 0) * c2;
-            p2 = base + (size_t)__ldg(idx + row * 3 + 1) * c2;
-            p3 = base + (size_t)__ldg(idx + row * 3 + 2) * c2;
-            if (weight && col == 0) { weight[row * 3 + 0] = w1; weight[row * 3 + 1] = w2; weight[row * 3 + 2] = w3; }
-          }
-          // tf_interpolate.cpp:119: p1*w1 + p2*w2 + p3*w3, left to right, un-fused
-          v[t] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(p1 + col), w1), __fmul_rn(__ldg(p2 + col), w2)),
-                           __fmul_rn(__ldg(p3 + col), w3));
-        } else {
-          v[t] = __ldg(points1 + row * (size_t)c1 + (col - c2));
-        }
-      }
-      if (++col == W) { col = 0; ++row; have = false; }
+    int i1 = 0, i2 = 0, i3 = 0;
+    if (my < rows && c2 > 0) {
+      fp_weights(dist, my, w1, w2, w3);
+      i1 = __ldg(idx + my * 3 + 0); i2 = __ldg(idx + my * 3 + 1); i3 = __ldg(idx + my * 3 + 2);
+      if (weight) { weight[my * 3 + 0] = w1; weight[my * 3 + 1] = w2; weight[my * 3 + 2] = w3; }
     }
-    if (vec_store && e0 + 3 < total) {
-      __stcs(reinterpret_cast<float4 *>(out + e0), make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (e0 + t < total) out[e0 + t] = v[t];
+    const int nr = (int)min((size_t)32, rows - r0);
+    for (int rr = 0; rr < nr; ++rr) {
+      const size_t row = r0 + rr;
+      const float a1 = __shfl_sync(PC_FULL_MASK, w1, rr), a2 = __shfl_sync(PC_FULL_MASK, w2, rr),
+                  a3 = __shfl_sync(PC_FULL_MASK, w3, rr);
+      const int j1 = __shfl_sync(PC_FULL_MASK, i1, rr), j2 = __shfl_sync(PC_FULL_MASK, i2, rr),
+                j3 = __shfl_sync(PC_FULL_MASK, i3, rr);
+      const size_t scene = row / n;
+      const float *base = points2 + scene * (size_t)m * c2;
+      const float *p1 = base + (size_t)j1 * c2, *p2 = base + (size_t)j2 * c2, *p3 = base + (size_t)j3 * c2;
+      float *o = out + row * (size_t)W;
+      const float *s1 = points1 + row * (size_t)c1;
+      if (vec) {  // c2 % 4 == 0, c1 % 4 == 0, 16-byte aligned bases
+        for (int q = lane; q < c2 / 4; q += 32) {
+          const float4 x = __ldg(reinterpret_cast<const float4 *>(p1) + q), y = __ldg(reinterpret_cast<const float4 *>(p2) + q),
+                       z = __ldg(reinterpret_cast<const float4 *>(p3) + q);
+          // tf_interpolate.cpp:119: p1*w1 + p2*w2 + p3*w3, left to right, un-fused
+          float4 r;
+          r.x = __fadd_rn(__fadd_rn(__fmul_rn(x.x, a1), __fmul_rn(y.x, a2)), __fmul_rn(z.x, a3));
+          r.y = __fadd_rn(__fadd_rn(__fmul_rn(x.y, a1), __fmul_rn(y.y, a2)), __fmul_rn(z.y, a3));
+          r.z = __fadd_rn(__fadd_rn(__fmul_rn(x.z, a1), __fmul_rn(y.z, a2)), __fmul_rn(z.z, a3));
+          r.w = __fadd_rn(__fadd_rn(__fmul_rn(x.w, a1), __fmul_rn(y.w, a2)), __fmul_rn(z.w, a3));
+          __stcs(reinterpret_cast<float4 *>(o) + q, r);
+        }
+        for (int q = lane; q < c1 / 4; q += 32)
+          __stcs(reinterpret_cast<float4 *>(o + c2) + q, __ldg(reinterpret_cast<const float4 *>(s1) + q));
+      } else {
+        for (int col = lane; col < c2; col += 32)
+          o[col] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(p1 + col), a1), __fmul_rn(__ldg(p2 + col), a2)),
+                             __fmul_rn(__ldg(p3 + col), a3));
+        for (int col = lane; col < c1; col += 32) o[c2 + col] = __ldg(s1 + col);
+      }
     }
   }
 }
@@ -138,11 +146,13 @@ extern "C" int pc_fp_interpolate(int b, int n, int m, int c2, int c1, const floa
   if (b < 0 || n < 0 || m < 0 || c2 < 0 || c1 < 0) return PC_ERR_INVALID_ARGUMENT;
   if (b == 0 || n == 0 || c2 + c1 == 0) return PC_OK;
   if (!out || (c2 > 0 && (m == 0 || !dist || !idx || !points2)) || (c1 > 0 && !points1)) return PC_ERR_INVALID_ARGUMENT;
-  const size_t total = (size_t)b * n * (c2 + c1);
-  size_t blocks = ((total + 3) / 4 + 255) / 256;
+  const size_t rows = (size_t)b * n;
+  size_t blocks = ((rows + 31) / 32 + 7) / 8;  // 8 warps per CTA, one 32-row group per warp
   const size_t cap = (size_t)pc::num_sms() * 32;
   if (blocks > cap) blocks = cap;
-  pc::fp_interp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, n, m, c2, c1, pc::aligned16(out), dist,
-                                                                         idx, points2, points1, out, weight);
+  const bool vec = c2 % 4 == 0 && c1 % 4 == 0 && pc::aligned16(out) && pc::aligned16(points2) &&
+                   (c1 == 0 || pc::aligned16(points1));
+  pc::fp_interp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, n, m, c2, c1, vec, dist, idx, points2,
+                                                                         points1, out, weight);
   PC_RETURN_LAUNCH_STATUS();
 }

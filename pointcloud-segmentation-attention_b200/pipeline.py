@@ -36,12 +36,17 @@ KEY_DIM = 4  # attention_layer.py:256-258: heads = C // 4, key_dim = output_dim 
 
 class ScanNetGeometry:
     def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0, own_streams=False,
-                 grid=True, fuse_gather=True):
+                 grid=True, fuse_gather=True, fuse_layers=False):
         self.B, self.N, self.CF = batch, npoints, feat_channels
         # development knob (scripts only): which parts of the forward to enqueue, e.g. PCOPS_PIPE_PARTS=fps
         import os
         self.parts = os.environ.get("PCOPS_PIPE_PARTS", "fps,side").split(",")
         self.fuse_gather = fuse_gather  # pc_fps_gather instead of pc_fps + pc_gather_point
+        # pc_sa_group (group xyz + centre + group features + concat) and pc_fp_interpolate (weights + interpolate)
+        # instead of two GroupPoint calls / weights + ThreeInterpolate: what sample_and_group / pointnet_fp_module need.
+        # Off by default here: it produces MORE than the reference-signature ops the benchmark counts (the concatenated
+        # tensor on top of grouped_xyz); the wrappers in pointnet_util.py use it, where it replaces 4-5 launches.
+        self.fuse_layers = fuse_layers
         self.grid = grid  # cell-grid ball query / three_nn (same outputs as the all-pairs kernels, far fewer pair tests)
         self.dev = torch.device(device)
         self.attention = attention
@@ -82,6 +87,8 @@ class ScanNetGeometry:
             lv["cnt"] = res((batch, m), i32)
             lv["gxyz"] = torch.empty((batch, m, ns, 3), dtype=f32, device=dev)
             lv["gfeat"] = torch.empty((batch, m, ns, cin), dtype=f32, device=dev)
+            if fuse_layers:
+                lv["new_points"] = torch.empty((batch, m, ns, 3 + cin), dtype=f32, device=dev)
             if attention:  # stand-ins for the Dense projections of the level's (B,m,ns,cout) activations
                 lv["Q"] = rnd(batch * m, cout)
                 lv["K"] = rnd(batch * m, ns, cout)
@@ -111,8 +118,8 @@ class ScanNetGeometry:
         # kernels per forward: FPS, gather, ball (+ grid build), group x2, attention per SA level; three_nn (+ grid build
         # when the known cloud has >= 64 points), weights, interpolate per FP level
         self.launches_per_step = len(self.levels) * ((6 if attention else 5) + (2 if grid else 0) -
-                                                     (1 if fuse_gather else 0)) + \
-            sum(3 + (2 if grid and fp["m"] >= 64 else 0) for fp in self.fps)
+                                                     (1 if fuse_gather else 0) - (1 if fuse_layers else 0)) + \
+            sum(3 + (2 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps)
         self._graph = None
 
     # ---- inputs / outputs ----------------------------------------------------------------------------------
@@ -158,10 +165,15 @@ class ScanNetGeometry:
         else:
             run("query_ball_sa%d" % (li + 1), side, lambda: L.pc_query_ball(
                 B, n, m, lv["r"], ns, p(lv["xyz"]), p(lv["new_xyz"]), p(lv["idx"]), p(lv["cnt"]), st))
-        run("group_xyz_sa%d" % (li + 1), side, lambda: L.pc_group_point(
-            B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
-        run("group_feat_sa%d" % (li + 1), side, lambda: L.pc_group_point(
-            B, n, cin, m, ns, p(lv["feat"]), p(lv["idx"]), p(lv["gfeat"]), st))
+        if self.fuse_layers:
+            run("sa_group_sa%d" % (li + 1), side, lambda: L.pc_sa_group(
+                B, n, cin, m, ns, p(lv["xyz"]), p(lv["feat"]), p(lv["idx"]), p(lv["new_xyz"]), p(lv["new_points"]),
+                p(lv["gxyz"]), st))
+        else:
+            run("group_xyz_sa%d" % (li + 1), side, lambda: L.pc_group_point(
+                B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
+            run("group_feat_sa%d" % (li + 1), side, lambda: L.pc_group_point(
+                B, n, cin, m, ns, p(lv["feat"]), p(lv["idx"]), p(lv["gfeat"]), st))
         if self.attention:
             run("attention_sa%d" % (li + 1), side, lambda: L.pc_attention_fwd(
                 B * m, ns, lv["cout"] // KEY_DIM, KEY_DIM, p(lv["Q"]), p(lv["K"]), p(lv["V"]), p(lv["att"]), st))
@@ -177,9 +189,13 @@ class ScanNetGeometry:
         else:
             run("three_nn_" + tag, side, lambda: L.pc_three_nn(
                 B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
-        run("three_weights_" + tag, side, lambda: L.pc_three_weights(B * n, p(fp["dist"]), p(fp["w"]), st))
-        run("three_interpolate_" + tag, side, lambda: L.pc_three_interpolate(
-            B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
+        if self.fuse_layers:
+            run("fp_interpolate_" + tag, side, lambda: L.pc_fp_interpolate(
+                B, n, m, c, 0, p(fp["dist"]), p(fp["idx"]), p(fp["points2"]), None, p(fp["out"]), p(fp["w"]), st))
+        else:
+            run("three_weights_" + tag, side, lambda: L.pc_three_weights(B * n, p(fp["dist"]), p(fp["w"]), st))
+            run("three_interpolate_" + tag, side, lambda: L.pc_three_interpolate(
+                B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
 
     def forward(self, overlap=True, probes=None):
         """Enqueue one forward on the current stream (plus the side stream when overlap=True).
@@ -225,12 +241,15 @@ class ScanNetGeometry:
         names = []
         for li in range(len(self.levels)):
             names += ["fps_sa%d" % (li + 1)] + ([] if self.fuse_gather else ["gather_sa%d" % (li + 1)]) + \
-                     ["query_ball_sa%d" % (li + 1), "group_xyz_sa%d" % (li + 1), "group_feat_sa%d" % (li + 1)]
+                     ["query_ball_sa%d" % (li + 1)] + \
+                     (["sa_group_sa%d" % (li + 1)] if self.fuse_layers else
+                      ["group_xyz_sa%d" % (li + 1), "group_feat_sa%d" % (li + 1)])
             if self.attention:
                 names.append("attention_sa%d" % (li + 1))
         for fp in self.fps:
             tag = "fp%d" % (4 - fp["level"])
-            names += ["three_nn_" + tag, "three_weights_" + tag, "three_interpolate_" + tag]
+            names += ["three_nn_" + tag] + (["fp_interpolate_" + tag] if self.fuse_layers else
+                                              ["three_weights_" + tag, "three_interpolate_" + tag])
         return names
 
     def algorithmic_work(self):
@@ -245,6 +264,8 @@ class ScanNetGeometry:
                                        bytes=B * (12 * n + 12 * m + 4 * m * ns + 4 * m))
             for nm, c in (("group_xyz", 3), ("group_feat", cin)):
                 w[nm + t] = dict(kind="bytes", amount=B * (4 * m * ns + 4 * min(n, m * ns) * c + 4 * m * ns * c))
+            w["sa_group" + t] = dict(kind="bytes", amount=B * (4 * m * ns + 12 * m + 4 * min(n, m * ns) * (3 + cin) +
+                                                               4 * m * ns * (3 + cin) + 12 * m * ns))
             if self.attention:
                 w["attention" + t] = dict(kind="bytes", amount=B * m * (2 * 4 * ns * cout + 2 * 4 * cout))
         for fp in self.fps:
@@ -252,6 +273,7 @@ class ScanNetGeometry:
             w["three_nn" + t] = dict(kind="fp32_ops", amount=B * n * m * 11, bytes=B * (12 * n + 12 * m + 24 * n))
             w["three_weights" + t] = dict(kind="bytes", amount=B * n * 24)
             w["three_interpolate" + t] = dict(kind="bytes", amount=B * (24 * n + 4 * m * c + 4 * n * c))
+            w["fp_interpolate" + t] = dict(kind="bytes", amount=B * (24 * n + 4 * m * c + 4 * n * c + 12 * n))
         return w
 
     # ---- CUDA graph ------------------------------------------------------------------------------------------

@@ -22,8 +22,13 @@ def check_against_oracle(pipe, xyz_np, feat_np):
         assert np.array_equal(npy(lv["new_xyz"]), new_xyz)
         idx, cnt = cpu.query_ball_point(lv["r"], lv["ns"], xyz, new_xyz)
         assert np.array_equal(npy(lv["idx"]), idx) and np.array_equal(npy(lv["cnt"]), cnt)
-        assert np.array_equal(npy(lv["gxyz"]), cpu.group_point(xyz, idx))
-        assert np.array_equal(npy(lv["gfeat"]), cpu.group_point(npy(lv["feat"]), idx))
+        if pipe.fuse_layers:   # centred grouped xyz and the [xyz_local, feats] tensor sample_and_group returns
+            want = cpu.group_point(xyz, idx) - new_xyz[:, :, None, :]
+            assert np.array_equal(npy(lv["gxyz"]), want)
+            assert np.array_equal(npy(lv["new_points"]), np.concatenate([want, cpu.group_point(npy(lv["feat"]), idx)], -1))
+        else:
+            assert np.array_equal(npy(lv["gxyz"]), cpu.group_point(xyz, idx))
+            assert np.array_equal(npy(lv["gfeat"]), cpu.group_point(npy(lv["feat"]), idx))
         if pipe.attention:
             want = cpu.attention_fwd(npy(lv["Q"]), npy(lv["K"]), npy(lv["V"]), lv["cout"] // KEY_DIM, KEY_DIM)
             np.testing.assert_allclose(npy(lv["att"]), want, rtol=1e-5, atol=1e-6)
@@ -36,16 +41,17 @@ def check_against_oracle(pipe, xyz_np, feat_np):
         assert np.array_equal(npy(fp["out"]), cpu.three_interpolate(npy(fp["points2"]), i3, w))
 
 
-@pytest.mark.parametrize("grid,fuse", [(True, True), (False, False)])
+@pytest.mark.parametrize("grid,fuse", [(True, True), (False, False), (True, False)])
 def test_pipeline_matches_oracle_eager_and_graph(grid, fuse):
     B = 2
     xyz_np, feat_np = synth.scannet_batch(300, B, 8192)
-    pipe = ScanNetGeometry(B, grid=grid, fuse_gather=fuse)
+    pipe = ScanNetGeometry(B, grid=grid, fuse_gather=fuse or grid, fuse_layers=fuse)
     pipe.set_inputs(torch.from_numpy(xyz_np), torch.from_numpy(feat_np))
     pipe.forward(overlap=False)
     torch.cuda.synchronize()
     check_against_oracle(pipe, xyz_np, feat_np)
-    assert pipe.launches_per_step == (46 if grid else 36)   # grid: +2 builds per binned op, -1 per fused gather
+    # grid: +2 builds per binned op (4 ball + 3 three_nn); fused: -1 gather, -1 group per SA level, -1 weights per FP level
+    assert pipe.launches_per_step == (38 if fuse else (46 if grid else 36))
 
     eager = [t.clone() for t in pipe.result_tensors()] + [fp["out"].clone() for fp in pipe.fps]
     pipe.capture(overlap=True)
