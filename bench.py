@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--graph", type=int, default=1, help="1: replay each forward as a CUDA graph (default); 0: eager")
     ap.add_argument("--depth", type=int, default=8, help="independent batches in flight (pipeline instances, own streams)")
     ap.add_argument("--attention", type=int, default=1, help="0: leave the attention contraction out (diagnostics only)")
+    ap.add_argument("--fuse-layers", type=int, default=0, help="1: pc_sa_group / pc_fp_interpolate instead of the op pairs")
     ap.add_argument("--grid", type=int, default=1, help="1: cell-grid ball query / three_nn; 0: all-pairs kernels")
     ap.add_argument("--no-overlap", action="store_true", help="single stream")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
@@ -269,7 +270,8 @@ def main():
         dev_feat.append(hf.to(dev))
 
     D = max(1, args.depth)
-    pipes = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=bool(args.attention), seed=rank * 64 + d, own_streams=True, grid=bool(args.grid))
+    pipes = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=bool(args.attention), seed=rank * 64 + d, own_streams=True, grid=bool(args.grid),
+                             fuse_layers=bool(args.fuse_layers))
              for d in range(D)]
     pipe = pipes[0]
     overlap = not args.no_overlap

@@ -207,17 +207,20 @@ struct TileSmem {
 };
 
 // Stages the candidates of the cell box [X0..X1] x [Y0..Y1] x [Z0..Z1] batch by batch and calls process(count) with
-// `count` (a multiple of 32, padded with +inf points) candidates in the stage.  Warp-collective.
-template <class F>
+// `count` (a multiple of 32, padded with +inf points) candidates in the stage.  Collective over NW warps that share
+// `st` (NW == 1: one warp, __syncwarp; NW > 1: the whole CTA of NW warps, __syncthreads).
+template <int NW, class F>
 __device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__restrict__ cell_start,
                                                const float4 *__restrict__ sorted, int X0, int X1, int Y0, int Y1, int Z0,
                                                int Z1, TileSmem &st, F &&process) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, t = (NW == 1) ? lane : (int)threadIdx.x;
+  constexpr int NT = NW * 32;
+  auto sync = [] { if (NW == 1) __syncwarp(); else __syncthreads(); };
   const float inf = __int_as_float(0x7f800000);
   const int nyu = Y1 - Y0 + 1, nrows = nyu * (Z1 - Z0 + 1);
   for (int r0 = 0; r0 < nrows; r0 += kMaxRows) {
     const int nr = min(kMaxRows, nrows - r0);
-    for (int r = lane; r < kMaxRows; r += 32) {
+    for (int r = t; r < kMaxRows; r += NT) {
       int s = 0, len = 0;
       if (r < nr) {
         const int rr = r0 + r, z = Z0 + rr / nyu, y = Y0 + rr % nyu, row = (z * g.ny + y) * g.nx;
@@ -227,28 +230,30 @@ __device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__re
       st.rs[r] = s;
       st.rl[r] = len;
     }
-    __syncwarp();
-    // exclusive prefix of the row lengths: lane owns rows [8*lane, 8*lane+8)
+    sync();
+    // exclusive prefix of the row lengths (every warp computes it redundantly; warp 0 stores): lane owns 8 rows
     int mine = 0;
 #pragma unroll
-    for (int t = 0; t < kMaxRows / 32; ++t) mine += st.rl[lane * (kMaxRows / 32) + t];
+    for (int u = 0; u < kMaxRows / 32; ++u) mine += st.rl[lane * (kMaxRows / 32) + u];
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(PC_FULL_MASK, incl, o);
-      if (lane >= o) incl += u;
+      const int v = __shfl_up_sync(PC_FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
     }
     const int total = __shfl_sync(PC_FULL_MASK, incl, 31);
-    int run = incl - mine;
+    if (NW == 1 || threadIdx.x < 32) {
+      int run = incl - mine;
 #pragma unroll
-    for (int t = 0; t < kMaxRows / 32; ++t) {
-      st.ro[lane * (kMaxRows / 32) + t] = run;
-      run += st.rl[lane * (kMaxRows / 32) + t];
+      for (int u = 0; u < kMaxRows / 32; ++u) {
+        st.ro[lane * (kMaxRows / 32) + u] = run;
+        run += st.rl[lane * (kMaxRows / 32) + u];
+      }
     }
-    __syncwarp();
+    sync();
     for (int b0 = 0; b0 < total; b0 += kCap) {
       const int bn = min(kCap, total - b0);
-      for (int r = lane; r < nr; r += 32) {  // a lane copies whole cell runs (contiguous float4s)
+      for (int r = t; r < nr; r += NT) {  // a thread copies whole cell runs (contiguous float4s)
         const int off = st.ro[r], s = st.rs[r];
         const int lo = max(off, b0), hi = min(off + st.rl[r], b0 + bn);
         for (int f = lo; f < hi; ++f) {
@@ -257,10 +262,10 @@ __device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__re
         }
       }
       const int bp = (bn + 31) & ~31;
-      for (int f = bn + lane; f < bp; f += 32) { st.x[f] = inf; st.y[f] = inf; st.z[f] = inf; st.i[f] = 0; }
-      __syncwarp();
+      for (int f = bn + t; f < bp; f += NT) { st.x[f] = inf; st.y[f] = inf; st.z[f] = inf; st.i[f] = 0; }
+      sync();
       process(bp);
-      __syncwarp();
+      sync();
     }
   }
 }
@@ -293,8 +298,12 @@ __device__ __forceinline__ unsigned filter_word(const TileSmem &st, int w0, f32x
   return __brev(word);
 }
 
-// Ball query, one warp per CTA, a tile = 32 consecutive cell-sorted queries.
-__global__ void __launch_bounds__(32)
+// Ball query: a tile = 32 consecutive cell-sorted queries (lane = query).  The kBallWarps warps of a CTA share the
+// tile: they stage the union neighbourhood together and split its 32-candidate words among themselves, recording hits
+// with shared-memory atomicOr into ONE per-query bitmap over original indices (a 1-warp CTA would pin 45 KB of shared
+// memory per resident warp); warp 0 then extracts the rows.
+constexpr int kBallWarps = 4;
+__global__ void __launch_bounds__(kBallWarps * 32)
 ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, float one, const int *__restrict__ ws_c,
                        const int *__restrict__ ws_q, int *__restrict__ idx, int *__restrict__ pts_cnt) {
   extern __shared__ __align__(16) int s_tile[];  // TileSmem | bitmap (nwords + nsumm) * 32
@@ -302,7 +311,7 @@ ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, flo
   const int nwords = (n + 31) >> 5, nsumm = (nwords + 31) >> 5;
   unsigned *s_bits = reinterpret_cast<unsigned *>(s_tile + kTileWarpInts);
   unsigned *s_summ = s_bits + (size_t)nwords * 32;
-  const int scene = blockIdx.y, lane = threadIdx.x;
+  const int scene = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int *cbase = ws_c + (size_t)scene * grid_scene_ints(n);
   const GridHdr g = *reinterpret_cast<const GridHdr *>(cbase);
   const int *cell_start = cbase + kHdrInts;
@@ -311,8 +320,8 @@ ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, flo
       reinterpret_cast<const float4 *>(ws_q + (size_t)scene * grid_scene_ints(m) + grid_sorted_offset_ints());
   const f32x2 one2 = pack2(one, one);
   const int thr = (s_star >= 0.0f) ? __float_as_int(s_star) + 1 : 0;
-  for (int i = lane; i < (nwords + nsumm) * 32; i += 32) s_bits[i] = 0;
-  __syncwarp();
+  for (int i = threadIdx.x; i < (nwords + nsumm) * 32; i += kBallWarps * 32) s_bits[i] = 0;
+  __syncthreads();
   const int ntiles = (m + 31) >> 5;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int qs = tile * 32 + lane;
@@ -320,49 +329,52 @@ ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, flo
     const float4 qv = __ldg(qsorted + (live ? qs : tile * 32));
     const int qi = __float_as_int(qv.w);
     const f32x2 qx2 = pack2(qv.x, qv.x), qy2 = pack2(qv.y, qv.y), qz2 = pack2(qv.z, qv.z);
-    // cell box of this lane's ball (dead lanes copy the tile's first query) and the warp's union box
+    // cell box of this lane's ball (dead lanes copy the tile's first query) and the tile's union box
     const int X0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.x - reach, g.ox, g.inv_h, g.nx));
     const int X1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.x + reach, g.ox, g.inv_h, g.nx));
     const int Y0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.y - reach, g.oy, g.inv_h, g.ny));
     const int Y1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.y + reach, g.oy, g.inv_h, g.ny));
     const int Z0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.z - reach, g.oz, g.inv_h, g.nz));
     const int Z1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.z + reach, g.oz, g.inv_h, g.nz));
-    for_each_batch(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
-      for (int w0 = 0; w0 < count; w0 += 32) {
+    for_each_batch<kBallWarps>(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
+      for (int w0 = warp * 32; w0 < count; w0 += kBallWarps * 32) {  // the CTA's warps take alternate words
         unsigned word = filter_word(st, w0, qx2, qy2, qz2, one2, thr, true);
-        while (word) {  // record each hit at its ORIGINAL index
+        while (word) {  // record each hit at its ORIGINAL index (other warps may touch the same bitmap word)
           const int k = st.i[w0 + __ffs(word) - 1], w = k >> 5;
           word &= word - 1;
-          s_bits[w * 32 + lane] |= 1u << (k & 31);
-          s_summ[(w >> 5) * 32 + lane] |= 1u << (w & 31);
+          atomicOr(&s_bits[w * 32 + lane], 1u << (k & 31));
+          atomicOr(&s_summ[(w >> 5) * 32 + lane], 1u << (w & 31));
         }
       }
     });
-    // ascending extraction; every touched word is cleared on the way so the bitmap is clean for the next tile
-    int *row_out = idx + ((size_t)scene * m + (live ? qi : 0)) * nsample;
-    int cnt = 0, first = 0;
-    for (int sidx = 0; sidx < nsumm; ++sidx) {
-      unsigned sw = s_summ[sidx * 32 + lane];
-      if (sw) s_summ[sidx * 32 + lane] = 0;
-      while (sw) {
-        const int w = sidx * 32 + __ffs(sw) - 1;
-        sw &= sw - 1;
-        unsigned word = s_bits[w * 32 + lane];
-        s_bits[w * 32 + lane] = 0;
-        while (word && cnt < nsample) {
-          const int k = w * 32 + __ffs(word) - 1;
-          word &= word - 1;
-          if (cnt == 0) first = k;
-          if (live) row_out[cnt] = k;
-          ++cnt;
+    // (for_each_batch ends with a CTA barrier: every warp's hits are in the bitmap)
+    if (warp == 0) {
+      // ascending extraction; every touched word is cleared on the way so the bitmap is clean for the next tile
+      int *row_out = idx + ((size_t)scene * m + (live ? qi : 0)) * nsample;
+      int cnt = 0, first = 0;
+      for (int sidx = 0; sidx < nsumm; ++sidx) {
+        unsigned sw = s_summ[sidx * 32 + lane];
+        if (sw) s_summ[sidx * 32 + lane] = 0;
+        while (sw) {
+          const int w = sidx * 32 + __ffs(sw) - 1;
+          sw &= sw - 1;
+          unsigned word = s_bits[w * 32 + lane];
+          s_bits[w * 32 + lane] = 0;
+          while (word && cnt < nsample) {
+            const int k = w * 32 + __ffs(word) - 1;
+            word &= word - 1;
+            if (cnt == 0) first = k;
+            if (live) row_out[cnt] = k;
+            ++cnt;
+          }
         }
       }
+      if (live) {
+        for (int l = cnt; l < nsample; ++l) row_out[l] = first;  // tf_grouping_g.cu:26-29; empty ball -> zero row
+        pts_cnt[(size_t)scene * m + qi] = cnt;
+      }
     }
-    if (live) {
-      for (int l = cnt; l < nsample; ++l) row_out[l] = first;  // tf_grouping_g.cu:26-29; empty ball -> zero row
-      pts_cnt[(size_t)scene * m + qi] = cnt;
-    }
-    __syncwarp();
+    __syncthreads();  // bitmap clean before the next tile's hits
   }
 }
 
@@ -398,7 +410,7 @@ three_nn_tile_kernel(int n, int m, float one, const int *__restrict__ ws_c, cons
     const int Z0 = max(__reduce_min_sync(PC_FULL_MASK, cz) - 1, 0), Z1 = min(__reduce_max_sync(PC_FULL_MASK, cz) + 1, g.nz - 1);
     float b1 = inf, b2 = inf, b3 = inf;
     int i1 = INT_MAX, i2 = INT_MAX, i3 = INT_MAX;
-    for_each_batch(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
+    for_each_batch<1>(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
       for (int w0 = 0; w0 < count; w0 += 32) {
         // stale filter d <= b3 (ties on the distance may still win on the index); exact replay of the survivors
         const int thr = (b3 == inf) ? 0x7f800000 : __float_as_int(b3) + 1;
@@ -490,7 +502,7 @@ extern "C" int pc_query_ball_grid(int b, int n, int m, float radius, int nsample
   PC_CUDA_TRY(pc::allow_smem(pc::ball_query_tile_kernel, smem));
   const int ntiles = (m + 31) / 32;
   dim3 grid(ntiles < 64 ? ntiles : 64, b);
-  pc::ball_query_tile_kernel<<<grid, 32, smem, st>>>(n, m, s_star, reach, nsample, 1.0f, ws_c, ws_q, idx, pts_cnt);
+  pc::ball_query_tile_kernel<<<grid, pc::kBallWarps * 32, smem, st>>>(n, m, s_star, reach, nsample, 1.0f, ws_c, ws_q, idx, pts_cnt);
   PC_RETURN_LAUNCH_STATUS();
 }
 
