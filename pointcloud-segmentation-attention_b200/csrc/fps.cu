@@ -191,6 +191,210 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Pruned variant for 2048 < n <= 8192: same rounds, same arithmetic, same winners -- but most warps skip most rounds.
+// At kernel start the scene is counting-sorted by the Morton code of a 16^3 cell grid (shared-memory histogram), so a
+// warp's points form a compact patch with a bounding box.  A new centre c cannot lower any running minimum of a warp
+// whose box is farther from c than the warp's largest running minimum:
+//        dist_lb(c, box)^2 * (1 - 1e-5)  >  max_p td[p]     =>     d(p, c) >= td[p] for every p of the warp
+// (the margin covers the fp32 rounding of both sides by two orders of magnitude), and then min(td, d) leaves every td,
+// the warp's maximum and its tie-break key unchanged: the warp republishes its cached (value, key) pair and skips the
+// P/2 packed updates.  After a few dozen samples a centre only touches the 2-3 patches around it, so the fp32 work of a
+// round drops by 3-4x while every output index stays bit-identical (ties use the ORIGINAL index through a slot ->
+// index table in shared memory; the sort order itself never shows in the result).
+template <int P, int T>
+__global__ void __maxnreg__(T >= 1024 ? 64 : (T >= 512 ? 120 : 200))
+fps_pruned_kernel(int b, int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out,
+                  float *__restrict__ out_xyz) {
+  extern __shared__ float s_dyn[];                       // xyz (n*3 floats) | hist (4096 ints) | perm (T*P ushorts)
+  __shared__ int2 s_pair[2][32];
+  __shared__ float s_red[32];
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  constexpr int H = P / 2, G = (P < 8) ? P : 8, NG = P / G, nwarps = T / 32, kBins = 4096;
+  float *s_xyz = s_dyn;
+  int *s_hist = reinterpret_cast<int *>(s_dyn + (size_t)n * 3);
+  unsigned short *s_perm = reinterpret_cast<unsigned short *>(s_hist + kBins);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const f32x2 one2 = pack2(one, one);
+  const float inf = __int_as_float(0x7f800000);
+
+  for (int scene = blockIdx.x; scene < b; scene += gridDim.x) {
+    const float *p = xyz + (size_t)scene * n * 3;
+    int *o = out + (size_t)scene * m;
+    float *oxyz = out_xyz ? out_xyz + (size_t)scene * m * 3 : nullptr;
+    __syncthreads();
+    for (int i = tid; i < n * 3; i += T) s_xyz[i] = p[i];
+    for (int i = tid; i < kBins; i += T) s_hist[i] = 0;
+    if (tid == 0) {
+      o[0] = 0;
+      s_carry = 0;
+      if (oxyz) { oxyz[0] = p[0]; oxyz[1] = p[1]; oxyz[2] = p[2]; }
+    }
+    __syncthreads();
+    // ---- bounding box of the scene
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int k = tid; k < n; k += T) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const float v = s_xyz[k * 3 + c]; lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v = q ? hi[c] : lo[c];
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) {
+          const float w = __shfl_xor_sync(PC_FULL_MASK, v, of);
+          v = q ? fmaxf(v, w) : fminf(v, w);
+        }
+        __syncthreads();
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        float r = s_red[0];
+        for (int i = 1; i < nwarps; ++i) r = q ? fmaxf(r, s_red[i]) : fminf(r, s_red[i]);
+        if (q) hi[c] = r; else lo[c] = r;
+      }
+    }
+    float scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float e = hi[c] - lo[c]; scale[c] = (e > 0.f && e < inf) ? 16.0f / e : 0.0f; }
+    auto morton = [&](int k) {
+      int key = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int q = (int)((s_xyz[k * 3 + c] - lo[c]) * scale[c]);
+        q = min(max(q, 0), 15);
+        key |= ((q & 1) | ((q & 2) << 2) | ((q & 4) << 4) | ((q & 8) << 6)) << c;  // bits 0,3,6,9 (+c)
+      }
+      return key;
+    };
+    // ---- counting sort of the point indices by Morton key (order inside a cell is irrelevant to the result)
+    for (int k = tid; k < n; k += T) atomicAdd(&s_hist[morton(k)], 1);
+    __syncthreads();
+    for (int b0 = 0; b0 < kBins; b0 += T) {
+      const int v = s_hist[b0 + tid];
+      int incl = v;
+#pragma unroll
+      for (int of = 1; of < 32; of <<= 1) {
+        const int u = __shfl_up_sync(PC_FULL_MASK, incl, of);
+        if (lane >= of) incl += u;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      int wsum = 0;
+      for (int i = 0; i < warp; ++i) wsum += s_warp[i];
+      const int excl = s_carry + wsum + incl - v;
+      s_hist[b0 + tid] = excl;
+      __syncthreads();
+      if (tid == T - 1) s_carry = excl + v;
+      __syncthreads();
+    }
+    for (int k = tid; k < n; k += T) s_perm[atomicAdd(&s_hist[morton(k)], 1)] = (unsigned short)k;
+    for (int k = n + tid; k < T * P; k += T) s_perm[k] = 0xffff;
+    __syncthreads();
+
+    // ---- slots: warp w owns sorted positions [w*32*P, (w+1)*32*P); slot i of lane l is position w*32*P + i*32 + l
+    const int pos0 = warp * 32 * P + lane;
+    f32x2 px[H], py[H], pz[H];
+    float td[P];
+    float blo[3] = {inf, inf, inf}, bhi[3] = {-inf, -inf, -inf};
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float x[2], y[2], z[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * h + e;
+        const int k = s_perm[pos0 + i * 32];
+        if (k != 0xffff) {
+          x[e] = s_xyz[k * 3 + 0]; y[e] = s_xyz[k * 3 + 1]; z[e] = s_xyz[k * 3 + 2];
+          td[i] = 1e38f;
+          blo[0] = fminf(blo[0], x[e]); bhi[0] = fmaxf(bhi[0], x[e]);
+          blo[1] = fminf(blo[1], y[e]); bhi[1] = fmaxf(bhi[1], y[e]);
+          blo[2] = fminf(blo[2], z[e]); bhi[2] = fmaxf(bhi[2], z[e]);
+        } else {
+          x[e] = y[e] = z[e] = 0.0f;
+          td[i] = -1.0f;
+        }
+      }
+      px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) {
+        blo[c] = fminf(blo[c], __shfl_xor_sync(PC_FULL_MASK, blo[c], of));
+        bhi[c] = fmaxf(bhi[c], __shfl_xor_sync(PC_FULL_MASK, bhi[c], of));
+      }
+    }
+    const bool empty = !(blo[0] <= bhi[0]);  // a warp of padding only
+
+    int old = 0, par = 1;
+    int cmax = empty ? __float_as_int(-1.0f) : __float_as_int(1e38f), ckey = INT_MAX;  // cached warp winner
+    bool fresh = false;  // cmax / ckey describe the current td values
+    for (int j = 1; j < m; ++j) {
+      const float cx = s_xyz[old * 3 + 0], cy = s_xyz[old * 3 + 1], cz = s_xyz[old * 3 + 2];
+      // squared distance from the centre to this warp's box (0 inside), un-fused like everything else
+      const float ex = fmaxf(fmaxf(blo[0] - cx, cx - bhi[0]), 0.f), ey = fmaxf(fmaxf(blo[1] - cy, cy - bhi[1]), 0.f),
+                  ez = fmaxf(fmaxf(blo[2] - cz, cz - bhi[2]), 0.f);
+      const float lb = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+      const bool skip = empty || (fresh && __fmul_rn(lb, 0.99999f) > __int_as_float(cmax));
+      if (!skip) {  // warp-uniform
+        const f32x2 cx2 = pack2(cx, cx), cy2 = pack2(cy, cy), cz2 = pack2(cz, cz);
+        float gm[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          gm[g] = -1.0f;
+#pragma unroll
+          for (int h = g * G / 2; h < (g + 1) * G / 2; ++h) {
+            float d0, d1;
+            unpack2(sqdist3_x2(px[h], py[h], pz[h], cx2, cy2, cz2, one2), d0, d1);
+            td[2 * h] = fminf(d0, td[2 * h]);
+            td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+            gm[g] = fmaxf(gm[g], fmaxf(td[2 * h], td[2 * h + 1]));
+          }
+        }
+        float vmax = gm[0];
+#pragma unroll
+        for (int g = 1; g < NG; ++g) vmax = fmaxf(vmax, gm[g]);
+        const int vb = __float_as_int(vmax);
+        cmax = __reduce_max_sync(PC_FULL_MASK, vb);
+        int tb = INT_MAX;
+        if (vb == cmax) {  // every slot at the maximum competes with its ORIGINAL index (slots are in sorted order)
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (__float_as_int(gm[g]) == cmax) {
+#pragma unroll
+              for (int e = 0; e < G; ++e)
+                if (__float_as_int(td[g * G + e]) == cmax) tb = min(tb, tie_key((int)s_perm[pos0 + (g * G + e) * 32]));
+            }
+          }
+        }
+        ckey = __reduce_min_sync(PC_FULL_MASK, tb);
+        fresh = true;
+      }
+      if (lane == 0) s_pair[par][warp] = make_int2(cmax, ckey);
+      __syncthreads();
+      const int2 pr = s_pair[par][lane < nwarps ? lane : 0];
+      const int gmax = __reduce_max_sync(PC_FULL_MASK, pr.x);
+      old = tie_key_to_index(__reduce_min_sync(PC_FULL_MASK, pr.x == gmax ? pr.y : INT_MAX));
+      par ^= 1;
+      if (tid == 0) {
+        o[j] = old;
+        if (oxyz) { oxyz[j * 3 + 0] = s_xyz[old * 3 + 0]; oxyz[j * 3 + 1] = s_xyz[old * 3 + 1]; oxyz[j * 3 + 2] = s_xyz[old * 3 + 2]; }
+      }
+    }
+  }
+}
+
+template <int P, int T>
+int launch_pruned(int b, int n, int m, const float *xyz, int *out, float *out_xyz, cudaStream_t st) {
+  const size_t smem = (size_t)n * 3 * sizeof(float) + 4096 * sizeof(int) + (size_t)T * P * sizeof(unsigned short);
+  PC_CUDA_TRY(allow_smem(fps_pruned_kernel<P, T>, smem));
+  fps_pruned_kernel<P, T><<<b, T, smem, st>>>(b, n, m, 1.0f, xyz, out, out_xyz);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 8192 < n <= 16 * 8192: one THREAD-BLOCK CLUSTER per scene.  CTA r of the cluster keeps points [8192 r, 8192 (r+1))
 // on chip exactly as the single-CTA kernel does (8 warps x 32 points, same slot order, same one-barrier CTA-level
 // winner); the CTA winners then meet through distributed shared memory: every CTA writes its (value, key, x, y, z)
@@ -422,12 +626,16 @@ extern "C" int pc_fps_gather(int b, int n, int m, const float *xyz, void *worksp
     if (n <= 1024) return pc::launch_onchip<8, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     if (n <= 2048) return pc::launch_onchip<16, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     if (n <= 4096) return pc::launch_onchip<32, 128>(b, n, m, xyz, out_idx, out_xyz, st);
-    // Two shapes for 4097..8192 points (measured on B200, 16 scenes x 8192 -> 1024):
-    //   default  8 warps x 32 points, one barrier per round, 168 registers: 645 us alone, but leaves a quarter of the
-    //            register file to CTAs of other kernels -- best whole-pipeline throughput with several batches in flight;
-    //   PCOPS_FPS_SHAPE=512  16 warps x 16 points, two-barrier tail: 584 us alone (lowest single-launch latency).
+    // 4097..8192 points (measured on B200, 16 ScanNet-shaped scenes x 8192 -> 1024, one launch alone):
+    //   default            pruned kernel, 16 warps x 16 points per thread                      539 us
+    //   PCOPS_FPS_SHAPE=256   un-pruned, 8 warps x 32 points, one barrier, 168 registers          645 us
+    //   PCOPS_FPS_SHAPE=512   un-pruned, 16 warps x 16 points, two-barrier tail                   584 us
+    //   PCOPS_FPS_SHAPE=1256  pruned, 8 warps x 32 points                                         618 us
+    // All give the same indices; with 8 batches in flight the whole-pipeline throughput is the same for all four.
     static int shape = -1;
-    if (shape < 0) { const char *e = getenv("PCOPS_FPS_SHAPE"); shape = e ? atoi(e) : 256; }
+    if (shape < 0) { const char *e = getenv("PCOPS_FPS_SHAPE"); shape = e ? atoi(e) : 1512; }
+    if (shape == 1512) return pc::launch_pruned<16, 512>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (shape == 1256) return pc::launch_pruned<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
     if (shape == 512) return pc::launch_onchip<16, 512, false, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
   }

@@ -253,12 +253,30 @@ __device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__re
     sync();
     for (int b0 = 0; b0 < total; b0 += kCap) {
       const int bn = min(kCap, total - b0);
-      for (int r = t; r < nr; r += NT) {  // a thread copies whole cell runs (contiguous float4s)
-        const int off = st.ro[r], s = st.rs[r];
-        const int lo = max(off, b0), hi = min(off + st.rl[r], b0 + bn);
-        for (int f = lo; f < hi; ++f) {
-          const float4 v = __ldg(sorted + s + (f - off));
-          st.x[f - b0] = v.x; st.y[f - b0] = v.y; st.z[f - b0] = v.z; st.i[f - b0] = __float_as_int(v.w);
+      // flat copy: candidate f of the concatenated runs lives in row r = last index with ro[r] <= f (binary search,
+      // zero-length rows sort before the row that holds f); four independent loads per thread are issued together
+      for (int f0 = b0 + t; f0 < b0 + bn; f0 += NT * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int f = f0 + u * NT;
+          v[u] = make_float4(inf, inf, inf, 0.f);
+          if (f < b0 + bn) {
+            int lo = 0, hi = nr;  // invariant: ro[lo] <= f, answer in [lo, hi)
+#pragma unroll
+            for (int step = 0; step < 8; ++step) {  // kMaxRows = 256 = 2^8
+              const int mid = (lo + hi) >> 1;
+              if (mid > lo && st.ro[mid] <= f) lo = mid; else hi = max(mid, lo + 1);
+            }
+            v[u] = __ldg(sorted + st.rs[lo] + (f - st.ro[lo]));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int f = f0 + u * NT;
+          if (f < b0 + bn) {
+            st.x[f - b0] = v[u].x; st.y[f - b0] = v[u].y; st.z[f - b0] = v[u].z; st.i[f - b0] = __float_as_int(v[u].w);
+          }
         }
       }
       const int bp = (bn + 31) & ~31;

@@ -6,6 +6,8 @@ gradient (:42-46 -> ``[GroupPointGrad, None]``) and ``knn_point(k, xyz1, xyz2)``
 kernel instead of a TF graph over a (b,m,n,c) tile.  Shape / attribute errors carry the reference OpKernel's
 messages (tf_grouping.cpp:70-74,79-85,112-118,149-157,180-191).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -14,7 +16,7 @@ from . import _lib
 # Module switch between the two implementations (identical outputs, tests run both): the all-pairs kernel has the lower
 # single-call latency at PointNet++ sizes (default for these eager wrappers); the cell-grid path issues far fewer
 # instructions and wins when many batches are in flight (pipeline.ScanNetGeometry uses it) or when clouds are large.
-USE_GRID = False
+USE_GRID = os.environ.get("PCOPS_USE_GRID", "0") == "1"
 
 
 def query_ball_point(radius, nsample, xyz1, xyz2):

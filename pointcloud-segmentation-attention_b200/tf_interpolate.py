@@ -7,6 +7,8 @@ Mirrors pointnet2_tensorflow/tf_ops/interpolation_3d/tf_interpolate.py: ``three_
 (tf_interpolate.cpp:163-168,197-206,231-243).  ``three_weights`` is pointnet_fp_module's inverse-distance weighting
 (pointnet_util.py:219-222) as one kernel.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -15,7 +17,7 @@ from . import _lib
 # Module switch between the two implementations (identical outputs, tests run both): the all-pairs kernel has the lower
 # single-call latency at PointNet++ sizes (default for these eager wrappers); the cell-grid path issues far fewer
 # instructions and wins when many batches are in flight (pipeline.ScanNetGeometry uses it) or when clouds are large.
-USE_GRID = False
+USE_GRID = os.environ.get("PCOPS_USE_GRID", "0") == "1"
 
 
 def three_nn(xyz1, xyz2):
