@@ -101,9 +101,10 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
   if (tid == 0) {
     const float ex = fmaxf(hi[0] - lo[0], 0.f), ey = fmaxf(hi[1] - lo[1], 0.f), ez = fmaxf(hi[2] - lo[2], 0.f);
     float h = min_edge;
-    if (mode == 1) {  // ~1 point per cell in volume terms, never finer than the surface / line density suggests
+    if (mode == 1) {  // ~4 points per cell in volume terms, never finer than the surface / line density suggests: the
+      // third neighbour must lie within one cell edge for a lane to be certified without the whole-cloud scan
       const float vol = ex * ey * ez, area = fmaxf(ex * ey, fmaxf(ex * ez, ey * ez)), len = fmaxf(ex, fmaxf(ey, ez));
-      h = fmaxf(fmaxf(cbrtf(vol / n), 0.7f * sqrtf(area / n)), fmaxf(len / n, 1e-12f));
+      h = fmaxf(fmaxf(1.6f * cbrtf(vol / n), 1.1f * sqrtf(area / n)), fmaxf(2.0f * len / n, 1e-12f));
       h = fmaxf(h, min_edge);
     }
     if (!(h > 0.f) || !isfinite(h)) h = 1.0f;
