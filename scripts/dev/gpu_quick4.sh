@@ -18,4 +18,4 @@ for g in (True, False):
     tf_grouping.USE_GRID=g
     print("ball SA1 grid=%s: %.1f us"%(g, t(lambda: ops.query_ball_point(0.1,32,x,nx))))
 PY
-bash scripts/gpu_ab7.sh
+bash scripts/dev/gpu_ab7.sh
