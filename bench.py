@@ -7,7 +7,8 @@
 A "step" is one pass of the hot path over one batch of B=16 synthetic 8192-point ScanNet-shaped chunks (xyz + 6
 feature channels), BASELINE.json configs[1] plus the attention contraction the metric names: per SA level
 FPS -> gather_point -> query_ball_point -> group_point(xyz) -> group_point(features) -> attention contraction, per FP
-level three_nn -> weights -> three_interpolate (36 kernel launches; pointcloud-segmentation-attention_b200/pipeline.py).
+level three_nn -> weights -> three_interpolate (36 reference-signature op calls; 46 kernel launches with the cell-grid
+neighbour search and the fused FPS+gather; pointcloud-segmentation-attention_b200/pipeline.py).
 
 Own arm (default).  One process per GPU, scenes sharded by rank, no data-path collective (weak scaling).  Prints ONE
 JSON line on rank 0:
