@@ -17,7 +17,7 @@ JSON line on rank 0:
                 independent batches, so --depth of them are in flight at once, each on its own streams and buffers
                 (FPS is a latency-bound chain on B SMs; the other SMs work on neighbouring batches meanwhile).
   e2e           same metric through host buffers: per step H2D of the batch from pinned memory, the forward, ONE D2H
-                of the geometry results (FPS / ball / three_nn indices, counts, three_nn distances) to pinned memory.
+                of the integer geometry results (FPS / ball / three_nn indices, counts) to pinned memory.
   roofline      the kernel with the largest share of a step, duration from CUDA events on its own stream, against
                 its own bound; `rooflines` lists every op (probed eager pass of one pipeline instance).
   cpu_baseline  the CPU oracle (C port of the reference algorithms) on this box's host cores, bounded sample.

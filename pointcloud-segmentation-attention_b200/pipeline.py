@@ -20,8 +20,8 @@ behind a per-level event, so grouping / interpolation / attention of all levels 
 The sequence is CUDA-graph capturable (no allocation, no host sync inside).  Independent batches overlap further by
 running several ``ScanNetGeometry`` instances, each on its own streams (bench.py --depth).
 
-All integer / distance results a host consumer reads back (FPS, ball and three_nn indices, counts, three_nn distances)
-are views into ONE contiguous device buffer, so a step's result is a single device-to-host copy.
+All integer results a host consumer reads back (FPS, ball and three_nn indices, counts) are views into ONE contiguous
+device buffer, so a step's result is a single device-to-host copy.
 """
 import ctypes
 
@@ -54,7 +54,7 @@ class ScanNetGeometry:
         # result arena: every tensor of result_tensors() is a view into it (4-byte elements, 16-byte aligned slots)
         sizes, n_ = [], npoints
         for (m_, _r, ns_, _c) in SA_LEVELS:
-            sizes += [batch * m_, batch * m_ * ns_, batch * m_, batch * n_ * 3, batch * n_ * 3]
+            sizes += [batch * m_, batch * m_ * ns_, batch * m_, batch * n_ * 3]
             n_ = m_
         self._arena = torch.empty(sum((x + 3) // 4 * 4 for x in sizes), dtype=torch.int32, device=self.dev)
         self._arena_off = 0
@@ -106,7 +106,7 @@ class ScanNetGeometry:
             lv = self.levels[li]
             fp = dict(n=lv["n"], m=lv["m"], c=c, xyz1=lv["xyz"], xyz2=lv["new_xyz"], level=li)
             fp["points2"] = rnd(batch, lv["m"], c)  # stand-in for the deeper level's features
-            fp["dist"] = res((batch, lv["n"], 3), f32)
+            fp["dist"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
             fp["idx"] = res((batch, lv["n"], 3), i32)
             fp["w"] = torch.empty((batch, lv["n"], 3), dtype=f32, device=dev)
             fp["out"] = torch.empty((batch, lv["n"], c), dtype=f32, device=dev)
@@ -138,17 +138,18 @@ class ScanNetGeometry:
         return self.xyz0.numel() * 4 + self.feat0.numel() * 4
 
     def result_tensors(self):
-        """The geometry decisions of a forward (what a host-side consumer reads back): FPS indices, ball indices and
-        counts per SA level, three_nn indices and squared distances per FP level."""
+        """The integer geometry decisions of a forward (what a host-side consumer reads back; together with the inputs
+        they determine every gathered / interpolated tensor): FPS indices, ball indices and counts per SA level, three_nn
+        indices per FP level."""
         out = []
         for lv in self.levels:
             out += [lv["fps_idx"], lv["idx"], lv["cnt"]]
         for fp in self.fps:
-            out += [fp["idx"], fp["dist"]]
+            out.append(fp["idx"])
         return out
 
     def result_arena(self):
-        """The one contiguous int32 device buffer all result_tensors() live in (floats are bit-views)."""
+        """The one contiguous int32 device buffer all result_tensors() live in."""
         return self._arena[:self._arena_off]
 
     def stream(self):
