@@ -203,6 +203,19 @@ PC_API int pc_fp_interpolate(int b, int n, int m, int c2, int c1, const float *d
 PC_API int pc_attention_fwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, float *out,
                      pc_stream_t stream);
 
+/* The whole AttentionLayer.call (attention_layer.py:29-45: Dense Q from the query row, Dense K and V from the S grouped
+ * rows, raw reshape to heads of key_dim 4, softmax(QK^T/2) V) in ONE kernel on the tcgen05 tensor cores: the K | V
+ * projection is a 3xTF32 split-accumulation UMMA into TMEM, the per-head softmax runs in the TMEM epilogue, K and V are
+ * never written to memory.
+ *   xq (G,C) query rows, x (G,S,C) grouped rows, wq/wk/wv (C,C) Dense kernels laid out [in][out], bq/bk/bv (C) or NULL
+ *   -> out (G,C), within 1e-5 relative of the fp32 composition.
+ * Supported in this build: S = 32, C = 64 (the SA1 attention level); otherwise PC_ERR_UNSUPPORTED (use a Dense GEMM +
+ * pc_attention_fwd).  workspace: pc_attention_layer_workspace_bytes(G,S,C) bytes, 16-byte aligned. */
+PC_API size_t pc_attention_layer_workspace_bytes(int G, int S, int C);
+PC_API int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq, const float *bq,
+                           const float *wk, const float *bk, const float *wv, const float *bv, float *out,
+                           void *workspace, pc_stream_t stream);
+
 /* Gradient of pc_attention_fwd w.r.t. Q, K, V given dout (G,HD); dQ (G,HD), dK and dV (G,S,HD) fully overwritten. */
 PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, const float *dout,
                      float *dQ, float *dK, float *dV, pc_stream_t stream);

@@ -47,6 +47,8 @@ SIGNATURES = {
     "pc_three_interpolate_grad": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_sa_group": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_fp_interpolate": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pc_attention_layer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pc_attention_layer_fwd": (_i, [_i, _i, _i] + [_vp] * 11),
     "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -36,6 +36,9 @@ class _AttentionContract(torch.autograd.Function):
         return dQ, dK, dV, None, None
 
 
+FUSED_LAYER = True  # AttentionLayer.forward uses pc_attention_layer_fwd where it applies (no-grad, S = 32, C = 64)
+
+
 def attention_contract(Q, K, V, num_heads, key_dim):
     """Q (..., HD), K (..., S, HD), V (..., S, HD) -> (..., HD) with HD = num_heads*key_dim."""
     HD = int(num_heads) * int(key_dim)
@@ -48,6 +51,23 @@ def attention_contract(Q, K, V, num_heads, key_dim):
     Vf = _lib.cuda_f32(V, "V").reshape(-1, S, HD)
     out = _AttentionContract.apply(Qf, Kf, Vf, int(num_heads), int(key_dim))
     return out.reshape(*lead, HD)
+
+
+def attention_layer_fused(xq, x, wq, bq, wk, bk, wv, bv):
+    """The whole AttentionLayer.call (attention_layer.py:29-45) in one tcgen05 kernel (csrc/attention_layer.cu):
+    xq (G,C) query rows, x (G,S,C) grouped rows, Dense kernels w* as (C_in, C_out) like Keras, biases (C) or None
+    -> (G, C).  Forward only; supported for S = 32, C = 64 (key_dim = output_dim = 4), else NotImplementedError."""
+    x = _lib.cuda_f32(x.detach(), "x")
+    xq = _lib.cuda_f32(xq.detach(), "xq")
+    G, S, C = x.shape
+    L = _lib.lib()
+    nbytes = L.pc_attention_layer_workspace_bytes(G, S, C)
+    ws = _lib.workspace(max(nbytes, 16), x.device)
+    out = torch.empty((G, C), dtype=torch.float32, device=x.device)
+    args = [_lib.ptr(_lib.cuda_f32(t.detach(), "weights")) if t is not None else None for t in (wq, bq, wk, bk, wv, bv)]
+    rc = L.pc_attention_layer_fwd(G, S, C, _lib.ptr(xq), _lib.ptr(x), *args, _lib.ptr(out), _lib.ptr(ws), _lib.stream())
+    _lib.check(rc, "pc_attention_layer_fwd")
+    return out
 
 
 class AttentionLayer(torch.nn.Module):
@@ -78,6 +98,16 @@ class AttentionLayer(torch.nn.Module):
         if self.query_net is None:
             self._build(inp.shape[-1])
             self.to(inp.device)
+        hd = self.key_dim * self.num_heads
+        if (FUSED_LAYER and not torch.is_grad_enabled() and inp.shape[-1] == 64 and hd == 64 and inp.shape[-2] == 32
+                and self.key_dim == 4):
+            # inference at the SA1 width: projections + contraction in one tensor-core kernel, K and V never stored
+            lead = inp.shape[:-2]
+            out = attention_layer_fused(query.reshape(-1, 64), inp.reshape(-1, 32, 64),
+                                        self.query_net.weight.t().contiguous(), self.query_net.bias,
+                                        self.key_net.weight.t().contiguous(), self.key_net.bias,
+                                        self.value_net.weight.t().contiguous(), self.value_net.bias)
+            return out.reshape(*lead, 64)
         Q = self.query_net(query)          # (B,np,1,HD)
         K = self.key_net(inp)              # (B,np,S,HD)
         V = self.value_net(inp)

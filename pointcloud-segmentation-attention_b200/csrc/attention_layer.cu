@@ -1,0 +1,284 @@
+// The whole AttentionLayer.call of the SA1 attention level in ONE kernel, on the 5th-generation tensor cores.
+//
+// Reference (attention_points/attention_scannet/attention_layer.py:29-45, used by pointnet_sa_module_attention :255-261
+// with output_dim = key_dim = 4, heads = C/4): three Dense(C) projections (Q from the query row, K and V from the 32
+// grouped rows), a RAW reshape to heads, softmax(QK^T / 2) V.  TensorFlow runs that as three cuBLAS GEMMs, two batched
+// GEMMs with M = 1 / K = 4, a softmax and five intermediate tensors; the K and V tensors alone are 268 MB at SA1.
+//
+// Here (C = 64 only in this round; the other widths take the Dense + pc_attention_fwd composition):
+//   * a persistent CTA per SM keeps W_k | W_v resident in shared memory as the B operand (N = 128, K = 64);
+//   * per tile of 4 neighbourhoods (128 rows) the X rows are loaded once, split into TF32 hi / lo parts and written to
+//     shared memory in the UMMA K-major no-swizzle core-matrix layout;
+//   * one elected thread issues 24 tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8): X_hi W_hi + X_hi W_lo + X_lo W_hi,
+//     i.e. 3xTF32 split accumulation in an fp32 TMEM accumulator (plain TF32 would miss the 1e-5 parity bound);
+//   * the epilogue reads each accumulator row straight from TMEM (tcgen05.ld 32x32b): with the reference's raw
+//     reshape a row of K (64 floats) is 16 pseudo-keys of one head, its neighbour row holds the other 16, so the
+//     softmax over the 32 pseudo-keys is register-local plus one shuffle; K and V never exist in memory.
+//   * Q (one row per neighbourhood) is a 64 x 64 GEMV on the CUDA cores of the same CTA.
+#include <math.h>
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int kC = 64;            // layer width handled by this kernel
+constexpr int kS = 32;            // samples per neighbourhood
+constexpr int kRows = 128;        // rows per tile = 4 neighbourhoods
+constexpr int kN = 2 * kC;        // K | V columns
+constexpr int kLBO = 128;         // bytes between the two 16-byte K-halves of one MMA step (core matrices along K)
+constexpr int kSBO = (kC / 4) * kLBO;  // bytes between 8-row groups
+constexpr int kOperandBytes = (kRows / 8) * kSBO;  // 32 KB for a 128 x 64 tf32 operand
+constexpr int kImageBytes = 2 * kOperandBytes + kC * kC * 4 + 3 * kC * 4;  // B_hi | B_lo | Wq | bq | bk | bv
+constexpr int kThreads = 160;     // warps 0-3: loaders + epilogue (one TMEM lane quarter each); warp 4: MMA issuer
+
+__host__ __device__ inline int operand_offset(int row, int k) {  // byte offset of element (row, k), k in tf32 elements
+  return (row >> 3) * kSBO + (k >> 2) * kLBO + (row & 7) * 16 + (k & 3) * 4;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Builds the per-layer image the main kernel copies into shared memory: W_k | W_v transposed to [n][k], split into
+// TF32 hi / lo, laid out as UMMA core matrices; then Wq and the three biases in fp32.
+__global__ void attention_layer_prep_kernel(const float *__restrict__ wq, const float *__restrict__ bq,
+                                            const float *__restrict__ wk, const float *__restrict__ bk,
+                                            const float *__restrict__ wv, const float *__restrict__ bv,
+                                            unsigned char *__restrict__ image) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kN * kC) {
+    const int n = t / kC, k = t - n * kC;
+    const float w = (n < kC) ? wk[k * kC + n] : wv[k * kC + (n - kC)];  // Dense kernel is [in][out]
+    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    *reinterpret_cast<float *>(image + operand_offset(n, k)) = hi;
+    *reinterpret_cast<float *>(image + kOperandBytes + operand_offset(n, k)) = lo;
+  }
+  float *tail = reinterpret_cast<float *>(image + 2 * kOperandBytes);
+  if (t < kC * kC) tail[t] = wq[t];
+  if (t < kC) {
+    tail[kC * kC + t] = bq ? bq[t] : 0.f;
+    tail[kC * kC + kC + t] = bk ? bk[t] : 0.f;
+    tail[kC * kC + 2 * kC + t] = bv ? bv[t] : 0.f;
+  }
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  // UMMA shared-memory descriptor, K-major, no swizzle: start address, LBO, SBO (16-byte units), version 1
+  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | ((uint32_t)(kLBO >> 4) << 16);
+  const uint32_t hi = (uint32_t)(kSBO >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+#define PC_TMEM_LD16(addr, v, o)                                                                                     \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),         \
+                 "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),      \
+                 "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                     \
+               : "r"(addr))
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__restrict__ x,
+                           const unsigned char *__restrict__ image, float *__restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *a_hi = smem, *a_lo = smem + kOperandBytes;
+  unsigned char *b_img = smem + 2 * kOperandBytes;  // B_hi | B_lo | Wq | bq | bk | bv  (kImageBytes)
+  float *s_wq = reinterpret_cast<float *>(b_img + 2 * kOperandBytes);
+  float *s_bq = s_wq + kC * kC, *s_bk = s_bq + kC, *s_bv = s_bk + kC;
+  float *s_xq = reinterpret_cast<float *>(b_img + kImageBytes);  // [4][64]
+  float *s_q = s_xq + 4 * kC;                                    // [4][64]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_q + 4 * kC);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
+
+  if (warp == 4) {  // TMEM: 128 fp32 columns x 128 lanes for the accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                 "r"(128u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  for (int i = tid; i < kImageBytes / 16; i += kThreads)
+    reinterpret_cast<uint4 *>(b_img)[i] = __ldg(reinterpret_cast<const uint4 *>(image) + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+  const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
+  const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_img), b_lo_s = b_hi_s + kOperandBytes;
+
+  const size_t total_rows = (size_t)G * kS;
+  const int ntiles = (int)((total_rows + kRows - 1) / kRows);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t row0 = (size_t)tile * kRows;
+    if (tid < kRows) {
+      // X tile: 128 rows x 64 floats, contiguous in memory -> coalesced float4 loads, hi / lo split, core-matrix stores
+      const float4 *src = reinterpret_cast<const float4 *>(x + row0 * kC);
+#pragma unroll 4
+      for (int i = 0; i < (kRows * kC / 4) / kRows; ++i) {
+        const int i4 = tid + kRows * i, row = i4 >> 4, kq = i4 & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + row < total_rows) v = __ldg(src + i4);
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        const int off = operand_offset(row, kq * 4);
+        *reinterpret_cast<float4 *>(a_hi + off) = h;
+        *reinterpret_cast<float4 *>(a_lo + off) = l;
+      }
+      // query rows of the tile's 4 neighbourhoods
+      for (int i = tid; i < 4 * kC; i += kRows) {
+        const size_t g = (size_t)tile * 4 + (i >> 6);
+        s_xq[i] = (g < (size_t)G) ? __ldg(xq + g * kC + (i & 63)) : 0.f;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();  // operands + query rows in shared memory; previous tile's TMEM reads finished (end-of-loop sync)
+    if (warp == 4) {
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc = 0;
+#pragma unroll
+        for (int split = 0; split < 3; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi
+          const uint32_t as = (split == 2) ? a_lo_s : a_hi_s, bs = (split == 1) ? b_lo_s : b_hi_s;
+#pragma unroll
+          for (int kk = 0; kk < kC / 8; ++kk) {
+            mma_tf32(tmem, smem_desc(as + kk * 2 * kLBO), smem_desc(bs + kk * 2 * kLBO), idesc, acc);
+            acc = 1;
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      }
+    } else {
+      // Q = xq Wq + bq for the 4 neighbourhoods: thread -> (neighbourhood tid/32, columns 2*(tid%32), +1)
+      {
+        const int g = tid >> 5, c0 = (tid & 31) * 2;
+        float q0 = s_bq[c0], q1 = s_bq[c0 + 1];
+#pragma unroll 8
+        for (int k = 0; k < kC; ++k) {
+          const float xv = s_xq[g * kC + k];
+          q0 = fmaf(xv, s_wq[k * kC + c0], q0);
+          q1 = fmaf(xv, s_wq[k * kC + c0 + 1], q1);
+        }
+        s_q[g * kC + c0] = q0;
+        s_q[g * kC + c0 + 1] = q1;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only: Q visible
+      // wait for the accumulator
+      uint32_t ok = 0, spins = 0;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(phase)
+                     : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost completion
+      } while (!ok);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+      // row r = tid of the tile: neighbourhood r / 32, sample row r % 32; with the raw reshape (attention_layer.py:35)
+      // this row holds pseudo-keys 16*(r&1) .. +15 of head (r % 32) / 2, four consecutive columns each
+      const int gl = tid >> 5, srow = tid & 31, head = srow >> 1;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      const float q0 = s_q[gl * kC + head * 4 + 0], q1 = s_q[gl * kC + head * 4 + 1], q2 = s_q[gl * kC + head * 4 + 2],
+                  q3 = s_q[gl * kC + head * 4 + 3];
+      uint32_t kv[kC];
+      PC_TMEM_LD16(taddr + 0, kv, 0);
+      PC_TMEM_LD16(taddr + 16, kv, 16);
+      PC_TMEM_LD16(taddr + 32, kv, 32);
+      PC_TMEM_LD16(taddr + 48, kv, 48);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float a[16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float k0 = __uint_as_float(kv[4 * j + 0]) + s_bk[4 * j + 0], k1 = __uint_as_float(kv[4 * j + 1]) + s_bk[4 * j + 1],
+                    k2 = __uint_as_float(kv[4 * j + 2]) + s_bk[4 * j + 2], k3 = __uint_as_float(kv[4 * j + 3]) + s_bk[4 * j + 3];
+        a[j] = 0.5f * fmaf(q3, k3, fmaf(q2, k2, fmaf(q1, k1, q0 * k0)));  // / sqrt(key_dim = 4)
+        mx = fmaxf(mx, a[j]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(PC_FULL_MASK, mx, 1));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { a[j] = expf(a[j] - mx); sum += a[j]; }
+      sum += __shfl_xor_sync(PC_FULL_MASK, sum, 1);
+      const float inv = 1.0f / sum;
+      PC_TMEM_LD16(taddr + 64, kv, 0);
+      PC_TMEM_LD16(taddr + 80, kv, 16);
+      PC_TMEM_LD16(taddr + 96, kv, 32);
+      PC_TMEM_LD16(taddr + 112, kv, 48);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float w = a[j] * inv;
+        o0 = fmaf(w, __uint_as_float(kv[4 * j + 0]) + s_bv[4 * j + 0], o0);
+        o1 = fmaf(w, __uint_as_float(kv[4 * j + 1]) + s_bv[4 * j + 1], o1);
+        o2 = fmaf(w, __uint_as_float(kv[4 * j + 2]) + s_bv[4 * j + 2], o2);
+        o3 = fmaf(w, __uint_as_float(kv[4 * j + 3]) + s_bv[4 * j + 3], o3);
+      }
+      o0 += __shfl_xor_sync(PC_FULL_MASK, o0, 1); o1 += __shfl_xor_sync(PC_FULL_MASK, o1, 1);
+      o2 += __shfl_xor_sync(PC_FULL_MASK, o2, 1); o3 += __shfl_xor_sync(PC_FULL_MASK, o3, 1);
+      const size_t g = (size_t)tile * 4 + gl;
+      if ((srow & 1) == 0 && g < (size_t)G)
+        *reinterpret_cast<float4 *>(out + g * kC + head * 4) = make_float4(o0, o1, o2, o3);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    phase ^= 1;
+    __syncthreads();  // accumulator and A operands free for the next tile
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
+  }
+}
+
+}  // namespace
+}  // namespace pc
+
+extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
+  (void)G;
+  if (S != pc::kS || C != pc::kC) return 0;
+  return (size_t)pc::kImageBytes;
+}
+
+extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq,
+                                      const float *bq, const float *wk, const float *bk, const float *wv,
+                                      const float *bv, float *out, void *workspace, pc_stream_t stream) {
+  if (G < 0 || S <= 0 || C <= 0) return PC_ERR_INVALID_ARGUMENT;
+  if (S != pc::kS || C != pc::kC) return PC_ERR_UNSUPPORTED;  // other widths: Dense + pc_attention_fwd
+  if (G == 0) return PC_OK;
+  if (!xq || !x || !wq || !wk || !wv || !out) return PC_ERR_INVALID_ARGUMENT;
+  if (!workspace) return PC_ERR_WORKSPACE;
+  if (!pc::aligned16(x) || !pc::aligned16(out) || !pc::aligned16(workspace)) return PC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *image = (unsigned char *)workspace;
+  pc::attention_layer_prep_kernel<<<(pc::kN * pc::kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
+  const size_t smem = 2 * pc::kOperandBytes + pc::kImageBytes + 8 * pc::kC * 4 + 64;
+  PC_CUDA_TRY(pc::allow_smem(pc::attention_layer_c64_kernel, smem));
+  const int ntiles = (int)(((size_t)G * pc::kS + pc::kRows - 1) / pc::kRows);
+  const int grid = ntiles < pc::num_sms() ? ntiles : pc::num_sms();
+  pc::attention_layer_c64_kernel<<<grid, pc::kThreads, smem, st>>>(G, xq, x, image, out);
+  PC_RETURN_LAUNCH_STATUS();
+}

@@ -493,3 +493,30 @@ def test_fused_fp_interpolate_equals_composition_and_oracle(c2, c1):
     assert same(p2.grad, cpu.three_interpolate_grad(p2_np, o3, w, npy(go)[..., :c2]))
     if c1:
         assert torch.equal(p1.grad, q1.grad)
+
+
+# -------------------------------------------------------------------- fused attention layer on tcgen05
+@pytest.mark.parametrize("G", [4, 7, 256, 1000])
+def test_attention_layer_fused_matches_oracle(G):
+    from pcops_b200.attention_layer import attention_layer_fused
+    rng = np.random.default_rng(G)
+    C, S = 64, 32
+    x = rng.standard_normal((G, S, C), dtype=np.float32)
+    xq = x[:, 0, :].copy()
+    W = [(rng.standard_normal((C, C), dtype=np.float32) / 8.0) for _ in range(3)]
+    bias = [rng.standard_normal(C, dtype=np.float32) * 0.1 for _ in range(3)]
+    want = cpu.attention_layer(x, xq, W[0], bias[0], W[1], bias[1], W[2], bias[2], C // 4, 4)
+    got = attention_layer_fused(cu(xq), cu(x), cu(W[0]), cu(bias[0]), cu(W[1]), cu(bias[1]), cu(W[2]), cu(bias[2]))
+    np.testing.assert_allclose(npy(got), want, rtol=1e-5, atol=2e-6)
+    # and the module: fused inference path == Dense + contraction path
+    layer = ops.AttentionLayer(4, 4, num_heads=16, in_features=C).to(DEV)
+    xt = cu(x).reshape(1, G, S, C)
+    with torch.no_grad():
+        a = layer([xt, xt[:, :, 0:1, :]])
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        b = layer([xt.requires_grad_(True), xt[:, :, 0:1, :]])     # grad enabled -> composition
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    np.testing.assert_allclose(npy(a), npy(b), rtol=2e-5, atol=2e-5)
