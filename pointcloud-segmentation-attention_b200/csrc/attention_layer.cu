@@ -8,13 +8,15 @@
 // Here (C = 64 only in this round; the other widths take the Dense + pc_attention_fwd composition):
 //   * a persistent CTA per SM keeps W_k | W_v resident in shared memory as the B operand (N = 128, K = 64);
 //   * per tile of 4 neighbourhoods (128 rows) the X rows are loaded once, split into TF32 hi / lo parts and written to
-//     shared memory in the UMMA K-major no-swizzle core-matrix layout;
+//     shared memory in the UMMA K-major 128-byte-swizzle layout;
 //   * one elected thread issues 24 tcgen05.mma (kind::tf32, M = 128, N = 128, K = 8): X_hi W_hi + X_hi W_lo + X_lo W_hi,
 //     i.e. 3xTF32 split accumulation in an fp32 TMEM accumulator (plain TF32 would miss the 1e-5 parity bound);
 //   * the epilogue reads each accumulator row straight from TMEM (tcgen05.ld 32x32b): with the reference's raw
 //     reshape a row of K (64 floats) is 16 pseudo-keys of one head, its neighbour row holds the other 16, so the
 //     softmax over the 32 pseudo-keys is register-local plus one shuffle; K and V never exist in memory.
-//   * Q (one row per neighbourhood) is a 64 x 64 GEMV on the CUDA cores of the same CTA.
+//   * Q (one row per neighbourhood) is a 64 x 64 GEMV on the CUDA cores of the same CTA;
+//   * two operand stages and two TMEM accumulators: the tensor core runs tile i+1 during the epilogue of tile i, and
+//     the global loads of tile i+2 are in flight meanwhile.
 #include <math.h>
 #include "common.cuh"
 
@@ -25,14 +27,18 @@ constexpr int kC = 64;            // layer width handled by this kernel
 constexpr int kS = 32;            // samples per neighbourhood
 constexpr int kRows = 128;        // rows per tile = 4 neighbourhoods
 constexpr int kN = 2 * kC;        // K | V columns
-constexpr int kLBO = 128;         // bytes between the two 16-byte K-halves of one MMA step (core matrices along K)
-constexpr int kSBO = (kC / 4) * kLBO;  // bytes between 8-row groups
-constexpr int kOperandBytes = (kRows / 8) * kSBO;  // 32 KB for a 128 x 64 tf32 operand
+// Operand layout in shared memory: UMMA K-major with 128-byte swizzle.  A row of K = 64 tf32 is two 128-byte segments
+// ("K blocks" of 32 elements); a K block of the operand is [row / 8][row % 8][128 bytes] with the eight 16-byte chunks
+// of a row XOR-permuted by row % 8 (Swizzle<3,4,3>); K blocks are 16 KB apart.  A warp's 128-bit stores of
+// consecutive float4s of a row then spread over all banks (4 wavefronts per 512 bytes, the minimum).
+constexpr int kSBO = 1024;                            // bytes between 8-row groups inside a K block
+constexpr int kKBlockBytes = (kRows / 8) * kSBO;      // 16 KB: 128 rows x 128 bytes
+constexpr int kOperandBytes = (kC / 32) * kKBlockBytes;  // 32 KB for a 128 x 64 tf32 operand
 constexpr int kImageBytes = 2 * kOperandBytes + kC * kC * 4 + 3 * kC * 4;  // B_hi | B_lo | Wq | bq | bk | bv
 constexpr int kThreads = 160;     // warps 0-3: loaders + epilogue (one TMEM lane quarter each); warp 4: MMA issuer
 
 __host__ __device__ inline int operand_offset(int row, int k) {  // byte offset of element (row, k), k in tf32 elements
-  return (row >> 3) * kSBO + (k >> 2) * kLBO + (row & 7) * 16 + (k & 3) * 4;
+  return (k >> 5) * kKBlockBytes + (row >> 3) * kSBO + (row & 7) * 128 + ((((k & 31) >> 2) ^ (row & 7)) << 4) + (k & 3) * 4;
 }
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -65,11 +71,14 @@ __global__ void attention_layer_prep_kernel(const float *__restrict__ wq, const 
 }
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-  // UMMA shared-memory descriptor, K-major, no swizzle: start address, LBO, SBO (16-byte units), version 1
-  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | ((uint32_t)(kLBO >> 4) << 16);
-  const uint32_t hi = (uint32_t)(kSBO >> 4) | (1u << 14);
+  // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start address (16-byte units), LBO = 1 (unused for swizzled
+  // K-major), SBO = 1024 bytes, version 1, layout type 2
+  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (1u << 16);
+  const uint32_t hi = (uint32_t)(kSBO >> 4) | (1u << 14) | (2u << 29);
   return ((uint64_t)hi << 32) | lo;
 }
+// start address of MMA K-step kk (8 tf32 = 32 bytes): K block kk / 4, then 32-byte steps inside the swizzled 128-byte row
+__device__ __forceinline__ uint32_t kstep_addr(uint32_t base, int kk) { return base + (kk >> 2) * kKBlockBytes + (kk & 3) * 32; }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -90,30 +99,53 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
                  "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                     \
                : "r"(addr))
 
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost arrival
+  } while (!ok);
+}
+
+// Software pipeline (one CTA per SM, persistent over tiles of 4 neighbourhoods):
+//   warps 0-3 ("workers"): X rows of tile i+1 are already in registers (prefetched one iteration ahead); they are split
+//            into TF32 hi / lo and stored into operand buffer (i+1)&1, then a_full[(i+1)&1] is signalled, the loads
+//            of tile i+2 are issued, Q of tile i+1 is computed on the CUDA cores, and only then the accumulator of
+//            tile i is awaited and its epilogue runs -- so the tensor core works on tile i+1 during the epilogue of i;
+//   warp 4:  waits a_full[s], issues the 24 UMMAs of the tile into accumulator s, commits to t_full[s].
+// Two operand buffers and two TMEM accumulators; every reuse hazard is ordered by the workers' own program order
+// (they observe t_full of tile i-2 before they overwrite its operands or let its accumulator be overwritten).
 __global__ void __launch_bounds__(kThreads, 1)
 attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__restrict__ x,
                            const unsigned char *__restrict__ image, float *__restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *a_hi = smem, *a_lo = smem + kOperandBytes;
-  unsigned char *b_img = smem + 2 * kOperandBytes;  // B_hi | B_lo | Wq | bq | bk | bv  (kImageBytes)
+  unsigned char *a_buf = smem;                          // [2 stages][hi | lo][kOperandBytes]
+  unsigned char *b_img = smem + 4 * kOperandBytes;      // B_hi | B_lo | Wq | bq | bk | bv  (kImageBytes)
   float *s_wq = reinterpret_cast<float *>(b_img + 2 * kOperandBytes);
   float *s_bq = s_wq + kC * kC, *s_bk = s_bq + kC, *s_bv = s_bk + kC;
   float *s_xq = reinterpret_cast<float *>(b_img + kImageBytes);  // [4][64]
-  float *s_q = s_xq + 4 * kC;                                    // [4][64]
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_q + 4 * kC);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1);
+  float *s_q = s_xq + 4 * kC;                                    // [2 stages][4][64]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_q + 8 * kC);  // a_full[2], t_full[2]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+  const uint32_t a_full[2] = {bar0, bar0 + 8}, t_full[2] = {bar0 + 16, bar0 + 24};
 
-  if (warp == 4) {  // TMEM: 128 fp32 columns x 128 lanes for the accumulator
+  if (warp == 4) {  // TMEM: two 128-column fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(s_tmem)),
-                 "r"(128u));
+                 "r"(256u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full[0]), "r"((uint32_t)kRows));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_full[1]), "r"((uint32_t)kRows));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full[0]), "r"(1u));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full[1]), "r"(1u));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   for (int i = tid; i < kImageBytes / 16; i += kThreads)
@@ -126,84 +158,55 @@ attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__r
 
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-  const uint32_t a_hi_s = (uint32_t)__cvta_generic_to_shared(a_hi), a_lo_s = (uint32_t)__cvta_generic_to_shared(a_lo);
+  const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(a_buf);
   const uint32_t b_hi_s = (uint32_t)__cvta_generic_to_shared(b_img), b_lo_s = b_hi_s + kOperandBytes;
-
   const size_t total_rows = (size_t)G * kS;
   const int ntiles = (int)((total_rows + kRows - 1) / kRows);
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const size_t row0 = (size_t)tile * kRows;
-    if (tid < kRows) {
-      // X tile: 128 rows x 64 floats, contiguous in memory -> coalesced float4 loads, hi / lo split, core-matrix stores
-      const float4 *src = reinterpret_cast<const float4 *>(x + row0 * kC);
-#pragma unroll 4
-      for (int i = 0; i < (kRows * kC / 4) / kRows; ++i) {
-        const int i4 = tid + kRows * i, row = i4 >> 4, kq = i4 & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + row < total_rows) v = __ldg(src + i4);
-        float4 h, l;
-        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-        const int off = operand_offset(row, kq * 4);
-        *reinterpret_cast<float4 *>(a_hi + off) = h;
-        *reinterpret_cast<float4 *>(a_lo + off) = l;
-      }
-      // query rows of the tile's 4 neighbourhoods
-      for (int i = tid; i < 4 * kC; i += kRows) {
-        const size_t g = (size_t)tile * 4 + (i >> 6);
-        s_xq[i] = (g < (size_t)G) ? __ldg(xq + g * kC + (i & 63)) : 0.f;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();  // operands + query rows in shared memory; previous tile's TMEM reads finished (end-of-loop sync)
-    if (warp == 4) {
-      if (lane == 0) {
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        mbar_wait(a_full[st], (it >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi_s = a_s + st * 2 * kOperandBytes, a_lo_s = a_hi_s + kOperandBytes;
         uint32_t acc = 0;
 #pragma unroll
         for (int split = 0; split < 3; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi
           const uint32_t as = (split == 2) ? a_lo_s : a_hi_s, bs = (split == 1) ? b_lo_s : b_hi_s;
 #pragma unroll
           for (int kk = 0; kk < kC / 8; ++kk) {
-            mma_tf32(tmem, smem_desc(as + kk * 2 * kLBO), smem_desc(bs + kk * 2 * kLBO), idesc, acc);
+            mma_tf32(tmem + st * kN, smem_desc(kstep_addr(as, kk)), smem_desc(kstep_addr(bs, kk)), idesc, acc);
             acc = 1;
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-      }
-    } else {
-      // Q = xq Wq + bq for the 4 neighbourhoods: thread -> (neighbourhood tid/32, columns 2*(tid%32), +1)
-      {
-        const int g = tid >> 5, c0 = (tid & 31) * 2;
-        float q0 = s_bq[c0], q1 = s_bq[c0 + 1];
-#pragma unroll 8
-        for (int k = 0; k < kC; ++k) {
-          const float xv = s_xq[g * kC + k];
-          q0 = fmaf(xv, s_wq[k * kC + c0], q0);
-          q1 = fmaf(xv, s_wq[k * kC + c0 + 1], q1);
-        }
-        s_q[g * kC + c0] = q0;
-        s_q[g * kC + c0 + 1] = q1;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only: Q visible
-      // wait for the accumulator
-      uint32_t ok = 0, spins = 0;
-      do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(phase)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_full[st])
                      : "memory");
-        if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost completion
-      } while (!ok);
+      }
+    }
+  } else {
+    constexpr int kLd = (kRows * kC / 4) / kRows;  // 16 float4 per worker thread per tile
+    float4 pre[kLd];
+    auto fetch = [&](int tile) {
+      const size_t row0 = (size_t)tile * kRows;
+      const float4 *src = reinterpret_cast<const float4 *>(x + row0 * kC);
+#pragma unroll
+      for (int i = 0; i < kLd; ++i) {
+        const int i4 = tid + kRows * i;
+        pre[i] = (tile < ntiles && row0 + (i4 >> 4) < total_rows) ? __ldg(src + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto epilogue = [&](int tile, int it) {
+      const int st = it & 1;
+      mbar_wait(t_full[st], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
       // row r = tid of the tile: neighbourhood r / 32, sample row r % 32; with the raw reshape (attention_layer.py:35)
       // this row holds pseudo-keys 16*(r&1) .. +15 of head (r % 32) / 2, four consecutive columns each
       const int gl = tid >> 5, srow = tid & 31, head = srow >> 1;
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-      const float q0 = s_q[gl * kC + head * 4 + 0], q1 = s_q[gl * kC + head * 4 + 1], q2 = s_q[gl * kC + head * 4 + 2],
-                  q3 = s_q[gl * kC + head * 4 + 3];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + st * kN;
+      const float *q = s_q + st * 4 * kC + gl * kC + head * 4;
+      const float q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
       uint32_t kv[kC];
       PC_TMEM_LD16(taddr + 0, kv, 0);
       PC_TMEM_LD16(taddr + 16, kv, 16);
@@ -244,13 +247,56 @@ attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__r
       const size_t g = (size_t)tile * 4 + gl;
       if ((srow & 1) == 0 && g < (size_t)G)
         *reinterpret_cast<float4 *>(out + g * kC + head * 4) = make_float4(o0, o1, o2, o3);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // orders these TMEM reads before later arrivals
+    };
+
+    fetch(blockIdx.x);
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      unsigned char *a_hi = a_buf + st * 2 * kOperandBytes, *a_lo = a_hi + kOperandBytes;
+#pragma unroll
+      for (int i = 0; i < kLd; ++i) {  // hi / lo split, core-matrix stores
+        const int i4 = tid + kRows * i, row = i4 >> 4, kq = i4 & 15;
+        const float4 v = pre[i];
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        const int off = operand_offset(row, kq * 4);
+        *reinterpret_cast<float4 *>(a_hi + off) = h;
+        *reinterpret_cast<float4 *>(a_lo + off) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full[st]) : "memory");
+      fetch(tile + gridDim.x);  // next tile's rows: in flight during everything below
+      // Q = xq Wq + bq for this tile's 4 neighbourhoods: thread -> (neighbourhood tid/32, columns 2*(tid%32), +1)
+      for (int i = tid; i < 4 * kC; i += kRows) {
+        const size_t g = (size_t)tile * 4 + (i >> 6);
+        s_xq[i] = (g < (size_t)G) ? __ldg(xq + g * kC + (i & 63)) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      {
+        const int g = tid >> 5, c0 = (tid & 31) * 2;
+        float q0 = s_bq[c0], q1 = s_bq[c0 + 1];
+#pragma unroll 8
+        for (int k = 0; k < kC; ++k) {
+          const float xv = s_xq[g * kC + k];
+          q0 = fmaf(xv, s_wq[k * kC + c0], q0);
+          q1 = fmaf(xv, s_wq[k * kC + c0 + 1], q1);
+        }
+        s_q[st * 4 * kC + g * kC + c0] = q0;
+        s_q[st * 4 * kC + g * kC + c0 + 1] = q1;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // Q of this tile visible, s_xq reusable
+      if (prev_tile >= 0) epilogue(prev_tile, it - 1);  // the tensor core is busy with `tile` meanwhile
+      prev_tile = tile;
     }
-    phase ^= 1;
-    __syncthreads();  // accumulator and A operands free for the next tile
+    if (prev_tile >= 0) epilogue(prev_tile, it - 1);
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
   }
 }
 
@@ -275,7 +321,7 @@ extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, cons
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char *image = (unsigned char *)workspace;
   pc::attention_layer_prep_kernel<<<(pc::kN * pc::kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
-  const size_t smem = 2 * pc::kOperandBytes + pc::kImageBytes + 8 * pc::kC * 4 + 64;
+  const size_t smem = 4 * pc::kOperandBytes + pc::kImageBytes + 12 * pc::kC * 4 + 64;
   PC_CUDA_TRY(pc::allow_smem(pc::attention_layer_c64_kernel, smem));
   const int ntiles = (int)(((size_t)G * pc::kS + pc::kRows - 1) / pc::kRows);
   const int grid = ntiles < pc::num_sms() ? ntiles : pc::num_sms();
