@@ -14,9 +14,9 @@
 //   * the epilogue reads each accumulator row straight from TMEM (tcgen05.ld 32x32b): with the reference's raw
 //     reshape a row of K (64 floats) is 16 pseudo-keys of one head, its neighbour row holds the other 16, so the
 //     softmax over the 32 pseudo-keys is register-local plus one shuffle; K and V never exist in memory.
-//   * Q (one row per neighbourhood) is a 64 x 64 GEMV on the CUDA cores of the same CTA;
-//   * two operand stages and two TMEM accumulators: the tensor core runs tile i+1 during the epilogue of tile i, and
-//     the global loads of tile i+2 are in flight meanwhile.
+//   * Q (one row per neighbourhood) is a 64 x 64 GEMV done by a small CUDA-core kernel in front (0.5 % of the work);
+//   * two worker groups with their own operand stage and TMEM accumulator run half a tile out of phase, so global
+//     loads, tensor-core work and epilogues of neighbouring tiles overlap.
 #include <math.h>
 #include "common.cuh"
 
@@ -35,7 +35,7 @@ constexpr int kSBO = 1024;                            // bytes between 8-row gro
 constexpr int kKBlockBytes = (kRows / 8) * kSBO;      // 16 KB: 128 rows x 128 bytes
 constexpr int kOperandBytes = (kC / 32) * kKBlockBytes;  // 32 KB for a 128 x 64 tf32 operand
 constexpr int kImageBytes = 2 * kOperandBytes + kC * kC * 4 + 3 * kC * 4;  // B_hi | B_lo | Wq | bq | bk | bv
-constexpr int kThreads = 160;     // warps 0-3: loaders + epilogue (one TMEM lane quarter each); warp 4: MMA issuer
+constexpr int kThreads = 288;     // warps 0-3, 4-7: two worker groups (loader + epilogue); warp 8: MMA issuer
 
 __host__ __device__ inline int operand_offset(int row, int k) {  // byte offset of element (row, k), k in tf32 elements
   return (k >> 5) * kKBlockBytes + (row >> 3) * kSBO + (row & 7) * 128 + ((((k & 31) >> 2) ^ (row & 7)) << 4) + (k & 3) * 4;
@@ -67,6 +67,27 @@ __global__ void attention_layer_prep_kernel(const float *__restrict__ wq, const 
     tail[kC * kC + t] = bq ? bq[t] : 0.f;
     tail[kC * kC + kC + t] = bk ? bk[t] : 0.f;
     tail[kC * kC + 2 * kC + t] = bv ? bv[t] : 0.f;
+  }
+}
+
+// Q = xq Wq + bq for every neighbourhood (G x 64 outputs, 64 MACs each: 0.5 % of the layer's work) into a scratch the
+// main kernel's epilogue reads back through L2; keeps the serial 64-step GEMV off the tile pipeline's critical path.
+__global__ void __launch_bounds__(256)
+attention_layer_q_kernel(int G, const float *__restrict__ xq, const float *__restrict__ wq, const float *__restrict__ bq,
+                         float *__restrict__ q) {
+  __shared__ float s_w[kC * kC];
+  __shared__ float s_x[4][kC];
+  for (int i = threadIdx.x; i < kC * kC; i += 256) s_w[i] = __ldg(wq + i);
+  const int gl = threadIdx.x >> 6, c = threadIdx.x & 63;
+  for (int g0 = blockIdx.x * 4; g0 < G; g0 += gridDim.x * 4) {
+    __syncthreads();
+    const int g = g0 + gl;
+    s_x[gl][c] = (g < G) ? __ldg(xq + (size_t)g * kC + c) : 0.f;
+    __syncthreads();
+    float acc = bq ? __ldg(bq + c) : 0.f;
+#pragma unroll 16
+    for (int k = 0; k < kC; ++k) acc = fmaf(s_x[gl][k], s_w[k * kC + c], acc);
+    if (g < G) q[(size_t)g * kC + c] = acc;
   }
 }
 
@@ -110,32 +131,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
-// Software pipeline (one CTA per SM, persistent over tiles of 4 neighbourhoods):
-//   warps 0-3 ("workers"): X rows of tile i+1 are already in registers (prefetched one iteration ahead); they are split
-//            into TF32 hi / lo and stored into operand buffer (i+1)&1, then a_full[(i+1)&1] is signalled, the loads
-//            of tile i+2 are issued, Q of tile i+1 is computed on the CUDA cores, and only then the accumulator of
-//            tile i is awaited and its epilogue runs -- so the tensor core works on tile i+1 during the epilogue of i;
-//   warp 4:  waits a_full[s], issues the 24 UMMAs of the tile into accumulator s, commits to t_full[s].
-// Two operand buffers and two TMEM accumulators; every reuse hazard is ordered by the workers' own program order
-// (they observe t_full of tile i-2 before they overwrite its operands or let its accumulator be overwritten).
+// Pipeline (one CTA per SM, persistent over tiles of 4 neighbourhoods = 128 rows):
+//   warps 0-3 and warps 4-7 are two identical worker groups; group g owns operand stage g and TMEM accumulator g and
+//   takes every second tile of the CTA.  Per tile a group: splits the X rows it prefetched into registers into TF32
+//   hi / lo, stores them into its operand stage, signals a_full[g], issues the global loads of its NEXT tile, waits
+//   for t_full[g] and runs the epilogue -- while the other group is half a tile out of phase, so loads, tensor-core
+//   work and epilogues of neighbouring tiles overlap;
+//   warp 8: waits a_full[s], issues the 24 UMMAs of the tile into accumulator s, commits to t_full[s].
+// Reuse hazards are ordered by each group's own program order (it observes t_full of its previous tile before it
+// overwrites that tile's operands or lets the accumulator be overwritten).
 __global__ void __launch_bounds__(kThreads, 1)
-attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__restrict__ x,
+attention_layer_c64_kernel(int G, const float *__restrict__ qg, const float *__restrict__ x,
                            const unsigned char *__restrict__ image, float *__restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *a_buf = smem;                          // [2 stages][hi | lo][kOperandBytes]
   unsigned char *b_img = smem + 4 * kOperandBytes;      // B_hi | B_lo | Wq | bq | bk | bv  (kImageBytes)
-  float *s_wq = reinterpret_cast<float *>(b_img + 2 * kOperandBytes);
-  float *s_bq = s_wq + kC * kC, *s_bk = s_bq + kC, *s_bv = s_bk + kC;
-  float *s_xq = reinterpret_cast<float *>(b_img + kImageBytes);  // [4][64]
-  float *s_q = s_xq + 4 * kC;                                    // [2 stages][4][64]
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_q + 8 * kC);  // a_full[2], t_full[2]
+  float *s_bk = reinterpret_cast<float *>(b_img + 2 * kOperandBytes) + kC * kC + kC, *s_bv = s_bk + kC;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(b_img + kImageBytes);  // a_full[2], t_full[2]
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
   const uint32_t a_full[2] = {bar0, bar0 + 8}, t_full[2] = {bar0 + 16, bar0 + 24};
 
-  if (warp == 4) {  // TMEM: two 128-column fp32 accumulators
+  if (warp == 8) {  // TMEM: two 128-column fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(s_tmem)),
                  "r"(256u));
@@ -163,7 +182,7 @@ attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__r
   const size_t total_rows = (size_t)G * kS;
   const int ntiles = (int)((total_rows + kRows - 1) / kRows);
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -186,78 +205,26 @@ attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__r
       }
     }
   } else {
-    constexpr int kLd = (kRows * kC / 4) / kRows;  // 16 float4 per worker thread per tile
+    const int grp = tid >> 7, wt = tid & 127, wq4 = warp & 3;  // worker group, thread in group, TMEM lane quarter
+    constexpr int kLd = (kRows * kC / 4) / kRows;               // 16 float4 per worker thread per tile
     float4 pre[kLd];
     auto fetch = [&](int tile) {
       const size_t row0 = (size_t)tile * kRows;
       const float4 *src = reinterpret_cast<const float4 *>(x + row0 * kC);
 #pragma unroll
       for (int i = 0; i < kLd; ++i) {
-        const int i4 = tid + kRows * i;
+        const int i4 = wt + kRows * i;
         pre[i] = (tile < ntiles && row0 + (i4 >> 4) < total_rows) ? __ldg(src + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto epilogue = [&](int tile, int it) {
-      const int st = it & 1;
-      mbar_wait(t_full[st], (it >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // row r = tid of the tile: neighbourhood r / 32, sample row r % 32; with the raw reshape (attention_layer.py:35)
-      // this row holds pseudo-keys 16*(r&1) .. +15 of head (r % 32) / 2, four consecutive columns each
-      const int gl = tid >> 5, srow = tid & 31, head = srow >> 1;
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + st * kN;
-      const float *q = s_q + st * 4 * kC + gl * kC + head * 4;
-      const float q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-      uint32_t kv[kC];
-      PC_TMEM_LD16(taddr + 0, kv, 0);
-      PC_TMEM_LD16(taddr + 16, kv, 16);
-      PC_TMEM_LD16(taddr + 32, kv, 32);
-      PC_TMEM_LD16(taddr + 48, kv, 48);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float a[16];
-      float mx = -INFINITY;
+    unsigned char *a_hi = a_buf + grp * 2 * kOperandBytes, *a_lo = a_hi + kOperandBytes;
+    const int stride2 = 2 * gridDim.x;
+    int tile = blockIdx.x + grp * gridDim.x;
+    fetch(tile);
+    for (int k = 0; tile < ntiles; tile += stride2, ++k) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float k0 = __uint_as_float(kv[4 * j + 0]) + s_bk[4 * j + 0], k1 = __uint_as_float(kv[4 * j + 1]) + s_bk[4 * j + 1],
-                    k2 = __uint_as_float(kv[4 * j + 2]) + s_bk[4 * j + 2], k3 = __uint_as_float(kv[4 * j + 3]) + s_bk[4 * j + 3];
-        a[j] = 0.5f * fmaf(q3, k3, fmaf(q2, k2, fmaf(q1, k1, q0 * k0)));  // / sqrt(key_dim = 4)
-        mx = fmaxf(mx, a[j]);
-      }
-      mx = fmaxf(mx, __shfl_xor_sync(PC_FULL_MASK, mx, 1));
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { a[j] = expf(a[j] - mx); sum += a[j]; }
-      sum += __shfl_xor_sync(PC_FULL_MASK, sum, 1);
-      const float inv = 1.0f / sum;
-      PC_TMEM_LD16(taddr + 64, kv, 0);
-      PC_TMEM_LD16(taddr + 80, kv, 16);
-      PC_TMEM_LD16(taddr + 96, kv, 32);
-      PC_TMEM_LD16(taddr + 112, kv, 48);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float w = a[j] * inv;
-        o0 = fmaf(w, __uint_as_float(kv[4 * j + 0]) + s_bv[4 * j + 0], o0);
-        o1 = fmaf(w, __uint_as_float(kv[4 * j + 1]) + s_bv[4 * j + 1], o1);
-        o2 = fmaf(w, __uint_as_float(kv[4 * j + 2]) + s_bv[4 * j + 2], o2);
-        o3 = fmaf(w, __uint_as_float(kv[4 * j + 3]) + s_bv[4 * j + 3], o3);
-      }
-      o0 += __shfl_xor_sync(PC_FULL_MASK, o0, 1); o1 += __shfl_xor_sync(PC_FULL_MASK, o1, 1);
-      o2 += __shfl_xor_sync(PC_FULL_MASK, o2, 1); o3 += __shfl_xor_sync(PC_FULL_MASK, o3, 1);
-      const size_t g = (size_t)tile * 4 + gl;
-      if ((srow & 1) == 0 && g < (size_t)G)
-        *reinterpret_cast<float4 *>(out + g * kC + head * 4) = make_float4(o0, o1, o2, o3);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // orders these TMEM reads before later arrivals
-    };
-
-    fetch(blockIdx.x);
-    int it = 0, prev_tile = -1;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int st = it & 1;
-      unsigned char *a_hi = a_buf + st * 2 * kOperandBytes, *a_lo = a_hi + kOperandBytes;
-#pragma unroll
-      for (int i = 0; i < kLd; ++i) {  // hi / lo split, core-matrix stores
-        const int i4 = tid + kRows * i, row = i4 >> 4, kq = i4 & 15;
+      for (int i = 0; i < kLd; ++i) {  // hi / lo split, swizzled stores
+        const int i4 = wt + kRows * i, row = i4 >> 4, kq = i4 & 15;
         const float4 v = pre[i];
         float4 h, l;
         h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -267,35 +234,66 @@ attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__r
         *reinterpret_cast<float4 *>(a_lo + off) = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full[st]) : "memory");
-      fetch(tile + gridDim.x);  // next tile's rows: in flight during everything below
-      // Q = xq Wq + bq for this tile's 4 neighbourhoods: thread -> (neighbourhood tid/32, columns 2*(tid%32), +1)
-      for (int i = tid; i < 4 * kC; i += kRows) {
-        const size_t g = (size_t)tile * 4 + (i >> 6);
-        s_xq[i] = (g < (size_t)G) ? __ldg(xq + g * kC + (i & 63)) : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      {
-        const int g = tid >> 5, c0 = (tid & 31) * 2;
-        float q0 = s_bq[c0], q1 = s_bq[c0 + 1];
-#pragma unroll 8
-        for (int k = 0; k < kC; ++k) {
-          const float xv = s_xq[g * kC + k];
-          q0 = fmaf(xv, s_wq[k * kC + c0], q0);
-          q1 = fmaf(xv, s_wq[k * kC + c0 + 1], q1);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full[grp]) : "memory");
+      fetch(tile + stride2);  // this group's next tile: in flight during the wait and the epilogue below
+
+      // row r = wt of the tile: neighbourhood r / 32, sample row r % 32; with the raw reshape (attention_layer.py:35)
+      // this row holds pseudo-keys 16*(r&1) .. +15 of head (r % 32) / 2, four consecutive columns each
+      const int gl = wt >> 5, srow = wt & 31, head = srow >> 1;
+      const size_t g = (size_t)tile * 4 + gl;
+      const float4 q4 = (g < (size_t)G) ? __ldg(reinterpret_cast<const float4 *>(qg + g * kC + head * 4))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(t_full[grp], k & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(wq4 * 32) << 16) + grp * kN;
+      float a[16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // K columns 16c .. 16c+15 = pseudo-keys 4c .. 4c+3 of this row
+        uint32_t kv[16];
+        PC_TMEM_LD16(taddr + 16 * c, kv, 0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = 16 * c + 4 * j;
+          const float k0 = __uint_as_float(kv[4 * j + 0]) + s_bk[col + 0], k1 = __uint_as_float(kv[4 * j + 1]) + s_bk[col + 1],
+                      k2 = __uint_as_float(kv[4 * j + 2]) + s_bk[col + 2], k3 = __uint_as_float(kv[4 * j + 3]) + s_bk[col + 3];
+          a[4 * c + j] = 0.5f * fmaf(q4.w, k3, fmaf(q4.z, k2, fmaf(q4.y, k1, q4.x * k0)));  // / sqrt(key_dim = 4)
+          mx = fmaxf(mx, a[4 * c + j]);
         }
-        s_q[st * 4 * kC + g * kC + c0] = q0;
-        s_q[st * 4 * kC + g * kC + c0 + 1] = q1;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // Q of this tile visible, s_xq reusable
-      if (prev_tile >= 0) epilogue(prev_tile, it - 1);  // the tensor core is busy with `tile` meanwhile
-      prev_tile = tile;
+      mx = fmaxf(mx, __shfl_xor_sync(PC_FULL_MASK, mx, 1));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { a[j] = expf(a[j] - mx); sum += a[j]; }
+      sum += __shfl_xor_sync(PC_FULL_MASK, sum, 1);
+      const float inv = 1.0f / sum;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t kv[16];
+        PC_TMEM_LD16(taddr + kC + 16 * c, kv, 0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = 16 * c + 4 * j;
+          const float w = a[4 * c + j] * inv;
+          o0 = fmaf(w, __uint_as_float(kv[4 * j + 0]) + s_bv[col + 0], o0);
+          o1 = fmaf(w, __uint_as_float(kv[4 * j + 1]) + s_bv[col + 1], o1);
+          o2 = fmaf(w, __uint_as_float(kv[4 * j + 2]) + s_bv[col + 2], o2);
+          o3 = fmaf(w, __uint_as_float(kv[4 * j + 3]) + s_bv[col + 3], o3);
+        }
+      }
+      o0 += __shfl_xor_sync(PC_FULL_MASK, o0, 1); o1 += __shfl_xor_sync(PC_FULL_MASK, o1, 1);
+      o2 += __shfl_xor_sync(PC_FULL_MASK, o2, 1); o3 += __shfl_xor_sync(PC_FULL_MASK, o3, 1);
+      if ((srow & 1) == 0 && g < (size_t)G)
+        *reinterpret_cast<float4 *>(out + g * kC + head * 4) = make_float4(o0, o1, o2, o3);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // orders these TMEM reads before later arrivals
     }
-    if (prev_tile >= 0) epilogue(prev_tile, it - 1);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
   }
 }
@@ -305,8 +303,8 @@ attention_layer_c64_kernel(int G, const float *__restrict__ xq, const float *__r
 
 extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
   (void)G;
-  if (S != pc::kS || C != pc::kC) return 0;
-  return (size_t)pc::kImageBytes;
+  if (S != pc::kS || C != pc::kC || G <= 0) return 0;
+  return (size_t)((pc::kImageBytes + 255) / 256) * 256 + (size_t)G * pc::kC * sizeof(float);  // operand image | Q scratch
 }
 
 extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq,
@@ -321,10 +319,13 @@ extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, cons
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char *image = (unsigned char *)workspace;
   pc::attention_layer_prep_kernel<<<(pc::kN * pc::kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
-  const size_t smem = 4 * pc::kOperandBytes + pc::kImageBytes + 12 * pc::kC * 4 + 64;
+  float *qbuf = reinterpret_cast<float *>(image + ((pc::kImageBytes + 255) / 256) * 256);
+  const int qblocks = (G + 3) / 4 < pc::num_sms() * 4 ? (G + 3) / 4 : pc::num_sms() * 4;
+  pc::attention_layer_q_kernel<<<qblocks, 256, 0, st>>>(G, xq, wq, bq, qbuf);
+  const size_t smem = 4 * pc::kOperandBytes + pc::kImageBytes + 64;
   PC_CUDA_TRY(pc::allow_smem(pc::attention_layer_c64_kernel, smem));
   const int ntiles = (int)(((size_t)G * pc::kS + pc::kRows - 1) / pc::kRows);
   const int grid = ntiles < pc::num_sms() ? ntiles : pc::num_sms();
-  pc::attention_layer_c64_kernel<<<grid, pc::kThreads, smem, st>>>(G, xq, x, image, out);
+  pc::attention_layer_c64_kernel<<<grid, pc::kThreads, smem, st>>>(G, qbuf, x, image, out);
   PC_RETURN_LAUNCH_STATUS();
 }
