@@ -75,19 +75,42 @@ __global__ void attention_layer_prep_kernel(const float *__restrict__ wq, const 
 __global__ void __launch_bounds__(256)
 attention_layer_q_kernel(int G, const float *__restrict__ xq, const float *__restrict__ wq, const float *__restrict__ bq,
                          float *__restrict__ q) {
-  __shared__ float s_w[kC * kC];
-  __shared__ float s_x[4][kC];
+  __shared__ __align__(16) float s_w[kC * kC];
+  __shared__ __align__(16) float s_x[64][kC + 4];  // 64 query rows per step; +4 keeps float4 rows aligned, spreads banks
   for (int i = threadIdx.x; i < kC * kC; i += 256) s_w[i] = __ldg(wq + i);
-  const int gl = threadIdx.x >> 6, c = threadIdx.x & 63;
-  for (int g0 = blockIdx.x * 4; g0 < G; g0 += gridDim.x * 4) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // thread -> rows 4*ty..+3, columns 4*tx..+3
+  float bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bias[j] = bq ? __ldg(bq + 4 * tx + j) : 0.f;
+  for (int g0 = blockIdx.x * 64; g0 < G; g0 += gridDim.x * 64) {
     __syncthreads();
-    const int g = g0 + gl;
-    s_x[gl][c] = (g < G) ? __ldg(xq + (size_t)g * kC + c) : 0.f;
+    for (int i = threadIdx.x; i < 64 * (kC / 4); i += 256) {
+      const int r = i >> 4, c4 = i & 15;
+      const float4 v = (g0 + r < G) ? __ldg(reinterpret_cast<const float4 *>(xq + (size_t)(g0 + r) * kC) + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4 *>(&s_x[r][4 * c4]) = v;
+    }
     __syncthreads();
-    float acc = bq ? __ldg(bq + c) : 0.f;
-#pragma unroll 16
-    for (int k = 0; k < kC; ++k) acc = fmaf(s_x[gl][k], s_w[k * kC + c], acc);
-    if (g < G) q[(size_t)g * kC + c] = acc;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = bias[j];
+#pragma unroll 8
+    for (int k = 0; k < kC; ++k) {  // every output accumulates k = 0 .. 63 in order
+      const float4 w = *reinterpret_cast<const float4 *>(&s_w[k * kC + 4 * tx]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xv = s_x[4 * ty + i][k];
+        acc[i][0] = fmaf(xv, w.x, acc[i][0]); acc[i][1] = fmaf(xv, w.y, acc[i][1]);
+        acc[i][2] = fmaf(xv, w.z, acc[i][2]); acc[i][3] = fmaf(xv, w.w, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int g = g0 + 4 * ty + i;
+      if (g < G) *reinterpret_cast<float4 *>(q + (size_t)g * kC + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
   }
 }
 
@@ -248,41 +271,38 @@ attention_layer_c64_kernel(int G, const float *__restrict__ qg, const float *__r
       const uint32_t taddr = tmem + ((uint32_t)(wq4 * 32) << 16) + grp * kN;
       float a[16];
       float mx = -INFINITY;
+      uint32_t kv[kC];
+      PC_TMEM_LD16(taddr + 0, kv, 0);    // the row's 64 K columns = pseudo-keys 0..15 of this row, one wait
+      PC_TMEM_LD16(taddr + 16, kv, 16);
+      PC_TMEM_LD16(taddr + 32, kv, 32);
+      PC_TMEM_LD16(taddr + 48, kv, 48);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {  // K columns 16c .. 16c+15 = pseudo-keys 4c .. 4c+3 of this row
-        uint32_t kv[16];
-        PC_TMEM_LD16(taddr + 16 * c, kv, 0);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = 16 * c + 4 * j;
-          const float k0 = __uint_as_float(kv[4 * j + 0]) + s_bk[col + 0], k1 = __uint_as_float(kv[4 * j + 1]) + s_bk[col + 1],
-                      k2 = __uint_as_float(kv[4 * j + 2]) + s_bk[col + 2], k3 = __uint_as_float(kv[4 * j + 3]) + s_bk[col + 3];
-          a[4 * c + j] = 0.5f * fmaf(q4.w, k3, fmaf(q4.z, k2, fmaf(q4.y, k1, q4.x * k0)));  // / sqrt(key_dim = 4)
-          mx = fmaxf(mx, a[4 * c + j]);
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float k0 = __uint_as_float(kv[4 * j + 0]) + s_bk[4 * j + 0], k1 = __uint_as_float(kv[4 * j + 1]) + s_bk[4 * j + 1],
+                    k2 = __uint_as_float(kv[4 * j + 2]) + s_bk[4 * j + 2], k3 = __uint_as_float(kv[4 * j + 3]) + s_bk[4 * j + 3];
+        a[j] = 0.5f * fmaf(q4.w, k3, fmaf(q4.z, k2, fmaf(q4.y, k1, q4.x * k0)));  // / sqrt(key_dim = 4)
+        mx = fmaxf(mx, a[j]);
       }
+      PC_TMEM_LD16(taddr + kC + 0, kv, 0);   // V columns: in flight during the softmax
+      PC_TMEM_LD16(taddr + kC + 16, kv, 16);
+      PC_TMEM_LD16(taddr + kC + 32, kv, 32);
+      PC_TMEM_LD16(taddr + kC + 48, kv, 48);
       mx = fmaxf(mx, __shfl_xor_sync(PC_FULL_MASK, mx, 1));
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { a[j] = expf(a[j] - mx); sum += a[j]; }
+      for (int j = 0; j < 16; ++j) { a[j] = exp2f((a[j] - mx) * 1.4426950408889634f); sum += a[j]; }  // MUFU.EX2, rel. err ~1e-7
       sum += __shfl_xor_sync(PC_FULL_MASK, sum, 1);
       const float inv = 1.0f / sum;
       float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t kv[16];
-        PC_TMEM_LD16(taddr + kC + 16 * c, kv, 0);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = 16 * c + 4 * j;
-          const float w = a[4 * c + j] * inv;
-          o0 = fmaf(w, __uint_as_float(kv[4 * j + 0]) + s_bv[col + 0], o0);
-          o1 = fmaf(w, __uint_as_float(kv[4 * j + 1]) + s_bv[col + 1], o1);
-          o2 = fmaf(w, __uint_as_float(kv[4 * j + 2]) + s_bv[col + 2], o2);
-          o3 = fmaf(w, __uint_as_float(kv[4 * j + 3]) + s_bv[col + 3], o3);
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float w = a[j] * inv;
+        o0 = fmaf(w, __uint_as_float(kv[4 * j + 0]) + s_bv[4 * j + 0], o0);
+        o1 = fmaf(w, __uint_as_float(kv[4 * j + 1]) + s_bv[4 * j + 1], o1);
+        o2 = fmaf(w, __uint_as_float(kv[4 * j + 2]) + s_bv[4 * j + 2], o2);
+        o3 = fmaf(w, __uint_as_float(kv[4 * j + 3]) + s_bv[4 * j + 3], o3);
       }
       o0 += __shfl_xor_sync(PC_FULL_MASK, o0, 1); o1 += __shfl_xor_sync(PC_FULL_MASK, o1, 1);
       o2 += __shfl_xor_sync(PC_FULL_MASK, o2, 1); o3 += __shfl_xor_sync(PC_FULL_MASK, o3, 1);
@@ -320,7 +340,7 @@ extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, cons
   unsigned char *image = (unsigned char *)workspace;
   pc::attention_layer_prep_kernel<<<(pc::kN * pc::kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
   float *qbuf = reinterpret_cast<float *>(image + ((pc::kImageBytes + 255) / 256) * 256);
-  const int qblocks = (G + 3) / 4 < pc::num_sms() * 4 ? (G + 3) / 4 : pc::num_sms() * 4;
+  const int qblocks = (G + 63) / 64 < pc::num_sms() * 2 ? (G + 63) / 64 : pc::num_sms() * 2;
   pc::attention_layer_q_kernel<<<qblocks, 256, 0, st>>>(G, xq, wq, bq, qbuf);
   const size_t smem = 4 * pc::kOperandBytes + pc::kImageBytes + 64;
   PC_CUDA_TRY(pc::allow_smem(pc::attention_layer_c64_kernel, smem));
