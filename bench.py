@@ -196,6 +196,50 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def time_fused_attention_layer(torch, ops, G):
+    from pcops_b200.attention_layer import attention_contract, attention_layer_fused
+    g = torch.Generator(device="cuda").manual_seed(5)
+    C, S = 64, 32
+    x = torch.randn(G, S, C, generator=g, device="cuda")
+    xq = x[:, 0, :].contiguous()
+    W = [torch.randn(C, C, generator=g, device="cuda") / 8 for _ in range(3)]
+    b = [torch.randn(C, generator=g, device="cuda") * 0.1 for _ in range(3)]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def comp():
+        return attention_contract(xq @ W[0] + b[0], x @ W[1] + b[1], x @ W[2] + b[2], C // 4, 4)
+
+    def fused():
+        return attention_layer_fused(xq, x, W[0], b[0], W[1], b[1], W[2], b[2])
+
+    def graph_ms(fn):
+        fn()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        ts = []
+        for _ in range(12):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+    try:
+        a, c = fused(), comp()
+        err = float(((a - c).abs().max() / c.abs().max()).item())
+        tf, tc = graph_ms(fused), graph_ms(comp)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    flops = 3 * 2.0 * G * S * C * 2 * C  # 3xTF32 split: three UMMA passes over the K|V projection
+    return {"shape": "G=%d S=32 C=64 heads=16 key_dim=4" % G, "fused_ms": tf, "fp32_cublas_composition_ms": tc,
+            "speedup": tc / tf, "max_rel_err_vs_fp32": err, "tf32_mma_tflops": flops / (tf * 1e-3) / 1e12,
+            "tensor_peak_note": "dense tf32 nominal 1.1 PFLOP/s; 3xTF32 split triples the issued flops"}
+
+
 def bind_to_gpu_cpus(index):
     """Pin this rank to the host cores NVML reports as local to GPU `index`, BEFORE any pinned buffer is allocated, so
     first-touch puts the staging memory on the GPU's NUMA node (with 8 ranks the host links are the e2e bottleneck)."""
@@ -407,7 +451,7 @@ def main():
                 "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms,
                 "peak_source": "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock)" % (nsm, sm_max)}
 
-    rooflines, op_ms, grid_ms = {}, {}, {}
+    rooflines, op_ms, grid_ms, fused_layer = {}, {}, {}, None
     if not args.skip_probe:
         # Every op's stand-alone duration: one pipeline instance alone, eager, ONE stream.  The table is taken with the
         # reference-signature ops (all-pairs ball query / three_nn, separate gather), whose algorithmic op counts the
@@ -433,6 +477,12 @@ def main():
         if args.grid:
             g = probe(pipe)
             grid_ms = {n: ms for n, ms in g.items() if n.startswith(("query_ball", "three_nn", "fps"))}
+        # The fused AttentionLayer (Dense Q/K/V + contraction on tcgen05, csrc/attention_layer.cu) at the SA1 shape, next
+        # to the composition it replaces (three fp32 cuBLAS GEMMs + pc_attention_fwd); GPU time of a CUDA-graph replay.
+        try:
+            fused_layer = time_fused_attention_layer(torch, pcops_b200, B * 1024)
+        except Exception as exc:  # reported, never fatal for the headline numbers
+            fused_layer = {"error": str(exc)[:200]}
     if probes:
         d = [a.elapsed_time(b) for a, b in probes[top_guess]]
         top_ms = sum(d) / len(d)
@@ -501,6 +551,7 @@ def main():
         "roofline": roofline,
         "rooflines": rooflines,
         "grid_variants_ms": grid_ms,
+        "attention_layer_tcgen05": fused_layer,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
