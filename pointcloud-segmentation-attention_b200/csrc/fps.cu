@@ -397,11 +397,12 @@ int launch_pruned(int b, int n, int m, const float *xyz, int *out, float *out_xy
 // ---------------------------------------------------------------------------------------------------------------
 // 8192 < n <= 16 * 8192: one THREAD-BLOCK CLUSTER per scene.  CTA r of the cluster keeps points [8192 r, 8192 (r+1))
 // on chip exactly as the single-CTA kernel does (8 warps x 32 points, same slot order, same one-barrier CTA-level
-// winner); the CTA winners then meet through distributed shared memory: every CTA writes its (value, key, x, y, z)
-// record into slot [parity][r] of EVERY CTA of the cluster (st.shared::cluster), one cluster barrier, and every CTA
-// reduces the C records locally -- the record carries the winner's coordinates, so the next round starts without
-// another remote read.  No global-memory traffic inside the m-1 rounds; the alternative for these sizes (running
-// minima streamed through L2, fps_stream_kernel) moves 16 n bytes per round.
+// winner); the CTA winners then meet through distributed shared memory: every CTA sends its (value, key, x, y, z)
+// record into slot [parity][r] of EVERY CTA of the cluster with st.async, which completes transaction bytes on the
+// receiver's mbarrier -- no cluster-wide barrier in the loop -- and every CTA reduces the C records locally; the record
+// carries the winner's coordinates, so the next round starts without another remote read.  No global-memory traffic
+// inside the m-1 rounds; the alternative for these sizes (running minima streamed through L2, fps_stream_kernel) moves
+// 16 n bytes per round.
 constexpr int kSlice = 8192;
 struct __align__(16) FpsRec { int value, key; float x, y; float z; int pad[3]; };
 
@@ -414,6 +415,7 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
   extern __shared__ float s_xyz[];  // this CTA's slice, up to kSlice * 3
   __shared__ int2 s_pair[2][32];
   __shared__ FpsRec s_rec[2][16];
+  __shared__ __align__(8) uint64_t s_mb[2];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int scene = blockIdx.x / CL;
@@ -449,7 +451,13 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
     }
     px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]);
   }
-  cluster.sync();  // every CTA's s_rec is addressable before the first remote store
+  const uint32_t mb_local[2] = {(uint32_t)__cvta_generic_to_shared(&s_mb[0]), (uint32_t)__cvta_generic_to_shared(&s_mb[1])};
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_local[0]), "r"(1u));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_local[1]), "r"(1u));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  cluster.sync();  // every CTA's s_rec / s_mb is initialised and addressable before the first remote store
 
   int par = 1;
   for (int j = 1; j < m; ++j) {
@@ -489,19 +497,39 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
     const int2 pr = s_pair[par][lane < nwarps ? lane : 0];
     const int cmax = __reduce_max_sync(PC_FULL_MASK, pr.x);
     const int ckey = __reduce_min_sync(PC_FULL_MASK, pr.x == cmax ? pr.y : INT_MAX);
-    if (tid < CL) {  // thread i delivers this CTA's record to CTA i
-      FpsRec r;
-      r.value = cmax; r.key = ckey;
-      r.x = r.y = r.z = 0.0f;
+    // Exchange without a cluster barrier: thread i sends this CTA's 32-byte record straight into slot [par][rank] of
+    // CTA i with two st.async (16 bytes each) that complete transaction bytes on CTA i's mbarrier s_mb[par]; every CTA
+    // armed that barrier for CL * 32 bytes and simply waits for its phase.
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb_local[par]), "r"((uint32_t)(CL * 32)) : "memory");
+    if (tid < CL) {
+      int rx = 0, ry = 0, rz = 0;
       if (cmax >= 0) {  // a CTA without live points reports (-1.0f bits): never the cluster winner
         const int kl = tie_key_to_index(ckey) - base;
-        r.x = s_xyz[kl * 3 + 0]; r.y = s_xyz[kl * 3 + 1]; r.z = s_xyz[kl * 3 + 2];
+        rx = __float_as_int(s_xyz[kl * 3 + 0]); ry = __float_as_int(s_xyz[kl * 3 + 1]); rz = __float_as_int(s_xyz[kl * 3 + 2]);
       }
-      FpsRec *dst = cluster.map_shared_rank(&s_rec[par][rank], tid);
-      *reinterpret_cast<int4 *>(dst) = make_int4(r.value, r.key, __float_as_int(r.x), __float_as_int(r.y));
-      dst->z = r.z;
+      const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_rec[par][rank]);
+      uint32_t rslot, rbar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot) : "r"(slot), "r"((uint32_t)tid));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(mb_local[par]), "r"((uint32_t)tid));
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(rslot),
+                   "r"(cmax), "r"(ckey), "r"(rx), "r"(ry), "r"(rbar)
+                   : "memory");
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(rslot + 16),
+                   "r"(rz), "r"(0), "r"(0), "r"(0), "r"(rbar)
+                   : "memory");
     }
-    cluster.sync();  // release the remote stores / acquire everyone else's
+    {
+      const uint32_t parity = ((j - 1) >> 1) & 1;  // s_mb[par] is used every second round
+      uint32_t ok = 0, spins = 0;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(mb_local[par]), "r"(parity)
+                     : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();
+      } while (!ok);
+    }
     const FpsRec *rr = &s_rec[par][lane < CL ? lane : 0];
     const int rv = rr->value, rk = rr->key;
     const float rx = rr->x, ry = rr->y, rz = rr->z;
