@@ -60,7 +60,7 @@ PC_API int pc_num_sms(void);                   /* SM count of the current device
  * (tf_sampling_g.cu:203-205, prototype tf_sampling.cpp:94; op FarthestPointSample tf_sampling.cpp:28-40,95-123).
  *   xyz (b,n,3) f32 -> out_idx (b,m) i32.  out_idx[:,0] = 0; ties resolve to the smallest (k mod 512, k) as the
  *   reference's 512-thread partition + left-biased tree does (tf_sampling_g.cu:130,153-163).
- * workspace: pc_fps_workspace_bytes(b,n,m) bytes (0 for n <= 131072: all state stays on chip -- one CTA per scene up
+ * workspace: pc_fps_workspace_bytes(b,n,m) bytes (0 for n <= 262144: all state stays on chip -- one CTA per scene up
  * to 8192 points, one thread-block cluster of 2..16 CTAs exchanging winners through DSMEM beyond); the reference needed
  * a (32,n) f32 temp tensor (tf_sampling.cpp:115).  m <= 0 returns PC_OK at once (tf_sampling_g.cu:106-107). */
 PC_API size_t pc_fps_workspace_bytes(int b, int n, int m);

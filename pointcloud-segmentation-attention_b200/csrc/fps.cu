@@ -403,14 +403,19 @@ int launch_pruned(int b, int n, int m, const float *xyz, int *out, float *out_xy
 // carries the winner's coordinates, so the next round starts without another remote read.  No global-memory traffic
 // inside the m-1 rounds; the alternative for these sizes (running minima streamed through L2, fps_stream_kernel) moves
 // 16 n bytes per round.
+//
+// Slice size: 8192 points per CTA (32 per thread, coordinates and running minima in registers) up to 131072 points;
+// up to 262144 points a CTA keeps 16384 (64 per thread): running minima for all of them in registers, coordinates in
+// registers for the first 32 slots and re-read from the shared-memory copy of the slice for the other 32 (PS).
 constexpr int kSlice = 8192;
+constexpr int kMaxClusterPoints = 16 * 16384;
 struct __align__(16) FpsRec { int value, key; float x, y; float z; int pad[3]; };
 
-template <int CL>
-__global__ void __maxnreg__(200)
+template <int CL, int P, int PS>
+__global__ void __maxnreg__((PS > 0) ? 255 : 200)
 fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out,
                    float *__restrict__ out_xyz) {
-  constexpr int P = 32, T = 256, H = P / 2, G = 8, NG = P / G, nwarps = T / 32;
+  constexpr int T = 256, H = P / 2, HR = (P - PS) / 2, G = 8, NG = P / G, nwarps = T / 32, kSlice = P * T;
   using Map = FpsMap<P, T>;
   extern __shared__ float s_xyz[];  // this CTA's slice, up to kSlice * 3
   __shared__ int2 s_pair[2][32];
@@ -426,6 +431,8 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
   float *oxyz = out_xyz ? out_xyz + (size_t)scene * m * 3 : nullptr;
   const int base = rank * kSlice, sn = max(0, min(kSlice, n - base));  // this CTA's points [base, base + sn)
   for (int i = tid; i < sn * 3; i += T) s_xyz[i] = p[(size_t)base * 3 + i];
+  if (PS > 0)
+    for (int i = sn * 3 + tid; i < kSlice * 3; i += T) s_xyz[i] = 0.0f;
   float cx = p[0], cy = p[1], cz = p[2];  // first centre = point 0 (tf_sampling_g.cu:114-116)
   if (rank == 0 && tid == 0) {
     o[0] = 0;
@@ -433,7 +440,7 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
   }
   __syncthreads();
 
-  f32x2 px[H], py[H], pz[H];
+  f32x2 px[HR], py[HR], pz[HR];
   float td[P];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
@@ -446,10 +453,10 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
         td[i] = 1e38f;
       } else {
         x[e] = y[e] = z[e] = 0.0f;
-        td[i] = -1.0f;
+        td[i] = -1.0f;  // never a winner; its shared-memory slot (PS part) is zero-filled below
       }
     }
-    px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]);
+    if (h < HR) { px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]); }
   }
   const uint32_t mb_local[2] = {(uint32_t)__cvta_generic_to_shared(&s_mb[0]), (uint32_t)__cvta_generic_to_shared(&s_mb[1])};
   if (tid == 0) {
@@ -469,7 +476,15 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
 #pragma unroll
       for (int h = g * G / 2; h < (g + 1) * G / 2; ++h) {
         float d0, d1;
-        unpack2(sqdist3_x2(px[h], py[h], pz[h], cx2, cy2, cz2, one2), d0, d1);
+        if (h < HR) {
+          unpack2(sqdist3_x2(px[h], py[h], pz[h], cx2, cy2, cz2, one2), d0, d1);
+        } else {  // coordinates from the slice copy (stride-3 words across lanes: conflict-free); slots beyond sn read
+                  // the zero fill -- their td stays -1 because fminf(d, -1) = -1 for every d >= 0
+          const int k0 = Map::k_of(tid, 2 * h), k1 = Map::k_of(tid, 2 * h + 1);
+          const f32x2 qx = pack2(s_xyz[k0 * 3 + 0], s_xyz[k1 * 3 + 0]), qy = pack2(s_xyz[k0 * 3 + 1], s_xyz[k1 * 3 + 1]),
+                      qz = pack2(s_xyz[k0 * 3 + 2], s_xyz[k1 * 3 + 2]);
+          unpack2(sqdist3_x2(qx, qy, qz, cx2, cy2, cz2, one2), d0, d1);
+        }
         td[2 * h] = fminf(d0, td[2 * h]);
         td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
         gm[g] = fmaxf(gm[g], fmaxf(td[2 * h], td[2 * h + 1]));
@@ -548,12 +563,13 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
   cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
-template <int CL>
+template <int CL, int P = 32, int PS = 0>
 int launch_cluster(int b, int n, int m, const float *xyz, int *out, float *out_xyz, cudaStream_t st) {
-  const int sn = n < kSlice ? n : kSlice;
-  const size_t smem = (size_t)sn * 3 * sizeof(float);
-  PC_CUDA_TRY(allow_smem(fps_cluster_kernel<CL>, smem));
-  if (CL > 8) PC_CUDA_TRY(cudaFuncSetAttribute(fps_cluster_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  constexpr int slice = P * 256;
+  const size_t smem = (size_t)(PS > 0 ? slice : (n < slice ? n : slice)) * 3 * sizeof(float);
+  auto kernel = fps_cluster_kernel<CL, P, PS>;
+  PC_CUDA_TRY(allow_smem(kernel, smem));
+  if (CL > 8) PC_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)b * CL);
   cfg.blockDim = dim3(256);
@@ -564,7 +580,7 @@ int launch_cluster(int b, int n, int m, const float *xyz, int *out, float *out_x
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CL>, n, m, 1.0f, xyz, out, out_xyz));
+  PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, n, m, 1.0f, xyz, out, out_xyz));
   return PC_OK;
 }
 
@@ -631,7 +647,7 @@ int launch_onchip(int b, int n, int m, const float *xyz, int *out, float *out_xy
 
 extern "C" size_t pc_fps_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 0;
-  if (n <= 16 * pc::kMaxRegPoints) return 0;  // single CTA or one thread-block cluster per scene: all state on chip
+  if (n <= pc::kMaxClusterPoints) return 0;  // single CTA or one thread-block cluster per scene: all state on chip
   return (size_t)b * n * sizeof(float);
 }
 
@@ -667,12 +683,13 @@ extern "C" int pc_fps_gather(int b, int n, int m, const float *xyz, void *worksp
     if (shape == 512) return pc::launch_onchip<16, 512, false, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
   }
-  if (n <= 16 * pc::kSlice && (long long)b * 16 < 0x7fffffffLL) {  // one cluster of 2 / 4 / 8 / 16 CTAs per scene
+  if (n <= pc::kMaxClusterPoints && (long long)b * 16 < 0x7fffffffLL) {  // one cluster of 2 / 4 / 8 / 16 CTAs per scene
     const int slices = (n + pc::kSlice - 1) / pc::kSlice;
     if (slices <= 2) return pc::launch_cluster<2>(b, n, m, xyz, out_idx, out_xyz, st);
     if (slices <= 4) return pc::launch_cluster<4>(b, n, m, xyz, out_idx, out_xyz, st);
     if (slices <= 8) return pc::launch_cluster<8>(b, n, m, xyz, out_idx, out_xyz, st);
-    return pc::launch_cluster<16>(b, n, m, xyz, out_idx, out_xyz, st);
+    if (slices <= 16) return pc::launch_cluster<16>(b, n, m, xyz, out_idx, out_xyz, st);
+    return pc::launch_cluster<16, 64, 32>(b, n, m, xyz, out_idx, out_xyz, st);  // 16384-point slices
   }
   if (!workspace) return PC_ERR_WORKSPACE;
   pc::fps_stream_kernel<<<b, 1024, 0, st>>>(b, n, m, xyz, (float *)workspace, out_idx);

@@ -53,13 +53,13 @@ def main():
     print("| op | N | npoint | B | ms | us per scene | path |")
     print("|---|---|---|---|---|---|---|")
     g = torch.Generator(device=dev).manual_seed(1)
-    for N, B in ((16384, 64), (65536, 64), (262144, 8)):
+    for N, B in ((16384, 64), (65536, 64), (262144, 8), (300000, 8)):
         x = torch.rand((B, N, 3), generator=g, device=dev)
         for m in (1024, 4096):
             if N >= 262144 and m > 1024:
                 continue
-            path = "cluster of %d CTAs (DSMEM)" % max(2, 1 << ((N + 8191) // 8192 - 1).bit_length()) if N <= 131072 \
-                else "streamed min-distances (L2)"
+            path = "cluster of %d CTAs (DSMEM)" % min(16, max(2, 1 << ((N + 8191) // 8192 - 1).bit_length())) \
+                if N <= 262144 else "streamed min-distances (L2)"
             ms = timeit(lambda: ops.farthest_point_sample(m, x), 3)
             print("| FPS | %d | %d | %d | %.2f | %.1f | %s |" % (N, m, B, ms, ms * 1e3 / B, path))
             if N > 65536:

@@ -73,9 +73,9 @@ def test_fps_ties_duplicates_and_big_batches():
 
 
 @pytest.mark.parametrize("n,m,b", [(8193, 64, 2), (16384, 80, 3), (16385, 80, 1), (20000, 96, 2), (40000, 64, 2),
-                                   (70000, 48, 1), (131072, 40, 1), (140000, 24, 1)])
+                                   (70000, 48, 1), (131072, 40, 1), (140000, 24, 1), (262144, 20, 1), (270000, 12, 1)])
 def test_fps_cluster_and_streaming_paths_above_8192_points(n, m, b):
-    """8192 < n <= 131072: one thread-block cluster (2/4/8/16 CTAs, DSMEM exchange) per scene; beyond: streaming."""
+    """8192 < n <= 262144: one thread-block cluster (2/4/8/16 CTAs, DSMEM exchange) per scene; beyond: streaming."""
     xyz, _ = synth.scannet_batch(n % 1000, b, n)
     x = cu(xyz)
     idx, new_xyz = ops.farthest_point_sample_and_gather(m, x)
@@ -89,6 +89,8 @@ def test_fps_cluster_ties_across_ctas():
     base = rng.random((1, 600, 3)).astype(np.float32)
     xyz = np.tile(base, (1, 30, 1))[:, :17000]          # every point repeated ~28 times across slices
     assert same(ops.farthest_point_sample(300, cu(xyz)), cpu.farthest_point_sample(300, xyz))
+    xyz = np.tile(base, (1, 240, 1))[:, :140000]        # 16384-point slices, half of each read from shared memory
+    assert same(ops.farthest_point_sample(200, cu(xyz)), cpu.farthest_point_sample(200, xyz))
 
 
 def test_fps_matches_reference_cuda_kernel(refgpu):
