@@ -238,7 +238,8 @@ def test_selection_sort_matches_reference_cuda_kernel(refgpu):
 
 @pytest.mark.parametrize("n,m,k,c,quant", [(512, 128, 64, 3, False), (512, 40, 32, 3, True), (300, 33, 7, 5, True),
                                            (2100, 20, 100, 3, False), (64, 16, 64, 3, True), (40, 9, 1, 2, True),
-                                           (8192, 64, 32, 3, False)])
+                                           (8192, 64, 32, 3, False), (3000, 50, 32, 3, True), (2500, 30, 128, 3, True),
+                                           (1500, 20, 128, 4, False), (129, 10, 128, 3, False), (700, 12, 33, 1, True)])
 def test_knn_matches_oracle(n, m, k, c, quant):
     rs = np.random.RandomState(n + k)
     if quant:   # quantised coordinates -> many exactly equal distances -> the swap-induced tie order matters
@@ -249,6 +250,17 @@ def test_knn_matches_oracle(n, m, k, c, quant):
     val, idx = ops.knn_point(k, cu(xyz1), cu(xyz2))
     oval, oidx = cpu.knn_point(k, xyz1, xyz2)
     assert same(idx, oidx) and same(val, oval)
+
+
+def test_knn_all_distances_equal():
+    """Every candidate ties: the buffer compaction must keep the EARLIEST positions, whatever the fill level."""
+    xyz1 = np.zeros((1, 1000, 3), np.float32)
+    xyz1[0, 500:] = 1.0                                  # two clusters of identical points
+    xyz2 = np.array([[[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5]]], np.float32)
+    for k in (5, 32, 100):
+        val, idx = ops.knn_point(k, cu(xyz1), cu(xyz2))
+        oval, oidx = cpu.knn_point(k, xyz1, xyz2)
+        assert same(idx, oidx) and same(val, oval)
 
 
 # --------------------------------------------------------------------------------- three_nn / interpolate (a8-a11)
