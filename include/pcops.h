@@ -71,6 +71,16 @@ PC_API int pc_fps(int b, int n, int m, const float *xyz, void *workspace, int *o
 PC_API int pc_fps_gather(int b, int n, int m, const float *xyz, void *workspace, int *out_idx, float *out_xyz,
                   pc_stream_t stream);
 
+/* ProbSample: categorical sampling by inverse CDF.  Replaces probsampleLauncher(b,n,m,inp_p,inp_r,temp,out)
+ * (tf_sampling_g.cu:197-200 = cumsumKernel :7-88 + binarysearchKernel :90-104; prototype tf_sampling.cpp:65; op
+ * ProbSample tf_sampling.cpp:14-27,66-92).
+ *   inp_p (b,n) f32 weights, inp_r (b,m) f32 uniforms -> out (b,m) i32: smallest index whose cumulative weight is
+ *   >= r * total.  temp: (b,n) f32, receives the cumulative sums (the reference's allocate_temp, tf_sampling.cpp:85-88);
+ *   they follow the reference's blocked summation tree bit for bit.  pc_cumsum is cumsumLauncher (:193-195) alone. */
+PC_API int pc_cumsum(int b, int n, const float *inp, float *out, pc_stream_t stream);
+PC_API int pc_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out,
+                   pc_stream_t stream);
+
 /* gather_point.  Replaces gatherpointLauncher(b,n,m,inp,idx,out) (tf_sampling_g.cu:206-208, prototype
  * tf_sampling.cpp:125; op GatherPoint tf_sampling.cpp:41-54,126-148).
  *   inp (b,n,3), idx (b,m) -> out (b,m,3);  out[b,j,:] = inp[b,idx[b,j],:] */

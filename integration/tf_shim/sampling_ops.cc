@@ -1,10 +1,22 @@
-// tf_sampling_so.so: FarthestPointSample, GatherPoint, GatherPointGrad over libpcops.so.
+// tf_sampling_so.so: ProbSample, FarthestPointSample, GatherPoint, GatherPointGrad over libpcops.so.
 // Registry (names, attrs, dtypes, shape functions, messages) restates the reference's
-// pointnet2_tensorflow/tf_ops/sampling/tf_sampling.cpp:14-63,95-178; the kernels are pc_fps / pc_gather_point /
-// pc_gather_point_grad.  ProbSample (tf_sampling.cpp:14-27) is on no model's path and is not re-registered.
+// pointnet2_tensorflow/tf_ops/sampling/tf_sampling.cpp:14-63,66-178; the kernels are pc_prob_sample / pc_fps /
+// pc_gather_point / pc_gather_point_grad.
 #include "shim_common.h"
 
 namespace pcshim {
+
+REGISTER_OP("ProbSample")
+    .Input("inp: float32")
+    .Input("inpr: float32")
+    .Output("out: int32")
+    .SetShapeFn([](InferenceContext *c) {
+      ShapeHandle p, r;  // (batch, ncategory), (batch, npoints)
+      TF_RETURN_IF_ERROR(c->WithRank(c->input(0), 2, &p));
+      TF_RETURN_IF_ERROR(c->WithRank(c->input(1), 2, &r));
+      c->set_output(0, c->MakeShape({c->Dim(r, 0), c->Dim(r, 1)}));
+      return Status::OK();
+    });
 
 REGISTER_OP("FarthestPointSample")
     .Attr("npoint: int")
@@ -40,6 +52,26 @@ REGISTER_OP("GatherPointGrad")
       c->set_output(0, c->input(0));
       return Status::OK();
     });
+
+class ProbSampleGpuOp : public OpKernel {
+ public:
+  explicit ProbSampleGpuOp(OpKernelConstruction *c) : OpKernel(c) {}
+  void Compute(OpKernelContext *ctx) override {
+    const Tensor &inp = ctx->input(0), &inpr = ctx->input(1);
+    OP_REQUIRES(ctx, inp.dims() == 2, errors::InvalidArgument("ProbSample expects (batch_size,num_choices) inp shape"));
+    const int b = dim(inp, 0), n = dim(inp, 1);
+    OP_REQUIRES(ctx, inpr.dims() == 2 && dim(inpr, 0) == b,
+                errors::InvalidArgument("ProbSample expects (batch_size,num_points) inpr shape"));
+    const int m = dim(inpr, 1);
+    Tensor *out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape{b, m}, &out));
+    Tensor temp;  // cumulative sums, tf_sampling.cpp:85-88
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_FLOAT, TensorShape{b, n}, &temp));
+    PCSHIM_CHECK_RC(ctx, pc_prob_sample(b, n, m, F(inp), F(inpr), temp.flat<float>().data(), I(out), PCSHIM_STREAM(ctx)),
+                    "pc_prob_sample");
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("ProbSample").Device(DEVICE_GPU), ProbSampleGpuOp);
 
 class FarthestPointSampleGpuOp : public OpKernel {
  public:

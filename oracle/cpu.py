@@ -63,6 +63,25 @@ def farthest_point_sample(npoint, inp, omp=False):
     return out
 
 
+def cumsum(inp):
+    inp = _f32(inp)
+    b, n = inp.shape
+    out = np.zeros((b, n), np.float32)
+    lib().orc_cumsum(b, n, _fp(inp), _fp(out))
+    return out
+
+
+def prob_sample(inp, inpr):
+    """inp (b,n) weights, inpr (b,m) uniforms in [0,1) -> (b,m) i32 category indices (tf_sampling.py:14-23)."""
+    inp, inpr = _f32(inp), _f32(inpr)
+    b, n = inp.shape
+    m = inpr.shape[1]
+    temp = np.zeros((b, n), np.float32)
+    out = np.zeros((b, m), np.int32)
+    lib().orc_prob_sample(b, n, m, _fp(inp), _fp(inpr), _fp(temp), _ip(out))
+    return out
+
+
 def gather_point(inp, idx):
     inp, idx = _f32(inp), _i32(idx)
     b, n, _ = inp.shape

@@ -18,7 +18,7 @@
  *                                       (its own known-answer b=2,n=4,m=2,k=3) in _ref
  *   three_nn / interpolate / grad    -> pinned against interpolation_3d/tf_interpolate.cpp
  *                                       compiled unmodified (TF headers stubbed) in _ref
- *   FPS / gather / gather-grad       -> pinned on the GPU box against sampling/tf_sampling_g.cu
+ *   FPS / gather / gather-grad / prob_sample -> pinned on the GPU box against sampling/tf_sampling_g.cu
  *                                       compiled unmodified (--fmad=false) in _ref
  *   kNN distances, FP weights, attention -> TensorFlow ops in the reference; TF is absent,
  *                                       so these three are "parity unpinned" (source-pinned only).
@@ -108,6 +108,76 @@ ORC_API void orc_fps_omp(int b, int n, int m, const float *xyz, int *out) {
 #pragma omp for schedule(dynamic, 1)
     for (int i = 0; i < b; ++i) fps_one(n, m, xyz + (size_t)i * n * 3, temp, out + (size_t)i * m);
     free(temp);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * a0  prob_sample -- sampling/tf_sampling_g.cu:7-104 (cumsumKernel + binarysearchKernel), launcher :197-200.
+ * Registered next to FPS in the sampling library, called by no model; restated because it is part of the
+ * op surface.  The cumulative sum is NOT a left-to-right sum: per block of 8192 values the kernel forms
+ *   - inside each group of four: p1 = v1, p2 = v2 + v1, p3 = v3 + p2, p4 = (v4 + v3) + p2       (:19-32)
+ *     (a trailing partial group is summed serially from 0, :33-42)
+ *   - an in-place scan of the group totals: up-sweep  G[((2k+2)<<u)-1] += G[((2k+1)<<u)-1]       (:47-56)
+ *                                           down-sweep G[((2k+3)<<u)-1] += G[((2k+2)<<u)-1]      (:58-67)
+ *   - element = in-group prefix + total of the groups before it (:69-77), + running sum of earlier blocks (:79-81)
+ *   - the running sum is carried across blocks with a compensation term                           (:82-85)
+ * and the fp32 roundings follow that tree.  The sample for uniform r is the smallest index whose
+ * cumulative value is >= r * total, found by the power-of-two descent of :92-101.
+ * ------------------------------------------------------------------------------------------ */
+static void cumsum_row(int n, const float *inp, float *out) {
+  enum { BLOCK = 8192 };
+  static __thread float p[BLOCK], G[BLOCK / 4];
+  float runningsum = 0.f, runningsum2 = 0.f;
+  for (int j = 0; j < n; j += BLOCK) {
+    const int cnt = n - j < BLOCK ? n - j : BLOCK;
+    const int n24 = (cnt + 3) & ~3, n2 = n24 >> 2;
+    for (int k = 0; k < cnt; k += 4) {
+      if (k + 3 < cnt) {
+        float v1 = inp[j + k], v2 = inp[j + k + 1], v3 = inp[j + k + 2], v4 = inp[j + k + 3];
+        v2 += v1;
+        v4 += v3;
+        v3 += v2;
+        v4 += v2;
+        p[k] = v1; p[k + 1] = v2; p[k + 2] = v3; p[k + 3] = v4;
+        G[k >> 2] = v4;
+      } else {
+        float v = 0.f;
+        for (int k2 = k; k2 < cnt; ++k2) { v += inp[j + k2]; p[k2] = v; }
+        for (int k2 = cnt; k2 < n24; ++k2) p[k2] = v;
+        G[k >> 2] = v;
+      }
+    }
+    int u = 0;
+    for (; (2 << u) <= n2; ++u)
+      for (int k = 0; k < (n2 >> (u + 1)); ++k) G[(((k << 1) + 2) << u) - 1] += G[(((k << 1) + 1) << u) - 1];
+    for (--u; u >= 0; --u)
+      for (int k = 0; k < ((n2 - (1 << u)) >> (u + 1)); ++k) G[(((k << 1) + 3) << u) - 1] += G[(((k << 1) + 2) << u) - 1];
+    for (int k = 4; k < n24; ++k) p[k] += G[(k >> 2) - 1];
+    for (int k = 0; k < cnt; ++k) out[j + k] = p[k] + runningsum;
+    const float t = G[n2 - 1] + runningsum2;
+    const float r2 = runningsum + t;
+    runningsum2 = t - (r2 - runningsum);
+    runningsum = r2;
+  }
+}
+
+ORC_API void orc_cumsum(int b, int n, const float *inp, float *out) {
+  for (int i = 0; i < b; ++i) cumsum_row(n, inp + (size_t)i * n, out + (size_t)i * n);
+}
+
+ORC_API void orc_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out) {
+  int base = 1;
+  while (base < n) base <<= 1;
+  for (int i = 0; i < b; ++i) {
+    float *cdf = temp + (size_t)i * n;
+    cumsum_row(n, inp_p + (size_t)i * n, cdf);
+    for (int j = 0; j < m; ++j) {
+      const float q = inp_r[(size_t)i * m + j] * cdf[n - 1];
+      int r = n - 1;
+      for (int k = base; k >= 1; k >>= 1)
+        if (r >= k && cdf[r - k] >= q) r -= k;
+      out[(size_t)i * m + j] = r;
+    }
   }
 }
 

@@ -164,6 +164,17 @@ class Gpu:
         if rc:
             raise RuntimeError("reference kernel failed: cuda error %d" % rc)
 
+    def prob_sample(self, inp, inpr):
+        t = self.torch
+        b, n = inp.shape
+        m = inpr.shape[1]
+        out = t.zeros((b, m), dtype=t.int32, device=inp.device)
+        temp = t.empty((b, n), dtype=t.float32, device=inp.device)  # tf_sampling.cpp:85-88
+        self._sync()
+        self.lib.ref_prob_sample(b, n, m, self._p(inp), self._p(inpr), self._p(temp), self._p(out))
+        self._sync()
+        return out, temp
+
     def farthest_point_sample(self, npoint, inp):
         t = self.torch
         b, n, _ = inp.shape

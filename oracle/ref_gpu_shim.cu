@@ -6,6 +6,7 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into libpcops.so.
 #include <cuda_runtime.h>
 
+void probsampleLauncher(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out);
 void farthestpointsamplingLauncher(int b, int n, int m, const float *inp, float *temp, int *out);
 void gatherpointLauncher(int b, int n, int m, const float *inp, const int *idx, float *out);
 void scatteraddpointLauncher(int b, int n, int m, const float *out_g, const int *idx, float *inp_g);
@@ -19,6 +20,10 @@ void groupPointGradLauncher(int b, int n, int c, int m, int nsample, const float
 // All reference launches go to the legacy default stream; callers synchronise the device
 // (torch.cuda.synchronize) before and after.
 extern "C" {
+int ref_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out) {
+  probsampleLauncher(b, n, m, inp_p, inp_r, temp, out);
+  return (int)cudaGetLastError();
+}
 int ref_fps(int b, int n, int m, const float *inp, float *temp32n, int *out) {
   farthestpointsamplingLauncher(b, n, m, inp, temp32n, out);
   return (int)cudaGetLastError();

@@ -27,6 +27,8 @@ SIGNATURES = {
     "pc_fps_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_fps": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_fps_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_cumsum": (_i, [_i, _i, _vp, _vp, _vp]),
+    "pc_prob_sample": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_gather_point": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_gather_point_grad_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_gather_point_grad": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

@@ -2,8 +2,8 @@
 
 Mirrors pointnet2_tensorflow/tf_ops/sampling/tf_sampling.py: ``farthest_point_sample(npoint, inp)`` (:49-58,
 NoGradient), ``gather_point(inp, idx)`` (:30-38) with its registered gradient (:44-48 -> ``[GatherPointGrad, None]``).
-``prob_sample`` (:14-23) is registered in the same reference library but is on no model's path and is
-not provided.  Shape errors carry the reference OpKernel's messages (tf_sampling.cpp:105,131,135).
+``prob_sample(inp, inpr)`` (:14-23, NoGradient) is on no model's path but part of the library's op
+surface.  Shape errors carry the reference OpKernel's messages (tf_sampling.cpp:105,131,135).
 """
 import torch
 
@@ -94,4 +94,29 @@ def gather_point_grad(inp, idx, out_g):
 
 
 def prob_sample(inp, inpr):
-    raise NotImplementedError("ProbSample is outside the accelerated hot path (no model calls it); see DESIGN.md")
+    """inp (b,ncategory) f32 weights, inpr (b,npoints) f32 uniforms -> (b,npoints) i32.  ProbSample,
+    tf_sampling.py:14-23 / tf_sampling.cpp:14-27,66-92; NoGradient (tf_sampling.py:23)."""
+    if inp.dim() != 2:
+        raise ValueError("ProbSample expects (batch_size,num_choices) inp shape")
+    if inpr.dim() != 2 or inpr.shape[0] != inp.shape[0]:
+        raise ValueError("ProbSample expects (batch_size,num_points) inpr shape")
+    inp = _lib.cuda_f32(inp.detach(), "inp")
+    inpr = _lib.cuda_f32(inpr.detach(), "inpr")
+    b, n = inp.shape
+    m = inpr.shape[1]
+    temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
+    out = torch.empty((b, m), dtype=torch.int32, device=inp.device)
+    rc = _lib.lib().pc_prob_sample(b, n, m, _lib.ptr(inp), _lib.ptr(inpr), _lib.ptr(temp), _lib.ptr(out), _lib.stream())
+    _lib.check(rc, "pc_prob_sample")
+    return out
+
+
+def cumsum(inp):
+    """(b,n) f32 -> (b,n) cumulative sums in the reference's summation order (cumsumLauncher, tf_sampling_g.cu:193-195)."""
+    if inp.dim() != 2:
+        raise ValueError("cumsum expects (batch_size,n) inp shape")
+    inp = _lib.cuda_f32(inp.detach(), "inp")
+    out = torch.empty_like(inp)
+    rc = _lib.lib().pc_cumsum(inp.shape[0], inp.shape[1], _lib.ptr(inp), _lib.ptr(out), _lib.stream())
+    _lib.check(rc, "pc_cumsum")
+    return out

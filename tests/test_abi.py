@@ -97,7 +97,7 @@ def test_wrappers_raise_reference_messages_and_have_no_cpu_fallback():
     # CPU tensors are refused outright: there is no host implementation behind these names
     with pytest.raises(_lib.PcopsError, match="CUDA tensor"):
         pcops_b200.farthest_point_sample(4, xyz)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match=r"ProbSample expects \(batch_size,num_choices\) inp shape"):
         pcops_b200.prob_sample(xyz, xyz)
 
 

@@ -72,6 +72,30 @@ def test_fps_ties_duplicates_and_big_batches():
     assert same(ops.farthest_point_sample(16, cu(small)), cpu.farthest_point_sample(16, small))   # m > n
 
 
+# --------------------------------------------------------------------------------- prob_sample (a0, op surface only)
+@pytest.mark.parametrize("n,m,b", [(1, 5, 2), (3, 7, 1), (4, 9, 2), (5, 16, 3), (100, 64, 2), (4095, 100, 2),
+                                   (8192, 300, 2), (8193, 300, 2), (8197, 64, 1), (40000, 1000, 3)])
+def test_prob_sample_matches_oracle(n, m, b):
+    """Cumulative sums in the reference's blocked summation tree (bit-exact), then its power-of-two descent."""
+    rs = np.random.RandomState(n + m)
+    w = rs.random_sample((b, n)).astype(np.float32)
+    w[:, rs.permutation(n)[: n // 5]] = 0.0              # zero-weight categories: plateaus in the cumulative sums
+    r = rs.random_sample((b, m)).astype(np.float32)
+    r[:, 0] = 0.0
+    assert same(ops.cumsum(cu(w)), cpu.cumsum(w))
+    assert same(ops.prob_sample(cu(w), cu(r)), cpu.prob_sample(w, r))
+
+
+def test_prob_sample_matches_reference_cuda_kernel(refgpu):
+    rs = np.random.RandomState(100)                        # the reference smoke scripts' seed (tf_sampling.py:63)
+    for b, n, m in ((32, 512, 128), (3, 20000, 999), (2, 8195, 64)):
+        w = cu(rs.random_sample((b, n)).astype(np.float32))
+        r = cu(rs.random_sample((b, m)).astype(np.float32))
+        out, temp = refgpu.prob_sample(w, r)
+        assert torch.equal(ops.cumsum(w), temp)
+        assert torch.equal(ops.prob_sample(w, r), out)
+
+
 @pytest.mark.parametrize("n,m,b", [(8193, 64, 2), (16384, 80, 3), (16385, 80, 1), (20000, 96, 2), (40000, 64, 2),
                                    (70000, 48, 1), (131072, 40, 1), (140000, 24, 1), (262144, 20, 1), (270000, 12, 1)])
 def test_fps_cluster_and_streaming_paths_above_8192_points(n, m, b):

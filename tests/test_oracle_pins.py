@@ -222,3 +222,69 @@ def test_attention_backward_against_finite_differences():
             dn = loss(Q, K, V)
             flat[pos] = old
             assert abs((up - dn) / (2 * eps) - grad.reshape(-1)[pos]) < 2e-3
+
+
+def test_prob_sample_oracle_against_python_emulation_of_the_kernel():
+    """cumsumKernel / binarysearchKernel (tf_sampling_g.cu:7-104) emulated literally in numpy float32 -- thread loops
+    unrolled into python loops, padded buffer indices kept -- against the C restatement (unpadded, regrouped)."""
+    def kernel_cumsum(inp):
+        f = np.float32
+        n = inp.shape[0]
+        out = np.zeros(n, f)
+        BS, PL = 2048, 5
+        rs, rs2 = f(0), f(0)
+        for j in range(0, n, BS * 4):
+            n24_i = min(n - j, BS * 4)
+            n24 = (n24_i + 3) & ~3
+            n2 = n24 >> 2
+            b4 = np.zeros(BS * 4, f)
+            bf = np.zeros(BS + (BS >> PL), f)
+            for k in range(0, n24_i, 4):
+                if k + 3 < n24_i:
+                    v1, v2, v3, v4 = (f(inp[j + k + t]) for t in range(4))
+                    v2 = f(v2 + v1); v4 = f(v4 + v3); v3 = f(v3 + v2); v4 = f(v4 + v2)
+                    b4[k:k + 4] = (v1, v2, v3, v4)
+                    bf[(k >> 2) + (k >> (2 + PL))] = v4
+                else:
+                    v = f(0)
+                    for k2 in range(k, n24_i):
+                        v = f(v + inp[j + k2]); b4[k2] = v
+                    b4[n24_i:n24] = v
+                    bf[(k >> 2) + (k >> (2 + PL))] = v
+            u = 0
+            while (2 << u) <= n2:
+                for k in range(n2 >> (u + 1)):
+                    i1 = (((k << 1) + 2) << u) - 1; i2 = (((k << 1) + 1) << u) - 1
+                    i1 += i1 >> PL; i2 += i2 >> PL
+                    bf[i1] = f(bf[i1] + bf[i2])
+                u += 1
+            u -= 1
+            while u >= 0:
+                for k in range((n2 - (1 << u)) >> (u + 1)):
+                    i1 = (((k << 1) + 3) << u) - 1; i2 = (((k << 1) + 2) << u) - 1
+                    i1 += i1 >> PL; i2 += i2 >> PL
+                    bf[i1] = f(bf[i1] + bf[i2])
+                u -= 1
+            for k in range(4, n24, 4):
+                k2 = ((k >> 2) - 1) + (((k >> 2) - 1) >> PL)
+                b4[k:k + 4] = b4[k:k + 4] + bf[k2]
+            out[j:j + n24_i] = b4[:n24_i] + rs
+            t = f(bf[(n2 - 1) + ((n2 - 1) >> PL)] + rs2)
+            r2 = f(rs + t)
+            rs2 = f(t - f(r2 - rs))
+            rs = r2
+        return out
+
+    rs = np.random.RandomState(100)
+    for n in (1, 2, 4, 7, 64, 129, 1000, 8192, 8199, 17000):
+        w = rs.random_sample((1, n)).astype(np.float32)
+        assert np.array_equal(cpu.cumsum(w)[0], kernel_cumsum(w[0])), n
+    w = rs.random_sample((2, 777)).astype(np.float32)
+    w[:, ::3] = 0
+    r = rs.random_sample((2, 300)).astype(np.float32)
+    cdf = cpu.cumsum(w)
+    got = cpu.prob_sample(w, r)
+    for i in range(2):
+        q = (r[i] * cdf[i, -1]).astype(np.float32)
+        want = np.searchsorted(cdf[i], q, side="left")      # smallest index with cdf >= q (cdf is non-decreasing)
+        assert np.array_equal(got[i], np.minimum(want, 776))

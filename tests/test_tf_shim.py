@@ -10,6 +10,7 @@ SHIM = os.path.join(ROOT, "integration", "tf_shim")
 
 # op -> (attrs, inputs, outputs) as registered by the reference
 REFERENCE_REGISTRY = {
+    "ProbSample": ([], ["inp: float32", "inpr: float32"], ["out: int32"]),
     "FarthestPointSample": (["npoint: int"], ["inp: float32"], ["out: int32"]),
     "GatherPoint": ([], ["inp: float32", "idx: int32"], ["out: float32"]),
     "GatherPointGrad": ([], ["inp: float32", "idx: int32", "out_g: float32"], ["inp_g: float32"]),
@@ -46,7 +47,7 @@ def test_every_registered_op_has_a_gpu_kernel_calling_the_c_abi():
     text = "".join(open(os.path.join(SHIM, f)).read() for f in ("sampling_ops.cc", "grouping_ops.cc", "interpolation_ops.cc"))
     kernels = set(re.findall(r'REGISTER_KERNEL_BUILDER\(Name\("(\w+)"\)\.Device\(DEVICE_GPU\)', text))
     assert kernels == set(REFERENCE_REGISTRY)
-    for fn in ("pc_fps", "pc_gather_point", "pc_gather_point_grad", "pc_query_ball_grid", "pc_selection_sort",
+    for fn in ("pc_prob_sample", "pc_fps", "pc_gather_point", "pc_gather_point_grad", "pc_query_ball_grid", "pc_selection_sort",
                "pc_group_point", "pc_group_point_grad", "pc_three_nn_grid", "pc_three_interpolate",
                "pc_three_interpolate_grad"):
         assert re.search(r"\b%s\(" % fn, text), fn
