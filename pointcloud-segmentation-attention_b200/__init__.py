@@ -13,7 +13,7 @@ Everything computes in libpcops.so (include/pcops.h); there is no CPU or eager f
 """
 from . import _lib  # noqa: F401
 from .tf_sampling import (farthest_point_sample, farthest_point_sample_and_gather, gather_point,  # noqa: F401
-                          gather_point_grad, prob_sample)
+                          gather_point_grad, prob_sample, cumsum)
 from .tf_grouping import (group_point, group_point_grad, knn_point, query_ball_point,  # noqa: F401
                           select_top_k)
 from .tf_interpolate import (three_interpolate, three_interpolate_grad, three_nn,  # noqa: F401
