@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true", help="single stream")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--train", type=int, default=1, help="1: also time config 3 (forward + the registered gradients)")
+    ap.add_argument("--train-depth", type=int, default=4, help="batches in flight for the config-3 region")
     ap.add_argument("--skip-probe", action="store_true")
     return ap.parse_args()
 
@@ -238,6 +240,54 @@ def time_fused_attention_layer(torch, ops, G):
     return {"shape": "G=%d S=32 C=64 heads=16 key_dim=4" % G, "fused_ms": tf, "fp32_cublas_composition_ms": tc,
             "speedup": tc / tf, "max_rel_err_vs_fp32": err, "tf32_mma_tflops": flops / (tf * 1e-3) / 1e12,
             "tensor_peak_note": "dense tf32 nominal 1.1 PFLOP/s; 3xTF32 split triples the issued flops"}
+
+
+def time_steady_state_gathers(torch, ops, hbm_peak):
+    """The HBM-bound gathers at a size where launch ramp and tail are amortised: B=64 scenes per launch (config 5's batch),
+    8 launches back to back on rotating buffer sets (> 126 MB L2 between reuses), one CUDA-event pair around all of them.
+    Fraction = algorithmic bytes (SURVEY.md 8d formulas) / time / measured HBM copy bandwidth."""
+    import ctypes
+    L, p = ops._lib.lib(), ops._lib.ptr
+    dev, B, reps = torch.device("cuda"), 64, 8
+    g = torch.Generator(device=dev).manual_seed(11)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = {}
+
+    def timed(name, nbytes, launch, nsets):
+        for r in range(nsets):
+            launch(r)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(reps):
+            launch(r % nsets)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "bytes": nbytes, "batch": B}
+
+    # group_point, SA2 features: points (B,1024,64), idx (B,256,32) -> (B,256,32,64)
+    for tag, n, m, ns, c in (("group_point_sa2_c64", 1024, 256, 32, 64), ("group_point_sa3_c128", 256, 64, 32, 128)):
+        nsets = 4
+        pts = [torch.randn(B, n, c, generator=g, device=dev) for _ in range(nsets)]
+        idx = [torch.randint(0, n, (B, m, ns), generator=g, device=dev, dtype=torch.int32) for _ in range(nsets)]
+        dst = [torch.empty(B, m, ns, c, device=dev) for _ in range(nsets)]
+        nbytes = B * (4 * m * ns + 4 * min(n, m * ns) * c + 4 * m * ns * c)
+        timed(tag, nbytes, lambda r: L.pc_group_point(B, n, c, m, ns, p(pts[r]), p(idx[r]), p(dst[r]), st), nsets)
+        del pts, idx, dst
+    # three_interpolate, FP4: points (B,1024,128), idx/weight (B,8192,3) -> (B,8192,128)
+    for tag, n, m, c in (("three_interpolate_fp4_c128", 8192, 1024, 128), ("three_interpolate_fp3_c256", 1024, 256, 256)):
+        nsets = 3
+        pts = [torch.randn(B, m, c, generator=g, device=dev) for _ in range(nsets)]
+        idx = [torch.randint(0, m, (B, n, 3), generator=g, device=dev, dtype=torch.int32) for _ in range(nsets)]
+        w = [torch.rand(B, n, 3, generator=g, device=dev) for _ in range(nsets)]
+        dst = [torch.empty(B, n, c, device=dev) for _ in range(nsets)]
+        nbytes = B * (24 * n + 4 * m * c + 4 * n * c)
+        timed(tag, nbytes, lambda r: L.pc_three_interpolate(B, m, c, n, p(pts[r]), p(idx[r]), p(w[r]), p(dst[r]), st), nsets)
+        del pts, idx, w, dst
+    torch.cuda.empty_cache()
+    return out
 
 
 def bind_to_gpu_cpus(index):
@@ -428,6 +478,51 @@ def main():
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     checksum = int(sum(int(h.to(torch.int64).sum()) for h in host_out))
 
+    # ---- timed region 3: config 3, a training step's geometry (forward + GroupPointGrad / ThreeInterpolateGrad /
+    # attention-contraction backward), inputs resident ----------------------------------------------------------
+    train = None
+    if args.train and args.attention:
+        TD = max(1, min(D, args.train_depth))
+        tp = pipes[:TD]
+        for pl in tp:
+            pl.allocate_backward(seed=4321 + rank)
+            pl.set_inputs(dev_xyz[0], dev_feat[0])
+            if use_graph:
+                pl.capture(overlap, train=True)
+            else:
+                pl.forward(overlap, train=True)
+        torch.cuda.synchronize(dev)
+
+        def step_train(i):
+            pl = tp[i % TD]
+            pl.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+            if use_graph:
+                pl.replay()
+            else:
+                pl.forward(overlap, train=True)
+        for i in range(max(3, TD)):
+            step_train(i)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(cur)
+        fork()
+        for i in range(K):
+            step_train(i)
+        join()
+        g1.record(cur)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        tr_ms = sharding.max_over_ranks(g0.elapsed_time(g1))
+        train = {"workload": "config 3: attention model with 6-ch features, forward + registered gradients "
+                             "(GroupPointGrad SA2-4, ThreeInterpolateGrad FP1-4, attention contraction backward SA1-4), "
+                             "B=%d x %d" % (B, NPOINTS),
+                 "value": world * B * K / (tr_ms * 1e-3), "unit": UNIT, "ms_per_step": tr_ms / K,
+                 "batches_in_flight": TD, "gpu_launches": tp[0].launches_per_train_step * K * world}
+        if use_graph:   # back to the forward-only graphs for the probes below
+            for pl in tp:
+                pl.capture(overlap)
+
     # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
     peaks = {}
     try:
@@ -451,7 +546,7 @@ def main():
                 "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms,
                 "peak_source": "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock)" % (nsm, sm_max)}
 
-    rooflines, op_ms, grid_ms, fused_layer = {}, {}, {}, None
+    rooflines, op_ms, grid_ms, fused_layer, steady = {}, {}, {}, None, None
     if not args.skip_probe:
         # Every op's stand-alone duration: one pipeline instance alone, eager, ONE stream.  The table is taken with the
         # reference-signature ops (all-pairs ball query / three_nn, separate gather), whose algorithmic op counts the
@@ -477,6 +572,20 @@ def main():
         if args.grid:
             g = probe(pipe)
             grid_ms = {n: ms for n, ms in g.items() if n.startswith(("query_ball", "three_nn", "fps"))}
+        if train is not None:      # the gradient ops alone (single stream, eager), against the HBM roofline
+            bw = pipe.backward_work()
+            allp = {n: [] for n in pipe.backward_op_names()}
+            for i in range(min(K, 10)):
+                pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+                pipe.forward(False, allp, train=True)
+                torch.cuda.synchronize(dev)
+            work.update(bw)
+            for n, evs in allp.items():
+                rooflines[n] = roof(n, sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2])
+        try:
+            steady = time_steady_state_gathers(torch, pcops_b200, hbm_peak)
+        except Exception as exc:
+            steady = {"error": str(exc)[:200]}
         # The fused AttentionLayer (Dense Q/K/V + contraction on tcgen05, csrc/attention_layer.cu) at the SA1 shape, next
         # to the composition it replaces (three fp32 cuBLAS GEMMs + pc_attention_fwd); GPU time of a CUDA-graph replay.
         try:
@@ -523,13 +632,16 @@ def main():
         from oracle import cpu  # test infrastructure, used here only as the timed CPU baseline
         cpu.lib()
         threads = host_threads()
-        ns = args.cpu_scenes or max(threads, 8)
-        x = np.concatenate([t.numpy() for t in host_xyz])[:ns]
-        f = np.concatenate([t.numpy() for t in host_feat])[:ns]
+        x = np.concatenate([t.numpy() for t in host_xyz])
+        f = np.concatenate([t.numpy() for t in host_feat])
         v1, dt1 = cpu_scenes_per_s(x[:2], f[:2], 1, False)
+        # bounded sample of about 10 s of wall time: the ring's scenes, cycled, sized from the single-thread rate
+        ns = args.cpu_scenes or int(min(4096, max(threads, 10.0 * v1 * threads * 0.6)))
+        sel = np.arange(ns) % x.shape[0]
+        x, f = x[sel], f[sel]
         vN, dtN = cpu_scenes_per_s(x, f, threads, False)
         cpu_baseline = {"value": vN, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "%d scenes of the bench batches, %d host threads (one scene per thread), %.1f s"
+                        "sample": "%d scenes drawn from the bench batches, %d host threads (one scene per thread), %.1f s"
                                   % (x.shape[0], threads, dtN),
                         "single_thread": {"value": v1, "cores": 1, "sample": "2 scenes, %.1f s" % dt1}}
 
@@ -551,6 +663,8 @@ def main():
         "roofline": roofline,
         "rooflines": rooflines,
         "grid_variants_ms": grid_ms,
+        "config3_training_step": train,
+        "gathers_steady_state": steady,
         "attention_layer_tcgen05": fused_layer,
         "cpu_baseline": cpu_baseline,
     }

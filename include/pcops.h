@@ -230,6 +230,45 @@ PC_API int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const fl
 PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, const float *dout,
                      float *dQ, float *dK, float *dV, pc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Whole-scene chunker and map-back (reference: attention_points/scannet_dataset/complete_scene_loader.py:4-117,
+ * attention_points/benchmark/generate_predictions.py:19-37) -- SURVEY.md 8f rank 4, BASELINE config 4
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Membership of every point of a scan in every padded 1.5 m cell, compacted per cell in ascending point index (the
+ * order of numpy's boolean mask, complete_scene_loader.py:35-36), plus the un-padded membership flag (:41).
+ *   points (n,3) f32; boxes (ncells,12) f32 = padded lo[3], padded hi[3], inner lo[3], inner hi[3] (inclusive compares;
+ *   the caller rounds the reference's float64 thresholds to fp32 so the compare is identical)
+ *   -> cell_base (ncells+1) i32: list offsets of each cell, [ncells] = total; list (capacity 4n) i32 point indices;
+ *      inner (capacity 4n) u8.   workspace: pc_scene_cells_workspace_bytes(n, ncells). */
+PC_API size_t pc_scene_cells_workspace_bytes(int n, int ncells);
+PC_API int pc_scene_cells(int n, int ncells, const float *points, const float *boxes, int *cell_base, int *list,
+                   unsigned char *inner, void *workspace, pc_stream_t stream);
+
+/* Candidate chunks are described by 5 ints {list_base, order_off, start, rest, fill_off}: row t < rest is cell position
+ * order[order_off+start+t] (the host-drawn np.random.shuffle order, :45-48), row t >= rest is the fill-up position
+ * order[order_off + fill[fill_off+t-rest]] (np.random.choice, :87-90); the source point is list[list_base+position].
+ * masksum[chunk] = number of rows t < rest inside the un-padded cell (chunks with 0 are dropped, :63,:99). */
+PC_API int pc_scene_chunk_masksum(int nchunks, int npoints, const int *desc, const int *order, const unsigned char *inner,
+                           int *masksum, pc_stream_t stream);
+/* The kept chunks: src_index (nchunks,npoints) i32 source point of every row, point_sets (nchunks,npoints,3) f32,
+ * masks (nchunks,npoints) u8 (0 on fill-up rows, :92), orig_idx (nchunks,npoints) i64 (0 on fill-up rows, :93-94). */
+PC_API int pc_scene_chunk_assemble(int nchunks, int npoints, const int *desc, const int *order, const int *fill,
+                            const int *list, const unsigned char *inner, const float *points, int *src_index,
+                            float *point_sets, unsigned char *masks, long long *orig_idx, pc_stream_t stream);
+/* out[r,:] = src[src_index[r],:] for rows of row_bytes bytes of any dtype (labels, colours, normals); rows whose index
+ * is negative are zero-filled. */
+PC_API int pc_gather_rows_bytes(size_t rows, int row_bytes, const void *src, const int *src_index, void *out,
+                         pc_stream_t stream);
+/* sample_weight (nchunks,npoints) f64 = label_weights[label] (ones(21) with [0]=0, :12-13; 1 when labels is NULL),
+ * times the mask for full chunks (:70) but not for the fill-up chunk (:100-103).  labels: gathered (nchunks,npoints) i32. */
+PC_API int pc_scene_sample_weights(int nchunks, int npoints, const int *desc, const int *labels, const unsigned char *masks,
+                            double *out, pc_stream_t stream);
+/* map_back (generate_predictions.py:19-37): winner[i] = last row r with mask[r] and orig_idx[r] == i, or -1; the
+ * remapped array is then pc_gather_rows_bytes(nres, ..., values, winner, res) (zeros where nobody wrote). */
+PC_API int pc_map_back_winner(size_t rows, int nres, const long long *orig_idx, const unsigned char *mask, int *winner,
+                       pc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,13 @@ SIGNATURES = {
     "pc_attention_layer_fwd": (_i, [_i, _i, _i] + [_vp] * 11),
     "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pc_scene_cells_workspace_bytes": (_sz, [_i, _i]),
+    "pc_scene_cells": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pc_scene_chunk_masksum": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_scene_chunk_assemble": (_i, [_i, _i] + [_vp] * 11),
+    "pc_gather_rows_bytes": (_i, [_sz, _i, _vp, _vp, _vp, _vp]),
+    "pc_scene_sample_weights": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_map_back_winner": (_i, [_sz, _i, _vp, _vp, _vp, _vp]),
 }
 
 

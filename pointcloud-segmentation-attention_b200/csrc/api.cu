@@ -16,6 +16,47 @@ int num_sms() {
   }
   return cached[dev];
 }
+
+cudaError_t allow_smem_cached(const void *kernel, size_t bytes) {
+  struct Entry { const void *k; int dev; size_t bytes; };
+  static std::mutex mu;
+  static Entry table[256];
+  static int used = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  Entry *slot = nullptr;
+  for (int i = 0; i < used; ++i)
+    if (table[i].k == kernel && table[i].dev == dev) { slot = &table[i]; break; }
+  if (slot && slot->bytes >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  if (slot) slot->bytes = bytes;
+  else if (used < 256) table[used++] = Entry{kernel, dev, bytes};
+  return cudaSuccess;
+}
+
+int resident_grid(const void *kernel, int threads, size_t smem, size_t needed) {
+  // occupancy per (kernel, threads, smem), cached: cudaOccupancyMaxActiveBlocksPerMultiprocessor costs microseconds
+  struct Entry { const void *k; int threads; size_t smem; int occ; };
+  static std::mutex mu;
+  static Entry table[64];
+  static int used = 0;
+  int occ = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < used; ++i)
+      if (table[i].k == kernel && table[i].threads == threads && table[i].smem == smem) { occ = table[i].occ; break; }
+    if (occ == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ <= 0) occ = 1;
+      if (used < 64) table[used++] = Entry{kernel, threads, smem, occ};
+    }
+  }
+  size_t g = (size_t)num_sms() * (size_t)occ;
+  if (g > needed) g = needed;
+  return g < 1 ? 1 : (int)g;
+}
 }  // namespace pc
 
 extern "C" int pc_version(void) { return 100; }

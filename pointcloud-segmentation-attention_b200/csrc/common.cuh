@@ -79,12 +79,33 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Exact floor(x / d) for 0 <= x < 2^31 as one widening multiply and a shift (s = 31 + ceil(log2 d),
+// m = ceil(2^s / d) < 2^32).  The flat-index kernels (gathers, interpolation) decode (row, channel, scene) from a
+// linear element index; a 64-bit hardware-less division there costs more issue slots than the gather itself.
+struct FastDiv {
+  uint32_t d, m, s;
+  FastDiv() : d(1), m(0x80000000u), s(31) {}
+  explicit FastDiv(uint32_t dd) : d(dd ? dd : 1) {
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    s = 31 + l;
+    m = (uint32_t)(((1ull << s) + d - 1) / d);
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return (uint32_t)(((unsigned long long)x * m) >> s); }
+};
+// Grid size for a grid-stride kernel: every SM filled to the kernel's real occupancy, never more CTAs than `needed`
+// (a second, partially filled wave costs a short HBM-bound kernel up to half its run time).
+int resident_grid(const void *kernel, int threads, size_t smem, size_t needed);
+
 // SM count of the current device, cached per device id.
 int num_sms();
 // Opt a kernel into > 48 KB dynamic shared memory (idempotent; cheap).
+// The attribute is set once per (kernel, device) and raised only when a larger size is asked for, so steady-state
+// calls (and calls made while a stream is being captured into a CUDA graph) touch no driver state.
+cudaError_t allow_smem_cached(const void *kernel, size_t bytes);
 template <class K>
 inline cudaError_t allow_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return allow_smem_cached((const void *)kernel, bytes);
 }
 
 // Largest float s with max(sqrtf(s), 1e-20f) < radius, or -1 if there is none (ball_query.cu): the exact form of the

@@ -152,27 +152,47 @@ __device__ __forceinline__ float blend3(float p1, float p2, float p3, float w1, 
 }
 
 constexpr int kInterpUnroll = 2;  // 2 x 3 independent 128-bit row loads in flight per thread
+// Index decoding: multiply-shift (FastDiv) while the output has < 2^31 elements, real 64-bit divisions beyond.
+template <class I> struct RowDecode;
+template <> struct RowDecode<uint32_t> {
+  FastDiv a, b;
+  RowDecode(size_t da, size_t db) : a((uint32_t)da), b((uint32_t)db) {}
+  __device__ __forceinline__ uint32_t by_a(uint32_t x) const { return a.div(x); }
+  __device__ __forceinline__ uint32_t by_b(uint32_t x) const { return b.div(x); }
+  __device__ __forceinline__ uint32_t da() const { return a.d; }
+};
+template <> struct RowDecode<size_t> {
+  size_t a, b;
+  RowDecode(size_t da, size_t db) : a(da ? da : 1), b(db ? db : 1) {}
+  __device__ __forceinline__ size_t by_a(size_t x) const { return x / a; }
+  __device__ __forceinline__ size_t by_b(size_t x) const { return x / b; }
+  __device__ __forceinline__ size_t da() const { return a; }
+};
+
+template <class I>
 __global__ void __launch_bounds__(256)
-interp_vec4_kernel(size_t total_vec, int c4, int n, int m, const float4 *__restrict__ points,
+interp_vec4_kernel(I total_vec, RowDecode<I> dec /* a = c4, b = n */, int m, const float4 *__restrict__ points,
                    const int *__restrict__ idx, const float *__restrict__ weight, float4 *__restrict__ out) {
-  const size_t step = (size_t)gridDim.x * blockDim.x;
-  for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < total_vec; v0 += step * kInterpUnroll) {
+  const I step = (I)gridDim.x * blockDim.x;
+  const I c4 = dec.da();
+  for (I v0 = (I)blockIdx.x * blockDim.x + threadIdx.x; v0 < total_vec; v0 += step * kInterpUnroll) {
     float4 a[kInterpUnroll], b[kInterpUnroll], c[kInterpUnroll];
     float w1[kInterpUnroll], w2[kInterpUnroll], w3[kInterpUnroll];
 #pragma unroll
     for (int u = 0; u < kInterpUnroll; ++u) {
-      const size_t v = min(v0 + u * step, total_vec - 1);
-      const size_t row = v / c4;  // scene*n + j
-      const int q = (int)(v - row * c4);
-      const size_t scene = row / n;
-      const int i1 = __ldg(idx + row * 3), i2 = __ldg(idx + row * 3 + 1), i3 = __ldg(idx + row * 3 + 2);
-      w1[u] = __ldg(weight + row * 3); w2[u] = __ldg(weight + row * 3 + 1); w3[u] = __ldg(weight + row * 3 + 2);
-      const float4 *base = points + scene * (size_t)m * c4 + q;
+      const I v = min(v0 + u * step, total_vec - 1);
+      const I row = dec.by_a(v);  // scene*n + j
+      const I q = v - row * c4;
+      const I scene = dec.by_b(row);
+      const size_t r3 = (size_t)row * 3;
+      const int i1 = __ldg(idx + r3), i2 = __ldg(idx + r3 + 1), i3 = __ldg(idx + r3 + 2);
+      w1[u] = __ldg(weight + r3); w2[u] = __ldg(weight + r3 + 1); w3[u] = __ldg(weight + r3 + 2);
+      const float4 *base = points + (size_t)scene * (size_t)m * c4 + q;
       a[u] = __ldg(base + (size_t)i1 * c4); b[u] = __ldg(base + (size_t)i2 * c4); c[u] = __ldg(base + (size_t)i3 * c4);
     }
 #pragma unroll
     for (int u = 0; u < kInterpUnroll; ++u) {
-      const size_t v = v0 + u * step;
+      const I v = v0 + u * step;
       if (v < total_vec)
         __stcs(out + v, make_float4(blend3(a[u].x, b[u].x, c[u].x, w1[u], w2[u], w3[u]),
                                     blend3(a[u].y, b[u].y, c[u].y, w1[u], w2[u], w3[u]),
@@ -182,17 +202,34 @@ interp_vec4_kernel(size_t total_vec, int c4, int n, int m, const float4 *__restr
   }
 }
 
+template <class I>
 __global__ void __launch_bounds__(256)
-interp_scalar_kernel(size_t total, int c, int n, int m, const float *__restrict__ points,
+interp_scalar_kernel(I total, RowDecode<I> dec /* a = c, b = n */, int m, const float *__restrict__ points,
                      const int *__restrict__ idx, const float *__restrict__ weight, float *__restrict__ out) {
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = e / c;
-    const int l = (int)(e - row * c);
-    const size_t scene = row / n;
-    const int i1 = __ldg(idx + row * 3), i2 = __ldg(idx + row * 3 + 1), i3 = __ldg(idx + row * 3 + 2);
-    const float w1 = __ldg(weight + row * 3), w2 = __ldg(weight + row * 3 + 1), w3 = __ldg(weight + row * 3 + 2);
-    const float *base = points + scene * (size_t)m * c + l;
+  const I c = dec.da();
+  for (I e = (I)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (I)gridDim.x * blockDim.x) {
+    const I row = dec.by_a(e);
+    const I l = e - row * c;
+    const I scene = dec.by_b(row);
+    const size_t r3 = (size_t)row * 3;
+    const int i1 = __ldg(idx + r3), i2 = __ldg(idx + r3 + 1), i3 = __ldg(idx + r3 + 2);
+    const float w1 = __ldg(weight + r3), w2 = __ldg(weight + r3 + 1), w3 = __ldg(weight + r3 + 2);
+    const float *base = points + (size_t)scene * (size_t)m * c + l;
     out[e] = blend3(__ldg(base + (size_t)i1 * c), __ldg(base + (size_t)i2 * c), __ldg(base + (size_t)i3 * c), w1, w2, w3);
+  }
+}
+
+template <class I>
+void launch_interp(size_t total, int c, int n, int m, const float *points, const int *idx, const float *weight,
+                   float *out, cudaStream_t st) {
+  if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+    const size_t nv = total / 4;
+    const int blocks = resident_grid((const void *)interp_vec4_kernel<I>, 256, 0, (nv + 256 * kInterpUnroll - 1) / (256 * kInterpUnroll));
+    interp_vec4_kernel<I><<<blocks, 256, 0, st>>>((I)nv, RowDecode<I>((size_t)c / 4, (size_t)n), m, (const float4 *)points, idx,
+                                                  weight, (float4 *)out);
+  } else {
+    const int blocks = resident_grid((const void *)interp_scalar_kernel<I>, 256, 0, (total + 255) / 256);
+    interp_scalar_kernel<I><<<blocks, 256, 0, st>>>((I)total, RowDecode<I>((size_t)c, (size_t)n), m, points, idx, weight, out);
   }
 }
 
@@ -232,17 +269,7 @@ extern "C" int pc_three_interpolate(int b, int m, int c, int n, const float *poi
   if (m == 0 || !points || !idx || !weight || !out) return PC_ERR_INVALID_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t total = (size_t)b * n * c;
-  const size_t cap = (size_t)pc::num_sms() * 16;
-  if (c % 4 == 0 && pc::aligned16(points) && pc::aligned16(out)) {
-    const size_t nv = total / 4;
-    size_t blocks = (nv + 256 * pc::kInterpUnroll - 1) / (256 * pc::kInterpUnroll);
-    if (blocks > cap) blocks = cap;
-    pc::interp_vec4_kernel<<<(unsigned)blocks, 256, 0, st>>>(nv, c / 4, n, m, (const float4 *)points, idx, weight,
-                                                             (float4 *)out);
-  } else {
-    size_t blocks = (total + 255) / 256;
-    if (blocks > cap) blocks = cap;
-    pc::interp_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(total, c, n, m, points, idx, weight, out);
-  }
+  if (total < (1ull << 31)) pc::launch_interp<uint32_t>(total, c, n, m, points, idx, weight, out, st);
+  else pc::launch_interp<size_t>(total, c, n, m, points, idx, weight, out, st);
   PC_RETURN_LAUNCH_STATUS();
 }

@@ -79,23 +79,36 @@ csr_build_kernel(int nkeys, int npos, int W, int part, const int *__restrict__ i
     int *c = cnt + warp * nkeys;
     const int lo = warp * part, hi = min(npos, lo + part);
     const unsigned lt = lanemask_lt();
-    for (int p0 = lo; p0 < hi; p0 += 32) {
-      const int p = p0 + lane;
-      const bool valid = p < hi;
-      const unsigned act = __ballot_sync(PC_FULL_MASK, valid);
-      if (valid) {
-        const int key = keys[p];
-        const unsigned peers = __match_any_sync(act, key);
-        const int leader = __ffs(peers) - 1;
-        int slot = 0;
-        if (lane == leader) {
-          slot = c[key];
-          c[key] = slot + __popc(peers);
-        }
-        slot = __shfl_sync(peers, slot, leader);
-        list[slot + __popc(peers & lt)] = p;
+    // keys of kPre steps are fetched ahead of the serial counter walk (the walk itself is a dependent
+    // shared-memory chain; a global load per step in front of it made every step an L2 / DRAM round trip)
+    constexpr int kPre = 8;
+    for (int p0 = lo; p0 < hi; p0 += 32 * kPre) {
+      int kreg[kPre];
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int p = p0 + 32 * u + lane;
+        kreg[u] = p < hi ? __ldg(keys + p) : -1;
       }
-      __syncwarp();  // orders this step's counter stores before the next step's loads
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int p = p0 + 32 * u + lane;
+        const bool valid = p < hi;
+        const unsigned act = __ballot_sync(PC_FULL_MASK, valid);
+        if (act == 0) break;
+        if (valid) {
+          const int key = kreg[u];
+          const unsigned peers = __match_any_sync(act, key);
+          const int leader = __ffs(peers) - 1;
+          int slot = 0;
+          if (lane == leader) {
+            slot = c[key];
+            c[key] = slot + __popc(peers);
+          }
+          slot = __shfl_sync(peers, slot, leader);
+          list[slot + __popc(peers & lt)] = p;
+        }
+        __syncwarp();  // orders this step's counter stores before the next step's loads
+      }
     }
   }
 }
@@ -181,8 +194,9 @@ csr_build_big_kernel(int nkeys, int npos, const int *__restrict__ idx, int *__re
 // out[scene, i, 4q..4q+3] = sum_{e in row i} src[scene, list[e]/div, 4q..] * (w ? w[scene, list[e]] : 1)
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
-csr_reduce_vec4_kernel(int nkeys, int npos, int c4, int div, const float4 *__restrict__ src,
-                       const float *__restrict__ w, const int *__restrict__ ws, float4 *__restrict__ out) {
+csr_reduce_vec4_kernel(int nkeys, int npos, int c4, int div, FastDiv fc, FastDiv fdiv, bool fits32,
+                       const float4 *__restrict__ src, const float *__restrict__ w, const int *__restrict__ ws,
+                       float4 *__restrict__ out) {
   const int scene = blockIdx.y;
   const int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
   const int *list = row_ptr + nkeys + 1;
@@ -190,18 +204,32 @@ csr_reduce_vec4_kernel(int nkeys, int npos, int c4, int div, const float4 *__res
   const float *ww = WEIGHTED ? w + (size_t)scene * npos : nullptr;
   const size_t total = (size_t)nkeys * c4;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(t / c4), q = (int)(t - (size_t)i * c4);
+    const int i = fits32 ? (int)fc.div((uint32_t)t) : (int)(t / c4), q = (int)(t - (size_t)i * c4);
     const int lo = row_ptr[i], hi = row_ptr[i + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = lo; e < hi; ++e) {
-      const int p = list[e];
-      float4 g = __ldg(s + (size_t)(p / div) * c4 + q);
-      if (WEIGHTED) {
-        const float wt = __ldg(ww + p);
-        g.x = __fmul_rn(g.x, wt); g.y = __fmul_rn(g.y, wt); g.z = __fmul_rn(g.z, wt); g.w = __fmul_rn(g.w, wt);
+    // four contributors' loads in flight at a time; the additions stay strictly in list order
+    constexpr int kU = 4;
+    for (int e = lo; e < hi; e += kU) {
+      int p[kU];
+      float4 g[kU];
+      float wt[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) p[u] = (e + u < hi) ? list[e + u] : -1;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        g[u] = p[u] >= 0 ? __ldg(s + (size_t)fdiv.div((uint32_t)p[u]) * c4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wt[u] = (WEIGHTED && p[u] >= 0) ? __ldg(ww + p[u]) : 1.0f;
       }
-      acc.x = __fadd_rn(acc.x, g.x); acc.y = __fadd_rn(acc.y, g.y);
-      acc.z = __fadd_rn(acc.z, g.z); acc.w = __fadd_rn(acc.w, g.w);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (p[u] < 0) break;
+        float4 t = g[u];
+        if (WEIGHTED) {
+          t.x = __fmul_rn(t.x, wt[u]); t.y = __fmul_rn(t.y, wt[u]); t.z = __fmul_rn(t.z, wt[u]); t.w = __fmul_rn(t.w, wt[u]);
+        }
+        acc.x = __fadd_rn(acc.x, t.x); acc.y = __fadd_rn(acc.y, t.y);
+        acc.z = __fadd_rn(acc.z, t.z); acc.w = __fadd_rn(acc.w, t.w);
+      }
     }
     out[((size_t)scene * nkeys + i) * c4 + q] = acc;
   }
@@ -209,8 +237,9 @@ csr_reduce_vec4_kernel(int nkeys, int npos, int c4, int div, const float4 *__res
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
-csr_reduce_scalar_kernel(int nkeys, int npos, int c, int div, const float *__restrict__ src,
-                         const float *__restrict__ w, const int *__restrict__ ws, float *__restrict__ out) {
+csr_reduce_scalar_kernel(int nkeys, int npos, int c, int div, FastDiv fc, FastDiv fdiv, bool fits32,
+                         const float *__restrict__ src, const float *__restrict__ w, const int *__restrict__ ws,
+                         float *__restrict__ out) {
   const int scene = blockIdx.y;
   const int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
   const int *list = row_ptr + nkeys + 1;
@@ -218,12 +247,12 @@ csr_reduce_scalar_kernel(int nkeys, int npos, int c, int div, const float *__res
   const float *ww = WEIGHTED ? w + (size_t)scene * npos : nullptr;
   const size_t total = (size_t)nkeys * c;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(t / c), l = (int)(t - (size_t)i * c);
+    const int i = fits32 ? (int)fc.div((uint32_t)t) : (int)(t / c), l = (int)(t - (size_t)i * c);
     const int lo = row_ptr[i], hi = row_ptr[i + 1];
     float acc = 0.f;
     for (int e = lo; e < hi; ++e) {
       const int p = list[e];
-      float g = __ldg(s + (size_t)(p / div) * c + l);
+      float g = __ldg(s + (size_t)fdiv.div((uint32_t)p) * c + l);
       if (WEIGHTED) g = __fmul_rn(g, __ldg(ww + p));
       acc = __fadd_rn(acc, g);
     }
@@ -268,15 +297,15 @@ int csr_reduce(int b, int nkeys, int npos, int c, int div, const float *src, con
     unsigned gx = (unsigned)((total + 255) / 256);
     if (gx > (unsigned)sms * 32) gx = (unsigned)sms * 32;
     dim3 grid(gx, b);
-    if (w) csr_reduce_vec4_kernel<true><<<grid, 256, 0, st>>>(nkeys, npos, c / 4, div, (const float4 *)src, w, workspace, (float4 *)out);
-    else   csr_reduce_vec4_kernel<false><<<grid, 256, 0, st>>>(nkeys, npos, c / 4, div, (const float4 *)src, w, workspace, (float4 *)out);
+    if (w) csr_reduce_vec4_kernel<true><<<grid, 256, 0, st>>>(nkeys, npos, c / 4, div, FastDiv((uint32_t)(c / 4)), FastDiv((uint32_t)div), total < (1ull << 31), (const float4 *)src, w, workspace, (float4 *)out);
+    else   csr_reduce_vec4_kernel<false><<<grid, 256, 0, st>>>(nkeys, npos, c / 4, div, FastDiv((uint32_t)(c / 4)), FastDiv((uint32_t)div), total < (1ull << 31), (const float4 *)src, w, workspace, (float4 *)out);
   } else {
     const size_t total = (size_t)nkeys * c;
     unsigned gx = (unsigned)((total + 255) / 256);
     if (gx > (unsigned)sms * 32) gx = (unsigned)sms * 32;
     dim3 grid(gx, b);
-    if (w) csr_reduce_scalar_kernel<true><<<grid, 256, 0, st>>>(nkeys, npos, c, div, src, w, workspace, out);
-    else   csr_reduce_scalar_kernel<false><<<grid, 256, 0, st>>>(nkeys, npos, c, div, src, w, workspace, out);
+    if (w) csr_reduce_scalar_kernel<true><<<grid, 256, 0, st>>>(nkeys, npos, c, div, FastDiv((uint32_t)c), FastDiv((uint32_t)div), total < (1ull << 31), src, w, workspace, out);
+    else   csr_reduce_scalar_kernel<false><<<grid, 256, 0, st>>>(nkeys, npos, c, div, FastDiv((uint32_t)c), FastDiv((uint32_t)div), total < (1ull << 31), src, w, workspace, out);
   }
   PC_RETURN_LAUNCH_STATUS();
 }

@@ -121,6 +121,7 @@ class ScanNetGeometry:
                                                      (1 if fuse_gather else 0) - (1 if fuse_layers else 0)) + \
             sum(3 + (2 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps)
         self._graph = None
+        self.training = False
 
     # ---- inputs / outputs ----------------------------------------------------------------------------------
     def set_inputs(self, xyz, feats, non_blocking=True):
@@ -198,8 +199,9 @@ class ScanNetGeometry:
             run("three_interpolate_" + tag, side, lambda: L.pc_three_interpolate(
                 B, m, c, n, p(fp["points2"]), p(fp["idx"]), p(fp["w"]), p(fp["out"]), st))
 
-    def forward(self, overlap=True, probes=None):
-        """Enqueue one forward on the current stream (plus the side stream when overlap=True).
+    def forward(self, overlap=True, probes=None, train=False):
+        """Enqueue one forward on the current stream (plus the side stream when overlap=True).  train=True (after
+        allocate_backward()) also enqueues the level's gradient ops behind its forward ops: a training step.
 
         ``probes``: optional dict name -> list; for every op whose name is a key, a (start, end) pair of CUDA events
         recorded on the op's own stream around its launch is appended (bench.py reads kernel durations from them)."""
@@ -234,6 +236,8 @@ class ScanNetGeometry:
             if "side" in parts:
                 self._sa_rest(lv, li, side, run)
                 self._fp(fp_of[li], side, run)
+                if train:
+                    self._backward_level(lv, li, fp_of[li], side, run)
         if overlap:
             for side in self.sides:
                 main.wait_stream(side)
@@ -277,16 +281,87 @@ class ScanNetGeometry:
             w["fp_interpolate" + t] = dict(kind="bytes", amount=B * (24 * n + 4 * m * c + 4 * n * c + 12 * n))
         return w
 
+    # ---- backward (config 3: a training step) ----------------------------------------------------------------
+    def allocate_backward(self, seed=1234):
+        """Buffers of the registered gradients a training step of the attention model with features runs
+        (a6 GroupPointGrad at SA2-4 -- the SA1 features are network inputs and carry no gradient,
+        a10 ThreeInterpolateGrad at FP1-4, the attention contraction's backward at the four attention levels).
+        The upstream gradients the (out-of-scope) dense layers would deliver are fixed synthetic stand-ins."""
+        if self.training:
+            return
+        B, dev, f32 = self.B, self.dev, torch.float32
+        g = torch.Generator(device=dev).manual_seed(seed)
+
+        def rnd(*shape):
+            return torch.randn(*shape, generator=g, dtype=f32, device=dev)
+        for li, lv in enumerate(self.levels):
+            n, m, ns, cin, cout = lv["n"], lv["m"], lv["ns"], lv["cin"], lv["cout"]
+            if self.attention:
+                lv["d_att"] = rnd(B * m, cout)
+                lv["dQ"] = torch.empty_like(lv["Q"])
+                lv["dK"] = torch.empty_like(lv["K"])
+                lv["dV"] = torch.empty_like(lv["V"])
+            if li > 0:
+                lv["d_gfeat"] = rnd(B, m, ns, cin)
+                lv["d_feat"] = torch.empty((B, n, cin), dtype=f32, device=dev)
+                lv["gg_ws"] = _lib.workspace(self.L.pc_group_point_grad_workspace_bytes(B, n, cin, m, ns), dev)
+        for fp in self.fps:
+            n, m, c = fp["n"], fp["m"], fp["c"]
+            fp["d_out"] = rnd(B, n, c)
+            fp["d_points2"] = torch.empty((B, m, c), dtype=f32, device=dev)
+            fp["ig_ws"] = _lib.workspace(self.L.pc_three_interpolate_grad_workspace_bytes(B, n, c, m), dev)
+        self.training = True
+        self.launches_per_train_step = self.launches_per_step + (len(self.levels) if self.attention else 0) + \
+            2 * (len(self.levels) - 1) + 2 * len(self.fps)   # each gradient op = CSR build + segmented reduce
+
+    def _backward_level(self, lv, li, fp, side, run):
+        L, B, p = self.L, self.B, _lib.ptr
+        st = ctypes.c_void_p(side.cuda_stream)
+        tag = "fp%d" % (4 - fp["level"])
+        run("three_interpolate_grad_" + tag, side, lambda: L.pc_three_interpolate_grad(
+            B, fp["n"], fp["c"], fp["m"], p(fp["d_out"]), p(fp["idx"]), p(fp["w"]), p(fp["d_points2"]), p(fp["ig_ws"]), st))
+        if self.attention:
+            run("attention_bwd_sa%d" % (li + 1), side, lambda: L.pc_attention_bwd(
+                B * lv["m"], lv["ns"], lv["cout"] // KEY_DIM, KEY_DIM, p(lv["Q"]), p(lv["K"]), p(lv["V"]), p(lv["d_att"]),
+                p(lv["dQ"]), p(lv["dK"]), p(lv["dV"]), st))
+        if li > 0:
+            run("group_point_grad_sa%d" % (li + 1), side, lambda: L.pc_group_point_grad(
+                B, lv["n"], lv["cin"], lv["m"], lv["ns"], p(lv["d_gfeat"]), p(lv["idx"]), p(lv["d_feat"]), p(lv["gg_ws"]), st))
+
+    def backward_op_names(self):
+        names = []
+        for li in range(len(self.levels)):
+            names.append("three_interpolate_grad_fp%d" % (4 - li))
+            if self.attention:
+                names.append("attention_bwd_sa%d" % (li + 1))
+            if li > 0:
+                names.append("group_point_grad_sa%d" % (li + 1))
+        return names
+
+    def backward_work(self):
+        """Algorithmic bytes of the gradient ops (same formulas as the forward ops with read / write swapped)."""
+        B, w = self.B, {}
+        for li, lv in enumerate(self.levels):
+            n, m, ns, cin, cout = lv["n"], lv["m"], lv["ns"], lv["cin"], lv["cout"]
+            w["group_point_grad_sa%d" % (li + 1)] = dict(kind="bytes", amount=B * (4 * m * ns + 4 * n * cin + 4 * m * ns * cin))
+            # reads Q, K, V, dout; writes dQ, dK, dV
+            w["attention_bwd_sa%d" % (li + 1)] = dict(kind="bytes", amount=B * m * (4 * 4 * ns * cout + 3 * 4 * cout))
+        for fp in self.fps:
+            n, m, c = fp["n"], fp["m"], fp["c"]
+            w["three_interpolate_grad_fp%d" % (4 - fp["level"])] = dict(kind="bytes", amount=B * (24 * n + 4 * m * c + 4 * n * c))
+        return w
+
     # ---- CUDA graph ------------------------------------------------------------------------------------------
-    def capture(self, overlap=True):
-        """Capture forward() into a CUDA graph (after one eager warm-up); replay with .replay()."""
-        self.forward(overlap)
+    def capture(self, overlap=True, train=False):
+        """Capture forward() (train=True: forward + backward) into a CUDA graph (after one eager warm-up); replay
+        with .replay()."""
+        self.forward(overlap, train=train)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         saved, self.main = self.main, None  # inside the capture the capture stream plays the role of main
         try:
             with torch.cuda.graph(g, stream=saved):
-                self.forward(overlap)
+                self.forward(overlap, train=train)
         finally:
             self.main = saved
         self._graph = g

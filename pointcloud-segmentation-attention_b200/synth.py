@@ -90,3 +90,39 @@ def uniform_cube(seed, *shape):
 
 def features(seed, *shape):
     return _rng(seed).standard_normal(shape, dtype=np.float32)
+
+
+def whole_scene(seed, npoints=None):
+    """One synthetic whole scan (config 4): a room of 4-9 m x 4-9 m x 2.4-3 m -- floor, four walls, box clutter --
+    sampled with ~5 mm noise at 100-200 k points (default), as complete_scene_loader.py expects it:
+    points (N,3) float32, labels (N,) int32 in 0..20, colors (N,3) uint8, normals (N,3) float32."""
+    rng = _rng(int(seed) + 7_000_000)
+    n = int(npoints) if npoints is not None else int(rng.integers(100_000, 200_001))
+    Lx, Ly, H = float(rng.uniform(4.0, 9.0)), float(rng.uniform(4.0, 9.0)), float(rng.uniform(2.4, 3.0))
+    ex, ey, ez = np.eye(3)
+    parts = [(Lx * Ly, np.zeros(3), Lx * ex, Ly * ey, ez, 2),
+             (Lx * H, np.zeros(3), Lx * ex, H * ez, ey, 1), (Lx * H, np.array([0, Ly, 0.0]), Lx * ex, H * ez, -ey, 1),
+             (Ly * H, np.zeros(3), Ly * ey, H * ez, ex, 1), (Ly * H, np.array([Lx, 0, 0.0]), Ly * ey, H * ez, -ex, 1)]
+    for _ in range(int(rng.integers(6, 20))):
+        sx, sy, sz = rng.uniform(0.3, 1.5), rng.uniform(0.3, 1.5), rng.uniform(0.3, 1.2)
+        o = np.array([rng.uniform(0, Lx - sx), rng.uniform(0, Ly - sy), 0.0])
+        lab = int(rng.integers(3, 21))
+        parts += [(sx * sy, o + sz * ez, sx * ex, sy * ey, ez, lab), (sx * sz, o, sx * ex, sz * ez, -ey, lab),
+                  (sy * sz, o, sy * ey, sz * ez, -ex, lab)]
+    areas = np.array([p[0] for p in parts])
+    counts = rng.multinomial(n, areas / areas.sum())
+    pts, nrm, col, lab = [], [], [], []
+    for (area, o, u, v, nn, lb), k in zip(parts, counts):
+        k = int(k)
+        if k == 0:
+            continue
+        p, q = _plane(rng, k, o, u, v, nn)
+        pts.append(p)
+        nrm.append(q)
+        base = rng.integers(30, 226, size=3)
+        col.append(np.clip(base[None, :] + rng.integers(-25, 26, size=(k, 3)), 0, 255))
+        lab.append(np.full(k, lb if rng.random() > 0.05 else 0, np.int32))
+    perm = rng.permutation(n)   # scan order is not surface order
+    pts = (np.concatenate(pts, 0) + rng.normal(0.0, 0.005, size=(n, 3)))[perm].astype(np.float32)
+    return pts, np.concatenate(lab)[perm], np.concatenate(col, 0).astype(np.uint8)[perm], \
+        np.concatenate(nrm, 0).astype(np.float32)[perm]

@@ -66,3 +66,40 @@ def test_pipeline_matches_oracle_eager_and_graph(grid, fuse):
     again = pipe.result_tensors() + [fp["out"] for fp in pipe.fps]
     for a, b in zip(eager, again):
         assert torch.equal(a, b)                                     # overlap + graph change nothing, bit for bit
+
+
+def test_training_step_gradients_match_oracle():
+    """Config 3: forward + the registered gradients (GroupPointGrad, ThreeInterpolateGrad) and the attention contraction's
+    backward, eager and as one CUDA graph; the gradient ops are bit-exact against the reference's serial order."""
+    B = 2
+    xyz_np, feat_np = synth.scannet_batch(500, B, 8192)
+    pipe = ScanNetGeometry(B)
+    pipe.allocate_backward(seed=9)
+    pipe.set_inputs(torch.from_numpy(xyz_np), torch.from_numpy(feat_np))
+
+    def check():
+        for li, lv in enumerate(pipe.levels):
+            dq, dk, dv = cpu.attention_bwd(npy(lv["Q"]), npy(lv["K"]), npy(lv["V"]), npy(lv["d_att"]),
+                                           lv["cout"] // KEY_DIM, KEY_DIM)
+            for got, want in ((lv["dQ"], dq), (lv["dK"], dk), (lv["dV"], dv)):
+                np.testing.assert_allclose(npy(got), want.reshape(got.shape), rtol=1e-5, atol=1e-5)
+            if li > 0:
+                want = cpu.group_point_grad(npy(lv["feat"]), npy(lv["idx"]), npy(lv["d_gfeat"]))
+                assert np.array_equal(npy(lv["d_feat"]), want)
+        for fp in pipe.fps:
+            want = cpu.three_interpolate_grad(npy(fp["points2"]), npy(fp["idx"]), npy(fp["w"]), npy(fp["d_out"]))
+            assert np.array_equal(npy(fp["d_points2"]), want)
+
+    pipe.forward(overlap=False, train=True)
+    torch.cuda.synchronize()
+    check_against_oracle(pipe, xyz_np, feat_np)
+    check()
+    assert pipe.launches_per_train_step == pipe.launches_per_step + 4 + 2 * 3 + 2 * 4
+    grads = [pipe.levels[1]["d_feat"].clone(), pipe.fps[3]["d_points2"].clone()]
+    pipe.capture(overlap=True, train=True)
+    for t in (pipe.levels[1]["d_feat"], pipe.fps[3]["d_points2"]):
+        t.zero_()
+    pipe.replay()
+    torch.cuda.synchronize()
+    check()
+    assert torch.equal(grads[0], pipe.levels[1]["d_feat"]) and torch.equal(grads[1], pipe.fps[3]["d_points2"])
