@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true", help="single stream")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--scenes", type=int, default=6, help="whole scans per GPU in the config-4 region (0: skip)")
     ap.add_argument("--train", type=int, default=1, help="1: also time config 3 (forward + the registered gradients)")
     ap.add_argument("--train-depth", type=int, default=4, help="batches in flight for the config-3 region")
     ap.add_argument("--skip-probe", action="store_true")
@@ -287,6 +288,95 @@ def time_steady_state_gathers(torch, ops, hbm_peak):
         timed(tag, nbytes, lambda r: L.pc_three_interpolate(B, m, c, n, p(pts[r]), p(idx[r]), p(w[r]), p(dst[r]), st), nsets)
         del pts, idx, w, dst
     torch.cuda.empty_cache()
+    return out
+
+
+def run_config4(torch, np, args, pipes, rank, world, dev, sharding, with_cpu):
+    """Config 4: whole-scan inference data path.  Per scan (100-200 k synthetic points, resident in HBM): the GPU chunker
+    (complete_scene_loader mirror: cells, shuffle, 8192-point chunks, fill-up, masks, original indices, feature gathers),
+    the geometry forward over its chunks in batches of B, and map_back of per-point values (coordinates and labels, as
+    generate_predictions.py:162-166 does).  Scans are sharded over ranks; no collective."""
+    from pcops_b200 import complete_scene_loader as csl
+    from pcops_b200 import synth
+    S, B = args.scenes, pipes[0].B
+    lo, _ = sharding.shard_bounds(world * S, rank, world)
+    scans = []
+    for i in range(S):
+        p, l, c, n = synth.whole_scene(1000 + lo + i)
+        f6 = np.concatenate([c.astype(np.float32) / 255.0, n], 1)      # train.py:95-98 (stock TF cast, outside the op path)
+        scans.append((p, tuple(torch.from_numpy(a).to(dev) for a in (p, l, f6))))
+    cur = torch.cuda.current_stream(dev)
+    use_graph = bool(args.graph)
+    stats = {"chunks": 0, "points": 0}
+
+    def one(i):
+        p, l, f6 = scans[i % S][1]
+        chunks = csl.chunk_scene(p)
+        feats = chunks.gather(f6)
+        labels = chunks.gather(l)
+        C = chunks.nchunks
+        nb = (C + B - 1) // B
+        keep = []   # batch tensors are produced on `cur` and read on the pipeline streams: hold them until the join
+        for b in range(nb):
+            pl = pipes[b % len(pipes)]
+            sel = torch.arange(b * B, b * B + B, device=dev) % C    # the last batch wraps around (fixed-size pipeline)
+            bx, bf = chunks.point_sets[sel], feats[sel]
+            keep.append((bx, bf))
+            pl.main.wait_stream(cur)
+            pl.set_inputs(bx, bf)
+            if use_graph:
+                pl.replay()
+            else:
+                pl.forward(True)
+        orig, masks = chunks.orig_idx.reshape(-1), chunks.masks.reshape(-1)
+        back_p = csl.map_back(chunks.point_sets.reshape(-1, 3), orig, masks, (p.shape[0], 3))
+        back_l = csl.map_back(labels.reshape(-1), orig, masks, (p.shape[0],))
+        for pl in pipes:
+            cur.wait_stream(pl.main)
+        del keep
+        stats["chunks"] += C
+        stats["points"] += int(p.shape[0])
+        return back_p, back_l
+
+    np.random.seed(99 + rank)
+    bp, bl = one(0)
+    torch.cuda.synchronize(dev)
+    # fraction of the scan's points whose coordinates come back bit-exact (the reference's float32 height bound can
+    # leave the top-most point outside every un-padded cell, complete_scene_loader.py:34,41 -- reproduced, not fixed)
+    ok = float((bp == scans[0][1][0]).all(dim=1).float().mean().item())
+    stats["chunks"] = stats["points"] = 0
+    sharding.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for i in range(S):
+        one(i)
+    e1.record(cur)
+    torch.cuda.synchronize(dev)
+    sharding.barrier()
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1))
+    # the chunker alone (device tensors in, device tensors out)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(cur)
+    for i in range(S):
+        ch = csl.chunk_scene(scans[i][1][0])
+        ch.gather(scans[i][1][2])
+    c1.record(cur)
+    torch.cuda.synchronize(dev)
+    out = {"workload": "config 4: whole-scan inference data path, %d synthetic scans per GPU (100-200 k points), chunker + "
+                       "geometry forward over the chunks (B=%d) + map_back" % (S, B),
+           "value": world * S / (ms * 1e-3), "unit": "scans/s", "ms_per_scan": ms / S,
+           "chunks_per_scan": stats["chunks"] / S, "points_per_scan": stats["points"] / S,
+           "chunker_ms_per_scan": c0.elapsed_time(c1) / S, "map_back_restored_fraction": ok}
+    if with_cpu:
+        from oracle import scene_chunks as osc   # test infrastructure, used here only as the timed CPU baseline
+        import time as _t
+        p = scans[0][0]
+        l, f6 = (t.cpu().numpy() for t in scans[0][1][1:])
+        np.random.seed(1)
+        t0 = _t.perf_counter()
+        osc.chunk_scene(p, [l, f6], True)
+        out["cpu_chunker_ms_per_scan"] = 1e3 * (_t.perf_counter() - t0)
+        out["cpu_chunker_kind"] = "port (numpy restatement of complete_scene_loader.py, 1 thread, 1 scan)"
     return out
 
 
@@ -523,6 +613,14 @@ def main():
             for pl in tp:
                 pl.capture(overlap)
 
+    # ---- timed region 4: config 4, whole scans through the GPU chunker + forward + map_back -------------------
+    config4 = None
+    if args.scenes > 0 and args.attention and not args.fuse_layers:
+        try:
+            config4 = run_config4(torch, np, args, pipes, rank, world, dev, sharding, world == 1 and not args.skip_cpu)
+        except Exception as exc:   # reported, never fatal for the headline numbers
+            config4 = {"error": repr(exc)[:300]}
+
     # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
     peaks = {}
     try:
@@ -665,6 +763,7 @@ def main():
         "grid_variants_ms": grid_ms,
         "config3_training_step": train,
         "gathers_steady_state": steady,
+        "config4_whole_scene": config4,
         "attention_layer_tcgen05": fused_layer,
         "cpu_baseline": cpu_baseline,
     }

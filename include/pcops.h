@@ -242,6 +242,8 @@ PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const fl
  *   -> cell_base (ncells+1) i32: list offsets of each cell, [ncells] = total; list (capacity 4n) i32 point indices;
  *      inner (capacity 4n) u8.   workspace: pc_scene_cells_workspace_bytes(n, ncells). */
 PC_API size_t pc_scene_cells_workspace_bytes(int n, int ncells);
+/* coordmin[3], coordmax[3] of a scan (complete_scene_loader.py:21-22) -> out6 (device). */
+PC_API int pc_scene_bbox(int n, const float *points, float *out6, pc_stream_t stream);
 PC_API int pc_scene_cells(int n, int ncells, const float *points, const float *boxes, int *cell_base, int *list,
                    unsigned char *inner, void *workspace, pc_stream_t stream);
 

@@ -9,6 +9,6 @@ if _root not in sys.path:
     sys.path.insert(0, _root)
 _pkg = importlib.import_module("pointcloud-segmentation-attention_b200")
 for _name in ("_lib", "tf_sampling", "tf_grouping", "tf_interpolate", "attention_layer", "pointnet_util", "pipeline", "synth",
-              "sharding"):
+              "sharding", "complete_scene_loader"):
     sys.modules[__name__ + "." + _name] = importlib.import_module("pointcloud-segmentation-attention_b200." + _name)
 sys.modules[__name__] = _pkg

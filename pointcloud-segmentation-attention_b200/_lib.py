@@ -54,6 +54,7 @@ SIGNATURES = {
     "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_scene_cells_workspace_bytes": (_sz, [_i, _i]),
+    "pc_scene_bbox": (_i, [_i, _vp, _vp, _vp]),
     "pc_scene_cells": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_scene_chunk_masksum": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_scene_chunk_assemble": (_i, [_i, _i] + [_vp] * 11),

@@ -223,8 +223,51 @@ winner_kernel(size_t rows, const long long *__restrict__ orig_idx, const unsigne
   }
 }
 
+// coordmin / coordmax of a scan (complete_scene_loader.py:21-22): one CTA, no atomics.  out = min[3], max[3].
+__global__ void __launch_bounds__(1024)
+bbox_kernel(int n, const float *__restrict__ points, float *__restrict__ out) {
+  __shared__ float s_lo[32][3], s_hi[32][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int p = tid; p < n; p += 1024)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = __ldg(points + 3 * (size_t)p + a);
+      lo[a] = fminf(lo[a], v);
+      hi[a] = fmaxf(hi[a], v);
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(PC_FULL_MASK, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(PC_FULL_MASK, hi[a], o));
+    }
+    if (lane == 0) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float l = s_lo[lane][a], h = s_hi[lane][a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        l = fminf(l, __shfl_xor_sync(PC_FULL_MASK, l, o));
+        h = fmaxf(h, __shfl_xor_sync(PC_FULL_MASK, h, o));
+      }
+      if (lane == 0) { out[a] = l; out[3 + a] = h; }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace pc
+
+extern "C" int pc_scene_bbox(int n, const float *points, float *out6, pc_stream_t stream) {
+  if (n <= 0 || !points || !out6) return PC_ERR_INVALID_ARGUMENT;
+  pc::bbox_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, points, out6);
+  PC_RETURN_LAUNCH_STATUS();
+}
 
 static inline int scene_nblk(int n) {
   const int per = pc::kCellThreads * pc::kCellSlabs;

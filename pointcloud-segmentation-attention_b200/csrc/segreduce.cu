@@ -13,12 +13,25 @@
 namespace pc {
 namespace {
 
+// Lanes of `act` holding the same key, as a mask (what __match_any_sync returns).  MATCH.ANY measured at ~135 cycles per
+// warp instruction and serialised per SM on B200 (it was 75 % of csr_build's run time); one ballot per key bit costs a
+// few issue slots and runs on all four schedulers.  nbits = bits needed for nkeys-1.  Lanes outside `act` get garbage.
+__device__ __forceinline__ unsigned same_key_lanes(unsigned act, int key, int nbits) {
+  unsigned peers = act;
+  for (int b = 0; b < nbits; ++b) {
+    const bool bit = (key >> b) & 1;
+    const unsigned bal = __ballot_sync(PC_FULL_MASK, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
 constexpr int kCsrThreads = 1024;
 constexpr size_t kCsrSmemBudget = 200 * 1024;
 
 // One CTA per scene.  Positions are split into W contiguous parts; counters cnt[w][key] live in shared memory.
 __global__ void __launch_bounds__(kCsrThreads, 1)
-csr_build_kernel(int nkeys, int npos, int W, int part, const int *__restrict__ idx, int *__restrict__ ws) {
+csr_build_kernel(int nkeys, int npos, int W, int part, int nbits, const int *__restrict__ idx, int *__restrict__ ws) {
   extern __shared__ int cnt[];  // W * nkeys
   __shared__ int s_carry;
   __shared__ int s_warp[32];
@@ -89,15 +102,17 @@ csr_build_kernel(int nkeys, int npos, int W, int part, const int *__restrict__ i
         const int p = p0 + 32 * u + lane;
         kreg[u] = p < hi ? __ldg(keys + p) : -1;
       }
+      int dst[kPre];
 #pragma unroll
       for (int u = 0; u < kPre; ++u) {
         const int p = p0 + 32 * u + lane;
         const bool valid = p < hi;
         const unsigned act = __ballot_sync(PC_FULL_MASK, valid);
-        if (act == 0) break;
+        dst[u] = -1;
+        if (act == 0) continue;
+        const unsigned peers = same_key_lanes(act, kreg[u], nbits);
         if (valid) {
           const int key = kreg[u];
-          const unsigned peers = __match_any_sync(act, key);
           const int leader = __ffs(peers) - 1;
           int slot = 0;
           if (lane == leader) {
@@ -105,10 +120,15 @@ csr_build_kernel(int nkeys, int npos, int W, int part, const int *__restrict__ i
             c[key] = slot + __popc(peers);
           }
           slot = __shfl_sync(peers, slot, leader);
-          list[slot + __popc(peers & lt)] = p;
+          dst[u] = slot + __popc(peers & lt);
         }
         __syncwarp();  // orders this step's counter stores before the next step's loads
       }
+      // the scattered global stores of the batch go out together, AFTER its warp barriers: a barrier with stores in
+      // flight waits for them (measured ~1.5 us per step when each step stored before its barrier)
+#pragma unroll
+      for (int u = 0; u < kPre; ++u)
+        if (dst[u] >= 0) list[dst[u]] = p0 + 32 * u + lane;
     }
   }
 }
@@ -207,28 +227,39 @@ csr_reduce_vec4_kernel(int nkeys, int npos, int c4, int div, FastDiv fc, FastDiv
     const int i = fits32 ? (int)fc.div((uint32_t)t) : (int)(t / c4), q = (int)(t - (size_t)i * c4);
     const int lo = row_ptr[i], hi = row_ptr[i + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // four contributors' loads in flight at a time; the additions stay strictly in list order
-    constexpr int kU = 4;
-    for (int e = lo; e < hi; e += kU) {
-      int p[kU];
-      float4 g[kU];
-      float wt[kU];
+    // U contributors' row loads in flight at a time, the NEXT batch's list entries fetched under them (a list -> row
+    // chain per batch otherwise doubles the latency); the additions stay strictly in list order.  Rows are uneven --
+    // ball query pads with its first hit, so low-index points collect hundreds of contributions -- and the longest
+    // rows set the kernel's duration: U = 16 for the unweighted (group_point) form, 8 for the weighted (interpolation)
+    // form whose rows are short (~3n/m) and which needs the registers for occupancy instead.
+    constexpr int U = WEIGHTED ? 8 : 16;
+    int pn[U];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) p[u] = (e + u < hi) ? list[e + u] : -1;
+    for (int u = 0; u < U; ++u) pn[u] = (lo + u < hi) ? list[lo + u] : -1;
+    for (int e = lo; e < hi; e += U) {
+      float4 g[U];
+      float wt[U];
+      bool on[U];
+      // loads are unconditional (a batch's missing entries re-read the row of position 0) so that nothing ties a load
+      // to its use: all U are issued before the first addition.  A masked-out term is +0, and acc + (+0) == acc bit for
+      // bit (acc starts at +0 and can never become -0)
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        g[u] = p[u] >= 0 ? __ldg(s + (size_t)fdiv.div((uint32_t)p[u]) * c4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        wt[u] = (WEIGHTED && p[u] >= 0) ? __ldg(ww + p[u]) : 1.0f;
+      for (int u = 0; u < U; ++u) {
+        on[u] = pn[u] >= 0;
+        const int pp = on[u] ? pn[u] : 0;
+        g[u] = __ldg(s + (size_t)fdiv.div((uint32_t)pp) * c4 + q);
+        wt[u] = WEIGHTED ? __ldg(ww + pp) : 1.0f;
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        if (p[u] < 0) break;
+      for (int u = 0; u < U; ++u) pn[u] = (e + U + u < hi) ? list[e + U + u] : -1;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         float4 t = g[u];
         if (WEIGHTED) {
           t.x = __fmul_rn(t.x, wt[u]); t.y = __fmul_rn(t.y, wt[u]); t.z = __fmul_rn(t.z, wt[u]); t.w = __fmul_rn(t.w, wt[u]);
         }
-        acc.x = __fadd_rn(acc.x, t.x); acc.y = __fadd_rn(acc.y, t.y);
-        acc.z = __fadd_rn(acc.z, t.z); acc.w = __fadd_rn(acc.w, t.w);
+        acc.x = __fadd_rn(acc.x, on[u] ? t.x : 0.0f); acc.y = __fadd_rn(acc.y, on[u] ? t.y : 0.0f);
+        acc.z = __fadd_rn(acc.z, on[u] ? t.z : 0.0f); acc.w = __fadd_rn(acc.w, on[u] ? t.w : 0.0f);
       }
     }
     out[((size_t)scene * nkeys + i) * c4 + q] = acc;
@@ -282,7 +313,9 @@ int csr_build(int b, int nkeys, int npos, const int *idx, int *workspace, cudaSt
     if (W < 1) W = 1;
     const size_t smem = (size_t)W * per_part;
     if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(csr_build_kernel, smem));
-    csr_build_kernel<<<b, kCsrThreads, smem, st>>>(nkeys, npos, W, part, idx, workspace);
+    int nbits = 0;
+    while ((1 << nbits) < nkeys) ++nbits;
+    csr_build_kernel<<<b, kCsrThreads, smem, st>>>(nkeys, npos, W, part, nbits, idx, workspace);
   } else {
     csr_build_big_kernel<<<b, 1024, 0, st>>>(nkeys, npos, idx, workspace);
   }

@@ -14,6 +14,10 @@ Sources of truth
   attention.npz    a literal numpy transcription of AttentionLayer.call (attention_layer.py:29-45: Dense, reshape,
                    matmul, softmax, matmul) in float64 -- TensorFlow itself is not installed, so this one is a
                    restatement, not reference output ("parity unpinned" for attention)
+  scene_chunks.npz the reference's own complete_scene_loader.py (pure numpy, imported from /root/reference) and
+                   generate_predictions.map_back (function body executed from its source, the module imports TF) on seeded
+                   synthetic scans (synth.whole_scene) under np.random.seed: masks, original indices and sha256 digests of
+                   every returned array
 Shapes follow the reference smoke scripts (np.random.seed(100); tf_grouping.py:79-83, tf_interpolate.py:39-42).
 """
 import os
@@ -104,6 +108,40 @@ def attention():
                         heads=heads, key_dim=kd)
 
 
+def scene_chunks():
+    from tests.scene_cases import scene_chunk_cases, sha as _sha
+    sys.path.insert(0, "/root/reference")
+    from attention_points.scannet_dataset import complete_scene_loader as R
+    # map_back lives in a module that imports tensorflow at the top: execute just that function's source
+    import ast
+    src = open("/root/reference/attention_points/benchmark/generate_predictions.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "map_back"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "generate_predictions.py", "exec"), ns)
+    out = {}
+    for name, seed, p, l, c, n in scene_chunk_cases():
+        np.random.seed(seed)
+        if l is None:
+            res = R.get_all_subsets_with_all_points_for_scene_numpy_test(p, c, n)
+            names = ("points", "colors", "normals", "masks", "orig")
+        else:
+            res = R.get_all_subsets_with_all_points_for_scene_numpy(p, l, c, n)
+            names = ("points", "labels", "colors", "normals", "weights", "masks", "orig")
+        d = dict(zip(names, res))
+        out[name + "_masks"] = np.packbits(d["masks"])
+        out[name + "_orig"] = d["orig"].astype(np.int32)
+        out[name + "_nchunks"] = np.int32(d["masks"].shape[0])
+        for k, v in d.items():
+            out[name + "_sha_" + k] = np.array(_sha(v))
+        # map_back of a per-row value (the row's own original index + 1, so unwritten points stay 0) and of the coordinates
+        vals = (d["orig"].reshape(-1) + 1).astype(np.int64)
+        mb = ns["map_back"](vals, d["orig"].reshape(-1), d["masks"].reshape(-1), (len(p),))
+        mp = ns["map_back"](d["points"].reshape(-1, 3), d["orig"].reshape(-1), d["masks"].reshape(-1), (len(p), 3))
+        out[name + "_sha_mapback"] = np.array(_sha(mb))
+        out[name + "_sha_mapback_points"] = np.array(_sha(mp))
+    np.savez_compressed(os.path.join(OUT, "scene_chunks.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref.available_cpu():
         sys.exit("oracle/_ref is not built: run `make -C oracle` where /root/reference is mounted")
@@ -112,5 +150,6 @@ if __name__ == "__main__":
     selsort()
     interpolate()
     attention()
+    scene_chunks()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

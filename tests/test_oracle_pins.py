@@ -288,3 +288,36 @@ def test_prob_sample_oracle_against_python_emulation_of_the_kernel():
         q = (r[i] * cdf[i, -1]).astype(np.float32)
         want = np.searchsorted(cdf[i], q, side="left")      # smallest index with cdf >= q (cdf is non-decreasing)
         assert np.array_equal(got[i], np.minimum(want, 776))
+
+
+# ---- whole-scene chunker: the restatement against the reference's own complete_scene_loader.py ------------------
+def test_scene_chunker_matches_reference_golden(golden):
+    from oracle import scene_chunks as sc
+    from tests.scene_cases import scene_chunk_cases, sha
+    g = golden("scene_chunks")
+    for name, seed, p, l, c, n in scene_chunk_cases():
+        np.random.seed(seed)
+        if l is None:
+            res = dict(zip(("points", "colors", "normals", "masks", "orig"),
+                           sc.get_all_subsets_with_all_points_for_scene_numpy_test(p, c, n)))
+        else:
+            res = dict(zip(("points", "labels", "colors", "normals", "weights", "masks", "orig"),
+                           sc.get_all_subsets_with_all_points_for_scene_numpy(p, l, c, n)))
+        assert res["masks"].shape[0] == int(g[name + "_nchunks"])
+        assert np.array_equal(np.packbits(res["masks"]), g[name + "_masks"])
+        assert np.array_equal(res["orig"], g[name + "_orig"])
+        for k, v in res.items():
+            assert sha(v) == str(g[name + "_sha_" + k]), (name, k)
+        flat_o, flat_m = res["orig"].reshape(-1), res["masks"].reshape(-1)
+        assert sha(sc.map_back((flat_o + 1).astype(np.int64), flat_o, flat_m, (len(p),))) == str(g[name + "_sha_mapback"])
+        assert sha(sc.map_back(res["points"].reshape(-1, 3), flat_o, flat_m, (len(p), 3))) == str(g[name + "_sha_mapback_points"])
+
+
+def test_scene_chunker_rejects_what_the_reference_rejects():
+    """A cell holding an exact multiple of 8192 points makes the reference concatenate an empty list with a 2-D array
+    (complete_scene_loader.py:89-90): ValueError."""
+    from oracle import scene_chunks as sc
+    rng = np.random.Generator(np.random.PCG64(3))
+    p = (rng.random((8192, 3)) * 1.4).astype(np.float32)
+    with pytest.raises(ValueError):
+        sc.chunk_scene(p, [np.zeros(8192, np.int32)], True)

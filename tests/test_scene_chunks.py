@@ -1,0 +1,132 @@
+"""Whole-scene chunker (config 4; reference complete_scene_loader.py:4-117, generate_predictions.py:19-37).
+
+CPU part: the HOST half of the product path (fp32 threshold rounding, numpy RNG planning, chunk descriptors) against
+the golden fixtures produced by the reference itself, with the kernels' contracts emulated in numpy inside this test.
+GPU part: the real path through libpcops.so against the oracle and the same fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scene_chunks as oracle_sc
+from pcops_b200 import complete_scene_loader as csl
+from tests.scene_cases import scene_chunk_cases, sha
+
+
+def _emulated_kernels(points, npoints=8192):
+    """What pc_scene_cells / pc_scene_chunk_masksum / pc_scene_chunk_assemble compute, in numpy (test-only)."""
+    boxes = csl._cell_boxes(np.min(points, axis=0), np.max(points, axis=0))
+    lists, inners, base = [], [], [0]
+    for b in boxes:
+        hit = np.all((points >= b[0:3]) & (points <= b[3:6]), axis=1)            # float32 compares, as the kernel does
+        sel = np.nonzero(hit)[0]
+        lists.append(sel)
+        inners.append(np.all((points[sel] >= b[6:9]) & (points[sel] <= b[9:12]), axis=1))
+        base.append(base[-1] + len(sel))
+    cell_list, inner = np.concatenate(lists), np.concatenate(inners)
+    desc, order, fill = csl._plan_chunks(np.asarray(base), npoints)
+    src, mask, orig = [], [], []
+    for lb, oo, start, rest, fo in desc:
+        t = np.arange(npoints)
+        pos = np.where(t < rest, order[oo + np.minimum(start + t, len(order) - 1 - oo)], 0)
+        fpos = order[oo + fill[fo + np.maximum(t - rest, 0) % max(1, npoints - rest)]] if rest < npoints else pos
+        pos = np.where(t < rest, pos, fpos)
+        m = np.where(t < rest, inner[lb + pos], False)
+        if m.sum() == 0:
+            continue
+        src.append(cell_list[lb + pos])
+        mask.append(m)
+        orig.append(np.where(t < rest, cell_list[lb + pos], 0))
+    return np.stack(src), np.stack(mask), np.stack(orig).astype(np.int64)
+
+
+def test_fp32_thresholds_equal_the_float64_compares():
+    for name, seed, p, l, c, n in scene_chunk_cases()[:2]:
+        boxes = csl._cell_boxes(np.min(p, axis=0), np.max(p, axis=0))
+        cells = oracle_sc.cell_bounds(p)
+        assert len(cells) == len(boxes)
+        for b, (curmin, curmax) in zip(boxes, cells):
+            want = np.sum((p >= (curmin - 0.2)) * (p <= (curmax + 0.2)), axis=1) == 3
+            assert np.array_equal(np.all((p >= b[0:3]) & (p <= b[3:6]), axis=1), want)
+            want = np.sum((p >= curmin) * (p <= curmax), axis=1) == 3
+            assert np.array_equal(np.all((p >= b[6:9]) & (p <= b[9:12]), axis=1), want)
+    # thresholds that are not representable in fp32, hit exactly from both sides
+    t = np.array([0.1, -0.3, 1.7000000001])
+    up, down = csl._round_up_f32(t), csl._round_down_f32(t)
+    assert (up.astype(np.float64) >= t).all() and (np.nextafter(up, np.float32(-np.inf)).astype(np.float64) < t).all()
+    assert (down.astype(np.float64) <= t).all() and (np.nextafter(down, np.float32(np.inf)).astype(np.float64) > t).all()
+
+
+def test_host_plan_reproduces_the_reference_rng_stream(golden):
+    g = golden("scene_chunks")
+    for name, seed, p, l, c, n in scene_chunk_cases():
+        np.random.seed(seed)
+        src, mask, orig = _emulated_kernels(p)
+        assert np.array_equal(np.packbits(mask), g[name + "_masks"]), name
+        assert np.array_equal(orig, g[name + "_orig"]), name
+        assert sha(p[src]) == str(g[name + "_sha_points"]), name
+        assert sha(c[src]) == str(g[name + "_sha_colors"]), name
+
+
+def test_host_plan_rejects_a_multiple_of_npoints():
+    with pytest.raises(ValueError):
+        csl._plan_chunks(np.array([0, 8192]))
+    with pytest.raises(ValueError):
+        csl._plan_chunks(np.array([0, 0, 0]))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_chunker_matches_reference_golden_numpy_in_numpy_out(golden):
+    g = golden("scene_chunks")
+    for name, seed, p, l, c, n in scene_chunk_cases():
+        np.random.seed(seed)
+        if l is None:
+            res = dict(zip(("points", "colors", "normals", "masks", "orig"),
+                           csl.get_all_subsets_with_all_points_for_scene_numpy_test(p, c, n)))
+        else:
+            res = dict(zip(("points", "labels", "colors", "normals", "weights", "masks", "orig"),
+                           csl.get_all_subsets_with_all_points_for_scene_numpy(p, l, c, n)))
+        assert res["masks"].dtype == np.bool_ and res["orig"].dtype == np.int64
+        assert np.array_equal(np.packbits(res["masks"]), g[name + "_masks"]), name
+        assert np.array_equal(res["orig"], g[name + "_orig"]), name
+        for k, v in res.items():
+            assert sha(v) == str(g[name + "_sha_" + k]), (name, k)
+        flat_o, flat_m = res["orig"].reshape(-1), res["masks"].reshape(-1)
+        mb = csl.map_back((flat_o + 1).astype(np.int64), flat_o, flat_m, (len(p),))
+        assert sha(mb) == str(g[name + "_sha_mapback"]), name
+        mp = csl.map_back(res["points"].reshape(-1, 3), flat_o, flat_m, (len(p), 3))
+        assert sha(mp) == str(g[name + "_sha_mapback_points"]), name
+
+
+@pytest.mark.gpu
+def test_chunker_matches_oracle_on_a_full_size_scan_device_tensors():
+    from oracle import synth
+    p, l, c, n = synth.whole_scene(11)            # 100-200 k points
+    np.random.seed(123)
+    want = oracle_sc.get_all_subsets_with_all_points_for_scene_numpy(p, l, c, n)
+    np.random.seed(123)
+    dev = torch.device("cuda")
+    got = csl.get_all_subsets_with_all_points_for_scene_numpy(*(torch.from_numpy(a).to(dev) for a in (p, l, c, n)))
+    assert all(isinstance(t, torch.Tensor) and t.is_cuda for t in got)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    # every point of the scan is predicted exactly once after map_back (masks select the un-padded cells)
+    orig, masks = got[6].reshape(-1), got[5].reshape(-1)
+    back = csl.map_back(got[0].reshape(-1, 3), orig, masks, (len(p), 3))
+    assert torch.equal(back.cpu(), torch.from_numpy(p))
+    # duplicates: the LAST masked occurrence wins, as in numpy fancy assignment
+    vals = torch.arange(6, dtype=torch.float32, device=dev)
+    o = torch.tensor([2, 0, 2, 1, 2, 0], device=dev)
+    m = torch.tensor([1, 1, 1, 1, 0, 1], dtype=torch.bool, device=dev)
+    want = oracle_sc.map_back(vals.cpu().numpy(), o.cpu().numpy(), m.cpu().numpy(), (4,))
+    assert np.array_equal(csl.map_back(vals, o, m, (4,)).cpu().numpy(), want.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_chunker_has_no_cpu_path_and_rejects_bad_input():
+    with pytest.raises(TypeError):
+        csl.chunk_scene(np.zeros((10, 3), np.float64))
+    rng = np.random.Generator(np.random.PCG64(3))
+    p = (rng.random((8192, 3)) * 1.4).astype(np.float32)
+    with pytest.raises(ValueError):                       # the reference raises here too (:89-90)
+        csl.chunk_scene(p)
