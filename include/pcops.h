@@ -219,7 +219,8 @@ PC_API int pc_attention_fwd(int G, int S, int H, int D, const float *Q, const fl
  * never written to memory.
  *   xq (G,C) query rows, x (G,S,C) grouped rows, wq/wk/wv (C,C) Dense kernels laid out [in][out], bq/bk/bv (C) or NULL
  *   -> out (G,C), within 1e-5 relative of the fp32 composition.
- * Supported in this build: S = 32, C = 64 (the SA1 attention level); otherwise PC_ERR_UNSUPPORTED (use a Dense GEMM +
+ * Supported in this build: S = 32, C in {64, 128, 256, 512} (the four ScanNet attention levels; for C >= 128 both
+ * operands stream through a shared-memory ring, W from a pre-split image); otherwise PC_ERR_UNSUPPORTED (use a Dense GEMM +
  * pc_attention_fwd).  workspace: pc_attention_layer_workspace_bytes(G,S,C) bytes, 16-byte aligned. */
 PC_API size_t pc_attention_layer_workspace_bytes(int G, int S, int C);
 PC_API int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq, const float *bq,

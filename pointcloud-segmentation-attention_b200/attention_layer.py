@@ -56,7 +56,8 @@ def attention_contract(Q, K, V, num_heads, key_dim):
 def attention_layer_fused(xq, x, wq, bq, wk, bk, wv, bv):
     """The whole AttentionLayer.call (attention_layer.py:29-45) in one tcgen05 kernel (csrc/attention_layer.cu):
     xq (G,C) query rows, x (G,S,C) grouped rows, Dense kernels w* as (C_in, C_out) like Keras, biases (C) or None
-    -> (G, C).  Forward only; supported for S = 32, C = 64 (key_dim = output_dim = 4), else NotImplementedError."""
+    -> (G, C).  Forward only; supported for S = 32, C in {64, 128, 256, 512} (key_dim = output_dim = 4), else
+    NotImplementedError."""
     x = _lib.cuda_f32(x.detach(), "x")
     xq = _lib.cuda_f32(xq.detach(), "xq")
     G, S, C = x.shape
@@ -99,15 +100,17 @@ class AttentionLayer(torch.nn.Module):
             self._build(inp.shape[-1])
             self.to(inp.device)
         hd = self.key_dim * self.num_heads
-        if (FUSED_LAYER and not torch.is_grad_enabled() and inp.shape[-1] == 64 and hd == 64 and inp.shape[-2] == 32
+        C = inp.shape[-1]
+        if (FUSED_LAYER and not torch.is_grad_enabled() and C in (64, 128, 256, 512) and hd == C and inp.shape[-2] == 32
                 and self.key_dim == 4):
-            # inference at the SA1 width: projections + contraction in one tensor-core kernel, K and V never stored
+            # inference at the four ScanNet attention widths: projections + contraction in one tensor-core kernel,
+            # K and V never stored
             lead = inp.shape[:-2]
-            out = attention_layer_fused(query.reshape(-1, 64), inp.reshape(-1, 32, 64),
+            out = attention_layer_fused(query.reshape(-1, C), inp.reshape(-1, 32, C),
                                         self.query_net.weight.t().contiguous(), self.query_net.bias,
                                         self.key_net.weight.t().contiguous(), self.key_net.bias,
                                         self.value_net.weight.t().contiguous(), self.value_net.bias)
-            return out.reshape(*lead, 64)
+            return out.reshape(*lead, C)
         Q = self.query_net(query)          # (B,np,1,HD)
         K = self.key_net(inp)              # (B,np,S,HD)
         V = self.value_net(inp)

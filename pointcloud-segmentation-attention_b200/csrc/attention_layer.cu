@@ -319,10 +319,18 @@ attention_layer_c64_kernel(int G, const float *__restrict__ qg, const float *__r
 }
 
 }  // namespace
+
+// attention_layer_wide.cu: C = 128 / 256 / 512
+size_t attention_layer_wide_image_bytes(int C);
+bool attention_layer_wide_supported(int S, int C);
+int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
+                             const float *wk, const float *bk, const float *wv, const float *bv, float *out,
+                             void *workspace, cudaStream_t st);
 }  // namespace pc
 
 extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
-  (void)G;
+  if (G > 0 && pc::attention_layer_wide_supported(S, C))
+    return pc::attention_layer_wide_image_bytes(C) + (size_t)G * C * sizeof(float);  // operand image | Q scratch
   if (S != pc::kS || C != pc::kC || G <= 0) return 0;
   return (size_t)((pc::kImageBytes + 255) / 256) * 256 + (size_t)G * pc::kC * sizeof(float);  // operand image | Q scratch
 }
@@ -331,7 +339,14 @@ extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, cons
                                       const float *bq, const float *wk, const float *bk, const float *wv,
                                       const float *bv, float *out, void *workspace, pc_stream_t stream) {
   if (G < 0 || S <= 0 || C <= 0) return PC_ERR_INVALID_ARGUMENT;
-  if (S != pc::kS || C != pc::kC) return PC_ERR_UNSUPPORTED;  // other widths: Dense + pc_attention_fwd
+  if (pc::attention_layer_wide_supported(S, C)) {
+    if (G == 0) return PC_OK;
+    if (!xq || !x || !wq || !wk || !wv || !out) return PC_ERR_INVALID_ARGUMENT;
+    if (!workspace) return PC_ERR_WORKSPACE;
+    if (!pc::aligned16(x) || !pc::aligned16(out) || !pc::aligned16(workspace)) return PC_ERR_UNSUPPORTED;
+    return pc::attention_layer_wide_fwd(G, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, (cudaStream_t)stream);
+  }
+  if (S != pc::kS || C != pc::kC) return PC_ERR_UNSUPPORTED;  // other shapes: Dense + pc_attention_fwd
   if (G == 0) return PC_OK;
   if (!xq || !x || !wq || !wk || !wv || !out) return PC_ERR_INVALID_ARGUMENT;
   if (!workspace) return PC_ERR_WORKSPACE;

@@ -1,0 +1,355 @@
+// AttentionLayer.call for the wide attention levels (C = 128, 256, 512; SA2-SA4) on the tcgen05 tensor cores.
+//
+// Reference: attention_points/attention_scannet/attention_layer.py:29-45 with output_dim = key_dim = 4, heads = C/4
+// (:255-261).  Same mathematics as attention_layer.cu (C = 64), different schedule: W_k | W_v no longer fits shared
+// memory (C x 2C fp32, split into TF32 hi / lo: 256 KB .. 4 MB), so both operands stream through a two-stage ring.
+//
+// The reference's RAW reshape (:35) views a neighbourhood's (32, C) K buffer as (C/4 heads, 32, 4): head h is the 128
+// consecutive floats starting at flat offset 128 h, i.e. columns [128 j, 128 j + 128) of row r with h = r * (C/128) + j.
+// A work item is therefore (tile of 128 rows = 4 neighbourhoods, column chunk j): accumulator D[128 x 256] =
+// X[128 x C] . [W_k[:, 128j..] | W_v[:, 128j..]] and a thread that owns accumulator row r has one whole head in
+// registers: its 32 pseudo-keys (K part) and 32 pseudo-values (V part).  Softmax and the weighted sum need no shuffles.
+//
+//   warps 0-3  producers: per K block of 32 columns, X rows global -> registers -> TF32 hi / lo -> swizzled A stage;
+//              one thread starts the bulk copy (cp.async.bulk, mbarrier complete_tx) of the pre-split, pre-swizzled
+//              B block (64 KB) of the weight image
+//   warp  8    one thread issues 12 tcgen05.mma (M128 N256 K8, kind::tf32) per K block: X_hi W_hi + X_hi W_lo + X_lo W_hi;
+//              tcgen05.commit frees the stage / publishes the accumulator
+//   warps 4-7  epilogue: tcgen05.ld of the row's K chunk, logits against Q (from the front kernel), softmax, V chunk,
+//              weighted sum, 16-byte store of the head's 4 outputs
+// Two TMEM accumulators (2 x 256 columns) let the tensor cores start the next item while the epilogue reads this one.
+#include <math.h>
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int kS = 32;
+constexpr int kRows = 128;                 // M: rows per tile = 4 neighbourhoods
+constexpr int kNc = 256;                   // N per item: 128 K columns | 128 V columns
+constexpr int kKB = 32;                    // tf32 elements per K block (one 128-byte swizzled row)
+constexpr int kSBO = 1024;                 // bytes between 8-row groups
+constexpr int kABlock = kRows * 128;       // 16 KB: A K-block (hi or lo)
+constexpr int kBBlock = kNc * 128;         // 32 KB: B K-block (hi or lo)
+constexpr int kStage = 2 * kABlock + 2 * kBBlock;   // 96 KB: A_hi | A_lo | B_hi | B_lo
+constexpr int kThreads = 288;
+constexpr int kMaxC = 512;
+
+__host__ __device__ inline int block_offset(int row, int k) {  // byte offset of (row, k) inside one K block, k < 32
+  return (row >> 3) * kSBO + (row & 7) * 128 + (((k >> 2) ^ (row & 7)) << 4) + (k & 3) * 4;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Weight image: for chunk j and K block kb, [B_hi 32 KB | B_lo 32 KB] exactly as the kernel wants it in shared memory.
+// Row n < 128 of a block is K column 128 j + n (Dense kernel W_k[k][col], [in][out]); row n >= 128 is V column 128 j + n - 128.
+__global__ void wide_prep_kernel(int C, const float *__restrict__ wk, const float *__restrict__ wv,
+                                 unsigned char *__restrict__ image) {
+  const int nkb = C / kKB;
+  const size_t total = (size_t)(C / 128) * nkb * kNc * kKB;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int kl = (int)(t % kKB);
+    const int n = (int)((t / kKB) % kNc);
+    const int kb = (int)((t / ((size_t)kKB * kNc)) % nkb);
+    const int j = (int)(t / ((size_t)kKB * kNc * nkb));
+    const int k = kb * kKB + kl;
+    const float w = (n < 128) ? wk[(size_t)k * C + 128 * j + n] : wv[(size_t)k * C + 128 * j + (n - 128)];
+    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    unsigned char *blk = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
+    *reinterpret_cast<float *>(blk + block_offset(n, kl)) = hi;
+    *reinterpret_cast<float *>(blk + kBBlock + block_offset(n, kl)) = lo;
+  }
+}
+
+// Q = xq Wq + bq: G x C outputs, C MACs each (1/64 of the layer's work), k ascending with fmaf from the bias.
+__global__ void __launch_bounds__(256)
+wide_q_kernel(int G, int C, const float *__restrict__ xq, const float *__restrict__ wq, const float *__restrict__ bq,
+              float *__restrict__ q) {
+  __shared__ float s_x[8][kMaxC];
+  for (int g0 = blockIdx.x * 8; g0 < G; g0 += gridDim.x * 8) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * C; i += 256) {
+      const int r = i / C, k = i - r * C;
+      s_x[r][k] = (g0 + r < G) ? __ldg(xq + (size_t)(g0 + r) * C + k) : 0.f;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < C; n += 256) {
+      float acc[8];
+      const float b = bq ? __ldg(bq + n) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = b;
+      for (int k = 0; k < C; ++k) {
+        const float w = __ldg(wq + (size_t)k * C + n);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(s_x[r][k], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (g0 + r < G) q[(size_t)(g0 + r) * C + n] = acc[r];
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B, SBO = 1024 (see attention_layer.cu)
+  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (1u << 16);
+  const uint32_t hi = (uint32_t)(kSBO >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+#define PCW_TMEM_LD16(addr, v, o)                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),         \
+                 "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),      \
+                 "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                     \
+               : "r"(addr))
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost arrival
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_layer_wide_kernel(int G, int C, const float *__restrict__ qg, const float *__restrict__ x,
+                            const unsigned char *__restrict__ image, const float *__restrict__ bk,
+                            const float *__restrict__ bv, float *__restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stage_buf = smem;                                          // [2][A_hi | A_lo | B_hi | B_lo]
+  float *s_bk = reinterpret_cast<float *>(smem + 2 * kStage), *s_bv = s_bk + kMaxC;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_bv + kMaxC);             // full[2], empty[2], t_full[2], t_empty[2]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+  const uint32_t full[2] = {bar0, bar0 + 8}, empty[2] = {bar0 + 16, bar0 + 24};
+  const uint32_t t_full[2] = {bar0 + 32, bar0 + 40}, t_empty[2] = {bar0 + 48, bar0 + 56};
+
+  if (warp == 8) {  // the whole TMEM: two 256-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(128u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty[s]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full[s]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty[s]), "r"(128u));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  for (int i = tid; i < C; i += kThreads) {
+    s_bk[i] = bk ? __ldg(bk + i) : 0.f;
+    s_bv[i] = bv ? __ldg(bv + i) : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+
+  const int nkb = C / kKB, nchunk = C / 128;
+  const size_t total_rows = (size_t)G * kS;
+  const int ntiles = (int)((total_rows + kRows - 1) / kRows);
+  const int nitems = ntiles * nchunk;                 // item = tile * nchunk + j: a tile's chunks run on neighbouring CTAs
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage_buf);
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producers
+    float4 pre[8];
+    auto fetch = [&](int item, int kb) {   // X[tile rows, 32 kb .. +31]: thread t takes float4 t + 128 i -> row (i4>>3), quad i4&7
+      const int tile = item / nchunk;
+      const size_t row0 = (size_t)tile * kRows;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+        pre[i] = (item < nitems && row0 + row < total_rows)
+                     ? __ldg(reinterpret_cast<const float4 *>(x + (row0 + row) * C + kb * kKB) + kq)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int it = 0;
+    int item = blockIdx.x;
+    if (item < nitems) fetch(item, 0);
+    for (; item < nitems; item += gridDim.x) {
+      const int j = item % nchunk;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it & 1;
+        mbar_wait(empty[s], ((it >> 1) & 1) ^ 1);       // the MMAs that read this stage two blocks ago have completed
+        unsigned char *st = stage_buf + s * kStage;
+        if (tid == 0) {  // B block: 64 KB, already hi | lo and swizzled in the image
+          const unsigned char *src = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
+          const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
+          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"((uint32_t)(2 * kBBlock))
+                       : "memory");
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst + c * (kBBlock / 2)),
+                         "l"(src + c * (kBBlock / 2)), "r"((uint32_t)(kBBlock / 2)), "r"(full[s])
+                         : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+          const float4 v = pre[i];
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          const int off = block_offset(row, kq * 4);
+          *reinterpret_cast<float4 *>(st + off) = h;
+          *reinterpret_cast<float4 *>(st + kABlock + off) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
+        // next block's X rows in flight while this one is consumed
+        if (kb + 1 < nkb) fetch(item, kb + 1);
+        else fetch(item + gridDim.x, 0);
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kNc >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+      int it = 0, w = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
+        const int a = w & 1;
+        mbar_wait(t_empty[a], ((w >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it & 1;
+          mbar_wait(full[s], (it >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = stage_s + s * kStage, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + kBBlock;
+#pragma unroll
+          for (int split = 0; split < 3; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi
+            const uint32_t as = (split == 2) ? a_lo : a_hi, bs = (split == 1) ? b_lo : b_hi;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              mma_tf32(tmem + a * kNc, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
+              acc = 1;
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty[s]) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_full[a]) : "memory");
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (warps 4-7: TMEM lane quarters 0-3)
+    const int r = (warp & 3) * 32 + lane;               // accumulator row = tile row
+    const int gl = r >> 5, srow = r & 31;
+    int w = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
+      const int a = w & 1, tile = item / nchunk, j = item - tile * nchunk;
+      const int head = srow * nchunk + j;
+      const size_t g = (size_t)tile * 4 + gl;
+      const float4 q4 = (g < (size_t)G) ? __ldg(reinterpret_cast<const float4 *>(qg + g * C + head * 4))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float *cbk = s_bk + 128 * j, *cbv = s_bv + 128 * j;
+      mbar_wait(t_full[a], (w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + a * kNc;
+      float p[32];
+      float mx = -INFINITY;
+      uint32_t kv[64];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {            // K chunk: 128 columns = 32 pseudo-keys of this head
+        PCW_TMEM_LD16(taddr + 64 * half + 0, kv, 0);
+        PCW_TMEM_LD16(taddr + 64 * half + 16, kv, 16);
+        PCW_TMEM_LD16(taddr + 64 * half + 32, kv, 32);
+        PCW_TMEM_LD16(taddr + 64 * half + 48, kv, 48);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const int c = 64 * half + 4 * t;
+          const float k0 = __uint_as_float(kv[4 * t + 0]) + cbk[c + 0], k1 = __uint_as_float(kv[4 * t + 1]) + cbk[c + 1],
+                      k2 = __uint_as_float(kv[4 * t + 2]) + cbk[c + 2], k3 = __uint_as_float(kv[4 * t + 3]) + cbk[c + 3];
+          const float lg = 0.5f * fmaf(q4.w, k3, fmaf(q4.z, k2, fmaf(q4.y, k1, q4.x * k0)));  // / sqrt(key_dim = 4)
+          p[16 * half + t] = lg;
+          mx = fmaxf(mx, lg);
+        }
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) { p[t] = exp2f((p[t] - mx) * 1.4426950408889634f); sum += p[t]; }
+      const float inv = 1.0f / sum;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {            // V chunk
+        PCW_TMEM_LD16(taddr + 128 + 64 * half + 0, kv, 0);
+        PCW_TMEM_LD16(taddr + 128 + 64 * half + 16, kv, 16);
+        PCW_TMEM_LD16(taddr + 128 + 64 * half + 32, kv, 32);
+        PCW_TMEM_LD16(taddr + 128 + 64 * half + 48, kv, 48);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const int c = 64 * half + 4 * t;
+          const float wgt = p[16 * half + t] * inv;
+          o0 = fmaf(wgt, __uint_as_float(kv[4 * t + 0]) + cbv[c + 0], o0);
+          o1 = fmaf(wgt, __uint_as_float(kv[4 * t + 1]) + cbv[c + 1], o1);
+          o2 = fmaf(wgt, __uint_as_float(kv[4 * t + 2]) + cbv[c + 2], o2);
+          o3 = fmaf(wgt, __uint_as_float(kv[4 * t + 3]) + cbv[c + 3], o3);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the accumulator is handed back
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty[a]) : "memory");
+      if (g < (size_t)G) *reinterpret_cast<float4 *>(out + g * C + head * 4) = make_float4(o0, o1, o2, o3);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+}  // namespace
+
+size_t attention_layer_wide_image_bytes(int C) { return (size_t)(C / 128) * (C / kKB) * (2 * kBBlock); }
+
+bool attention_layer_wide_supported(int S, int C) { return S == kS && (C == 128 || C == 256 || C == 512); }
+
+int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
+                             const float *wk, const float *bk, const float *wv, const float *bv, float *out,
+                             void *workspace, cudaStream_t st) {
+  unsigned char *image = (unsigned char *)workspace;
+  const size_t img = attention_layer_wide_image_bytes(C);
+  float *qbuf = reinterpret_cast<float *>(image + img);
+  const size_t elems = img / 8;
+  wide_prep_kernel<<<(unsigned)((elems + 255) / 256 < 4096 ? (elems + 255) / 256 : 4096), 256, 0, st>>>(C, wk, wv, image);
+  const int qb = (G + 7) / 8 < num_sms() * 4 ? (G + 7) / 8 : num_sms() * 4;
+  wide_q_kernel<<<qb, 256, 0, st>>>(G, C, xq, wq, bq, qbuf);
+  const size_t smem = 2 * (size_t)kStage + 2 * kMaxC * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+  PC_CUDA_TRY(allow_smem(attention_layer_wide_kernel, smem));
+  const int ntiles = (int)(((size_t)G * kS + kRows - 1) / kRows);
+  const int nitems = ntiles * (C / 128);
+  const int grid = nitems < num_sms() ? nitems : num_sms();
+  attention_layer_wide_kernel<<<grid, kThreads, smem, st>>>(G, C, qbuf, x, image, bk, bv, out);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace pc

@@ -534,20 +534,30 @@ def test_fused_fp_interpolate_equals_composition_and_oracle(c2, c1):
 
 
 # -------------------------------------------------------------------- fused attention layer on tcgen05
-@pytest.mark.parametrize("G", [4, 7, 256, 1000])
-def test_attention_layer_fused_matches_oracle(G):
+@pytest.mark.parametrize("G,C", [(4, 64), (7, 64), (256, 64), (1000, 64),
+                                 (4, 128), (7, 128), (600, 128), (5, 256), (300, 256), (3, 512), (150, 512)])
+def test_attention_layer_fused_matches_oracle(G, C):
+    """C = 64: attention_layer.cu (W resident); C = 128 / 256 / 512: attention_layer_wide.cu (both operands streamed).
+    G not a multiple of 4 exercises the partial last tile; more items than SMs the persistent loop and stage reuse."""
     from pcops_b200.attention_layer import attention_layer_fused
-    rng = np.random.default_rng(G)
-    C, S = 64, 32
+    rng = np.random.default_rng(G + C)
+    S = 32
     x = rng.standard_normal((G, S, C), dtype=np.float32)
     xq = x[:, 0, :].copy()
-    W = [(rng.standard_normal((C, C), dtype=np.float32) / 8.0) for _ in range(3)]
+    W = [(rng.standard_normal((C, C), dtype=np.float32) / np.float32(np.sqrt(C))) for _ in range(3)]
     bias = [rng.standard_normal(C, dtype=np.float32) * 0.1 for _ in range(3)]
     want = cpu.attention_layer(x, xq, W[0], bias[0], W[1], bias[1], W[2], bias[2], C // 4, 4)
     got = attention_layer_fused(cu(xq), cu(x), cu(W[0]), cu(bias[0]), cu(W[1]), cu(bias[1]), cu(W[2]), cu(bias[2]))
-    np.testing.assert_allclose(npy(got), want, rtol=1e-5, atol=2e-6)
+    if C == 64:
+        np.testing.assert_allclose(npy(got), want, rtol=1e-5, atol=2e-6)
+    else:
+        # tolerance: 1e-5 relative to the output scale (max-norm), against the float64-accumulated oracle.  The 3xTF32
+        # products carry 22 mantissa bits and the tensor core accumulates K = C terms in fp32; measured 2e-6 (C = 128),
+        # 3e-6 (256), 7e-6 (512) of max|out|.  Entries near zero are not held to an elementwise relative bound.
+        err = np.abs(npy(got) - want).max() / np.abs(want).max()
+        assert err <= 1e-5, err
     # and the module: fused inference path == Dense + contraction path
-    layer = ops.AttentionLayer(4, 4, num_heads=16, in_features=C).to(DEV)
+    layer = ops.AttentionLayer(4, 4, num_heads=C // 4, in_features=C).to(DEV)
     xt = cu(x).reshape(1, G, S, C)
     with torch.no_grad():
         a = layer([xt, xt[:, :, 0:1, :]])
@@ -557,4 +567,4 @@ def test_attention_layer_fused_matches_oracle(G):
         b = layer([xt.requires_grad_(True), xt[:, :, 0:1, :]])     # grad enabled -> composition
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    np.testing.assert_allclose(npy(a), npy(b), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(npy(a), npy(b), rtol=2e-5, atol=2e-5)   # fp32 cuBLAS composition vs fused
