@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-overlap", action="store_true", help="single stream")
     ap.add_argument("--cpu-scenes", type=int, default=0, help="scenes in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--attention-layers", type=int, default=1,
+                    help="1: also time the forward with the whole AttentionLayer (Dense Q/K/V + contraction on tcgen05) per level")
     ap.add_argument("--scenes", type=int, default=6, help="whole scans per GPU in the config-4 region (0: skip)")
     ap.add_argument("--train", type=int, default=1, help="1: also time config 3 (forward + the registered gradients)")
     ap.add_argument("--train-depth", type=int, default=4, help="batches in flight for the config-3 region")
@@ -199,22 +201,15 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def time_fused_attention_layer(torch, ops, G):
+def time_fused_attention_layer(torch, ops, B):
+    """The fused AttentionLayer (Dense Q/K/V + contraction on tcgen05: csrc/attention_layer.cu for C = 64,
+    csrc/attention_layer_wide.cu for C = 128 / 256 / 512) at the four ScanNet attention levels of a B-scene batch, next to
+    the composition it replaces (three fp32 cuBLAS GEMMs + pc_attention_fwd); GPU time of a CUDA-graph replay."""
     from pcops_b200.attention_layer import attention_contract, attention_layer_fused
+    from pcops_b200.pipeline import SA_LEVELS
     g = torch.Generator(device="cuda").manual_seed(5)
-    C, S = 64, 32
-    x = torch.randn(G, S, C, generator=g, device="cuda")
-    xq = x[:, 0, :].contiguous()
-    W = [torch.randn(C, C, generator=g, device="cuda") / 8 for _ in range(3)]
-    b = [torch.randn(C, generator=g, device="cuda") * 0.1 for _ in range(3)]
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
-
-    def comp():
-        return attention_contract(xq @ W[0] + b[0], x @ W[1] + b[1], x @ W[2] + b[2], C // 4, 4)
-
-    def fused():
-        return attention_layer_fused(xq, x, W[0], b[0], W[1], b[1], W[2], b[2])
 
     def graph_ms(fn):
         fn()
@@ -231,16 +226,35 @@ def time_fused_attention_layer(torch, ops, G):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         return sorted(ts)[len(ts) // 2]
+    out = {"tensor_peak_note": "dense tf32 nominal 1.1 PFLOP/s; the 3xTF32 split triples the issued flops", "levels": {}}
     try:
-        a, c = fused(), comp()
-        err = float(((a - c).abs().max() / c.abs().max()).item())
-        tf, tc = graph_ms(fused), graph_ms(comp)
+        for li, (m, _r, S, C) in enumerate(SA_LEVELS):
+            G = B * m
+            x = torch.randn(G, S, C, generator=g, device="cuda")
+            xq = x[:, 0, :].contiguous()
+            W = [torch.randn(C, C, generator=g, device="cuda") / C ** 0.5 for _ in range(3)]
+            b = [torch.randn(C, generator=g, device="cuda") * 0.1 for _ in range(3)]
+
+            def comp():
+                return attention_contract(xq @ W[0] + b[0], x @ W[1] + b[1], x @ W[2] + b[2], C // 4, 4)
+
+            def fused():
+                return attention_layer_fused(xq, x, W[0], b[0], W[1], b[1], W[2], b[2])
+            a, c = fused(), comp()
+            err = float(((a - c).abs().max() / c.abs().max()).item())
+            tf, tc = graph_ms(fused), graph_ms(comp)
+            flops = 3 * 2.0 * G * S * C * 2 * C  # three UMMA passes over the K|V projection
+            out["levels"]["sa%d" % (li + 1)] = {
+                "shape": "G=%d S=%d C=%d heads=%d key_dim=4" % (G, S, C, C // 4), "fused_ms": tf,
+                "fp32_cublas_composition_ms": tc, "speedup": tc / tf, "max_err_over_max_abs_vs_fp32": err,
+                "issued_tf32_tflops": flops / (tf * 1e-3) / 1e12}
+            del x, xq, W, b
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    flops = 3 * 2.0 * G * S * C * 2 * C  # 3xTF32 split: three UMMA passes over the K|V projection
-    return {"shape": "G=%d S=32 C=64 heads=16 key_dim=4" % G, "fused_ms": tf, "fp32_cublas_composition_ms": tc,
-            "speedup": tc / tf, "max_rel_err_vs_fp32": err, "tf32_mma_tflops": flops / (tf * 1e-3) / 1e12,
-            "tensor_peak_note": "dense tf32 nominal 1.1 PFLOP/s; 3xTF32 split triples the issued flops"}
+    lv = out["levels"]
+    out["fused_ms_all_levels"] = sum(v["fused_ms"] for v in lv.values())
+    out["composition_ms_all_levels"] = sum(v["fp32_cublas_composition_ms"] for v in lv.values())
+    return out
 
 
 def time_steady_state_gathers(torch, ops, hbm_peak):
@@ -613,6 +627,52 @@ def main():
             for pl in tp:
                 pl.capture(overlap)
 
+    # ---- timed region 3b: the forward with the WHOLE attention layer per level (Dense Q/K/V on the tensor cores +
+    # contraction, from stand-in grouped activations) instead of the contraction alone on stand-in K / V -------------
+    with_layers = None
+    if args.attention_layers and args.attention:
+        LD = max(1, min(D, 4))
+        lp = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=True, seed=rank * 64 + 32 + d, own_streams=True,
+                              grid=bool(args.grid), attention_layers=True) for d in range(LD)]
+        for pl in lp:
+            pl.set_inputs(dev_xyz[0], dev_feat[0])
+            pl.forward(overlap)
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            for pl in lp:
+                pl.capture(overlap)
+
+        def step_layers(i):
+            pl = lp[i % LD]
+            pl.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+            if use_graph:
+                pl.replay()
+            else:
+                pl.forward(overlap)
+        for i in range(max(3, LD)):
+            step_layers(i)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(cur)
+        for pl in lp:
+            pl.main.wait_stream(cur)
+        for i in range(K):
+            step_layers(i)
+        for pl in lp:
+            cur.wait_stream(pl.main)
+        h1.record(cur)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        lay_ms = sharding.max_over_ranks(h0.elapsed_time(h1))
+        with_layers = {"workload": "the same forward with pc_attention_layer_fwd (Dense Q/K/V as 3xTF32 tcgen05 UMMA + "
+                                   "contraction, K and V never stored) at all four levels instead of the contraction on "
+                                   "stand-in K / V; 25.8 GFLOP of projections per step added",
+                       "value": world * B * K / (lay_ms * 1e-3), "unit": UNIT, "ms_per_step": lay_ms / K,
+                       "batches_in_flight": LD, "gpu_launches": lp[0].launches_per_step * K * world}
+        del lp
+        torch.cuda.empty_cache()
+
     # ---- timed region 4: config 4, whole scans through the GPU chunker + forward + map_back -------------------
     config4 = None
     if args.scenes > 0 and args.attention and not args.fuse_layers:
@@ -687,7 +747,7 @@ def main():
         # The fused AttentionLayer (Dense Q/K/V + contraction on tcgen05, csrc/attention_layer.cu) at the SA1 shape, next
         # to the composition it replaces (three fp32 cuBLAS GEMMs + pc_attention_fwd); GPU time of a CUDA-graph replay.
         try:
-            fused_layer = time_fused_attention_layer(torch, pcops_b200, B * 1024)
+            fused_layer = time_fused_attention_layer(torch, pcops_b200, B)
         except Exception as exc:  # reported, never fatal for the headline numbers
             fused_layer = {"error": str(exc)[:200]}
     if probes:
@@ -761,6 +821,7 @@ def main():
         "roofline": roofline,
         "rooflines": rooflines,
         "grid_variants_ms": grid_ms,
+        "with_attention_layers": with_layers,
         "config3_training_step": train,
         "gathers_steady_state": steady,
         "config4_whole_scene": config4,

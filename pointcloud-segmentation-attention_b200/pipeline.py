@@ -36,7 +36,7 @@ KEY_DIM = 4  # attention_layer.py:256-258: heads = C // 4, key_dim = output_dim 
 
 class ScanNetGeometry:
     def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0, own_streams=False,
-                 grid=True, fuse_gather=True, fuse_layers=False):
+                 grid=True, fuse_gather=True, fuse_layers=False, attention_layers=False):
         self.B, self.N, self.CF = batch, npoints, feat_channels
         # development knob (scripts only): which parts of the forward to enqueue, e.g. PCOPS_PIPE_PARTS=fps
         import os
@@ -50,6 +50,9 @@ class ScanNetGeometry:
         self.grid = grid  # cell-grid ball query / three_nn (same outputs as the all-pairs kernels, far fewer pair tests)
         self.dev = torch.device(device)
         self.attention = attention
+        # attention_layers: run the WHOLE AttentionLayer (Dense Q/K/V + contraction, pc_attention_layer_fwd on tcgen05)
+        # on stand-in grouped activations X instead of the contraction alone on stand-in K / V
+        self.attention_layers = bool(attention and attention_layers)
         self.L = _lib.lib()
         # result arena: every tensor of result_tensors() is a view into it (4-byte elements, 16-byte aligned slots)
         sizes, n_ = [], npoints
@@ -89,7 +92,14 @@ class ScanNetGeometry:
             lv["gfeat"] = torch.empty((batch, m, ns, cin), dtype=f32, device=dev)
             if fuse_layers:
                 lv["new_points"] = torch.empty((batch, m, ns, 3 + cin), dtype=f32, device=dev)
-            if attention:  # stand-ins for the Dense projections of the level's (B,m,ns,cout) activations
+            if self.attention_layers:  # stand-in for the shared MLP's output (B,m,ns,cout) + the three Dense layers
+                lv["X"] = rnd(batch * m, ns, cout)
+                lv["XQ"] = lv["X"][:, 0, :].contiguous()          # query = sample 0 of the group (attention_layer.py:259)
+                lv["W"] = [rnd(cout, cout) / cout ** 0.5 for _ in range(3)]
+                lv["b"] = [rnd(cout) * 0.1 for _ in range(3)]
+                lv["att"] = torch.empty((batch * m, cout), dtype=f32, device=dev)
+                lv["att_ws"] = _lib.workspace(self.L.pc_attention_layer_workspace_bytes(batch * m, ns, cout), dev)
+            elif attention:  # stand-ins for the Dense projections of the level's (B,m,ns,cout) activations
                 lv["Q"] = rnd(batch * m, cout)
                 lv["K"] = rnd(batch * m, ns, cout)
                 lv["V"] = rnd(batch * m, ns, cout)
@@ -119,7 +129,8 @@ class ScanNetGeometry:
         # when the known cloud has >= 64 points), weights, interpolate per FP level
         self.launches_per_step = len(self.levels) * ((6 if attention else 5) + (2 if grid else 0) -
                                                      (1 if fuse_gather else 0) - (1 if fuse_layers else 0)) + \
-            sum(3 + (2 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps)
+            sum(3 + (2 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps) + \
+            (2 * len(self.levels) if self.attention_layers else 0)   # fused layer = operand prep + Q + main kernel
         self._graph = None
         self.training = False
 
@@ -176,7 +187,12 @@ class ScanNetGeometry:
                 B, n, 3, m, ns, p(lv["xyz"]), p(lv["idx"]), p(lv["gxyz"]), st))
             run("group_feat_sa%d" % (li + 1), side, lambda: L.pc_group_point(
                 B, n, cin, m, ns, p(lv["feat"]), p(lv["idx"]), p(lv["gfeat"]), st))
-        if self.attention:
+        if self.attention_layers:
+            W, b = lv["W"], lv["b"]
+            run("attention_sa%d" % (li + 1), side, lambda: L.pc_attention_layer_fwd(
+                B * m, ns, lv["cout"], p(lv["XQ"]), p(lv["X"]), p(W[0]), p(b[0]), p(W[1]), p(b[1]), p(W[2]), p(b[2]),
+                p(lv["att"]), p(lv["att_ws"]), st))
+        elif self.attention:
             run("attention_sa%d" % (li + 1), side, lambda: L.pc_attention_fwd(
                 B * m, ns, lv["cout"] // KEY_DIM, KEY_DIM, p(lv["Q"]), p(lv["K"]), p(lv["V"]), p(lv["att"]), st))
 

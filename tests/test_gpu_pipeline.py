@@ -103,3 +103,30 @@ def test_training_step_gradients_match_oracle():
     torch.cuda.synchronize()
     check()
     assert torch.equal(grads[0], pipe.levels[1]["d_feat"]) and torch.equal(grads[1], pipe.fps[3]["d_points2"])
+
+
+def test_pipeline_with_whole_attention_layers():
+    """attention_layers=True: every level runs pc_attention_layer_fwd (tcgen05) on stand-in grouped activations; eager and
+    graph replay agree bit for bit and match the oracle's Dense + contraction within 1e-5 of the output scale."""
+    B = 1
+    xyz_np, feat_np = synth.scannet_batch(600, B, 8192)
+    pipe = ScanNetGeometry(B, attention_layers=True)
+    pipe.set_inputs(torch.from_numpy(xyz_np), torch.from_numpy(feat_np))
+    pipe.forward(overlap=False)
+    torch.cuda.synchronize()
+    assert pipe.launches_per_step == 46 + 8
+    eager = []
+    for lv in pipe.levels[1:]:          # SA2-SA4 (G = 256, 64, 16): small enough for the CPU oracle
+        C = lv["cout"]
+        W, b = [npy(w) for w in lv["W"]], [npy(v) for v in lv["b"]]
+        want = cpu.attention_layer(npy(lv["X"]), npy(lv["XQ"]), W[0], b[0], W[1], b[1], W[2], b[2], C // KEY_DIM, KEY_DIM)
+        err = np.abs(npy(lv["att"]) - want).max() / np.abs(want).max()
+        assert err <= 1e-5, (C, err)
+        eager.append(lv["att"].clone())
+    pipe.capture(overlap=True)
+    for lv in pipe.levels:
+        lv["att"].zero_()
+    pipe.replay()
+    torch.cuda.synchronize()
+    for lv, a in zip(pipe.levels[1:], eager):
+        assert torch.equal(lv["att"], a)
