@@ -177,55 +177,65 @@ attention_layer_wide_kernel(int G, int C, const float *__restrict__ qg, const fl
 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers
-    float4 pre[8];
-    auto fetch = [&](int item, int kb) {   // X[tile rows, 32 kb .. +31]: thread t takes float4 t + 128 i -> row (i4>>3), quad i4&7
-      const int tile = item / nchunk;
+    // The CTA's K blocks form one sequence it = 0, 1, ...: item blockIdx.x + (it / nkb) * gridDim.x, block it % nkb.
+    // X rows are fetched TWO blocks ahead into alternating register sets, so a block's global loads have a whole
+    // block period to land before they are split and stored (one block ahead left the tensor pipe 10 % busy: every
+    // block waited out a full global-load latency).
+    const int my_items = blockIdx.x < nitems ? (nitems - 1 - blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_it = my_items * nkb;
+    auto fetch = [&](float4 (&buf)[8], int it_) {   // thread t takes float4 t + 128 i -> row (i4 >> 3), quad i4 & 7
+      const int w = it_ / nkb, kb = it_ - w * nkb;
+      const int tile = (blockIdx.x + w * (int)gridDim.x) / nchunk;
       const size_t row0 = (size_t)tile * kRows;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
-        pre[i] = (item < nitems && row0 + row < total_rows)
+        buf[i] = (it_ < n_it && row0 + row < total_rows)
                      ? __ldg(reinterpret_cast<const float4 *>(x + (row0 + row) * C + kb * kKB) + kq)
                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    int it = 0;
-    int item = blockIdx.x;
-    if (item < nitems) fetch(item, 0);
-    for (; item < nitems; item += gridDim.x) {
-      const int j = item % nchunk;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it & 1;
-        mbar_wait(empty[s], ((it >> 1) & 1) ^ 1);       // the MMAs that read this stage two blocks ago have completed
-        unsigned char *st = stage_buf + s * kStage;
-        if (tid == 0) {  // B block: 64 KB, already hi | lo and swizzled in the image
-          const unsigned char *src = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
-          const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
-          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"((uint32_t)(2 * kBBlock))
+    auto produce = [&](const float4 (&buf)[8], int it_) {
+      const int w = it_ / nkb, kb = it_ - w * nkb;
+      const int j = (blockIdx.x + w * (int)gridDim.x) % nchunk;
+      const int s = it_ & 1;
+      mbar_wait(empty[s], ((it_ >> 1) & 1) ^ 1);       // the MMAs that read this stage two blocks ago have completed
+      unsigned char *st = stage_buf + s * kStage;
+      if (tid == 0) {  // B block: 64 KB, already hi | lo and swizzled in the image
+        const unsigned char *src = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
+        const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"((uint32_t)(2 * kBBlock))
+                     : "memory");
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           dst + c * (kBBlock / 2)),
+                       "l"(src + c * (kBBlock / 2)), "r"((uint32_t)(kBBlock / 2)), "r"(full[s])
                        : "memory");
+      }
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             dst + c * (kBBlock / 2)),
-                         "l"(src + c * (kBBlock / 2)), "r"((uint32_t)(kBBlock / 2)), "r"(full[s])
-                         : "memory");
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
-          const float4 v = pre[i];
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          const int off = block_offset(row, kq * 4);
-          *reinterpret_cast<float4 *>(st + off) = h;
-          *reinterpret_cast<float4 *>(st + kABlock + off) = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
-        // next block's X rows in flight while this one is consumed
-        if (kb + 1 < nkb) fetch(item, kb + 1);
-        else fetch(item + gridDim.x, 0);
+      for (int i = 0; i < 8; ++i) {
+        const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+        const float4 v = buf[i];
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        const int off = block_offset(row, kq * 4);
+        *reinterpret_cast<float4 *>(st + off) = h;
+        *reinterpret_cast<float4 *>(st + kABlock + off) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
+    };
+    float4 bufA[8], bufB[8];
+    fetch(bufA, 0);
+    fetch(bufB, 1);
+    for (int it = 0; it < n_it; it += 2) {
+      produce(bufA, it);
+      fetch(bufA, it + 2);
+      if (it + 1 < n_it) {
+        produce(bufB, it + 1);
+        fetch(bufB, it + 3);
       }
     }
   } else if (warp == 8) {
