@@ -45,7 +45,7 @@ NPOINTS = 8192
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=2000)  # ~0.55 s timed region: several 100 ms clock samples fall inside it
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="scenes per GPU per step (the config names 16)")
@@ -313,12 +313,25 @@ def run_config4(torch, np, args, pipes, rank, world, dev, sharding, with_cpu):
     from pcops_b200 import complete_scene_loader as csl
     from pcops_b200 import synth
     S, B = args.scenes, pipes[0].B
-    lo, _ = sharding.shard_bounds(world * S, rank, world)
-    scans = []
-    for i in range(S):
-        p, l, c, n = synth.whole_scene(1000 + lo + i)
+    # This function contains NO collective: a rank-local failure must not leave the other ranks in a barrier.  The caller
+    # agrees on the timing (max over ranks) outside its try block.
+    # Scans: seeds 1000 + 1000 * rank + k, k = 0, 1, ...  A scan in which some cell holds an exact multiple of 8192
+    # points makes the reference raise (complete_scene_loader.py:89-90 concatenates an empty list with a 2-D array) and
+    # so does the mirror; such scans (about 1 in 50 here) are not part of the workload: skipped, and counted.
+    scans, skipped, k = [], 0, 0
+    while len(scans) < S and k < 8 * S + 8:
+        p, l, c, n = synth.whole_scene(1000 + 1000 * rank + k)
+        k += 1
         f6 = np.concatenate([c.astype(np.float32) / 255.0, n], 1)      # train.py:95-98 (stock TF cast, outside the op path)
-        scans.append((p, tuple(torch.from_numpy(a).to(dev) for a in (p, l, f6))))
+        dev_scan = tuple(torch.from_numpy(a).to(dev) for a in (p, l, f6))
+        try:
+            csl.chunk_scene(dev_scan[0])
+        except ValueError:
+            skipped += 1
+            continue
+        scans.append((p, dev_scan))
+    if len(scans) < S:
+        raise RuntimeError("could not find %d chunkable scans" % S)
     cur = torch.cuda.current_stream(dev)
     use_graph = bool(args.graph)
     stats = {"chunks": 0, "points": 0}
@@ -359,15 +372,13 @@ def run_config4(torch, np, args, pipes, rank, world, dev, sharding, with_cpu):
     # leave the top-most point outside every un-padded cell, complete_scene_loader.py:34,41 -- reproduced, not fixed)
     ok = float((bp == scans[0][1][0]).all(dim=1).float().mean().item())
     stats["chunks"] = stats["points"] = 0
-    sharding.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(cur)
     for i in range(S):
         one(i)
     e1.record(cur)
     torch.cuda.synchronize(dev)
-    sharding.barrier()
-    ms = sharding.max_over_ranks(e0.elapsed_time(e1))
+    ms = e0.elapsed_time(e1)
     # the chunker alone (device tensors in, device tensors out)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record(cur)
@@ -378,7 +389,7 @@ def run_config4(torch, np, args, pipes, rank, world, dev, sharding, with_cpu):
     torch.cuda.synchronize(dev)
     out = {"workload": "config 4: whole-scan inference data path, %d synthetic scans per GPU (100-200 k points), chunker + "
                        "geometry forward over the chunks (B=%d) + map_back" % (S, B),
-           "value": world * S / (ms * 1e-3), "unit": "scans/s", "ms_per_scan": ms / S,
+           "ms_local": ms, "scans_per_gpu": S, "unit": "scans/s", "scans_rejected_like_the_reference": skipped,
            "chunks_per_scan": stats["chunks"] / S, "points_per_scan": stats["points"] / S,
            "chunker_ms_per_scan": c0.elapsed_time(c1) / S, "map_back_restored_fraction": ok}
     if with_cpu:
@@ -676,10 +687,21 @@ def main():
     # ---- timed region 4: config 4, whole scans through the GPU chunker + forward + map_back -------------------
     config4 = None
     if args.scenes > 0 and args.attention and not args.fuse_layers:
+        c4_ms = -1.0
         try:
             config4 = run_config4(torch, np, args, pipes, rank, world, dev, sharding, world == 1 and not args.skip_cpu)
+            c4_ms = float(config4.pop("ms_local"))
         except Exception as exc:   # reported, never fatal for the headline numbers
             config4 = {"error": repr(exc)[:300]}
+        # every rank takes part in both reductions whether or not its own region succeeded
+        c4_max, c4_all_ok = sharding.agree_on_region(c4_ms)
+        if "error" not in config4:
+            if not c4_all_ok:
+                config4 = {"error": "the config-4 region failed on another rank"}
+            else:
+                S4 = config4["scans_per_gpu"]
+                config4["value"] = world * S4 / (c4_max * 1e-3)
+                config4["ms_per_scan"] = c4_max / S4
 
     # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
     peaks = {}

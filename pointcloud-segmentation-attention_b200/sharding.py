@@ -45,3 +45,15 @@ def sum_over_ranks(value, device=None):
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def agree_on_region(local_ms):
+    """Outcome of an OPTIONAL timed region that a rank may have failed on its own (it caught an exception and passes
+    ``None`` or a negative time): returns (max over ranks of the times, True if every rank succeeded).  Every rank must
+    call this exactly once per region, success or not -- the region itself must contain no collective, otherwise a
+    rank-local failure leaves the others waiting in it (this happened: one rank's scan was rejected by the chunker and
+    seven ranks sat in a barrier until the NCCL watchdog fired)."""
+    ms = -1.0 if local_ms is None or local_ms < 0 else float(local_ms)
+    slowest = max_over_ranks(ms)
+    fastest = -max_over_ranks(-ms)
+    return slowest, fastest >= 0

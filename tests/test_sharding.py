@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pcops_b200.sharding import max_over_ranks, shard_bounds, shard_sizes, sum_over_ranks
+from pcops_b200.sharding import agree_on_region, max_over_ranks, shard_bounds, shard_sizes, sum_over_ranks
 
 
 @pytest.mark.parametrize("n,world", [(312, 8), (16, 1), (16, 2), (7, 4), (3, 8), (0, 2), (1000003, 8)])
@@ -64,3 +64,43 @@ def test_two_rank_gloo_run_covers_every_scene_once():
     total, slowest, count = q.get()
     assert total == sum((s * 2654435761) % 1000003 for s in range(n_units))
     assert slowest == 2.0 and count == n_units
+
+
+def _region_worker(rank, world, port, out):
+    """An optional region that fails on rank 1 only: nobody may hang, everybody learns that it failed."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    local = None
+    try:
+        if rank == 1:
+            raise ValueError("this rank's scan is rejected")
+        local = 5.0 + rank
+    except ValueError:
+        pass
+    slowest, ok = agree_on_region(local)
+    slowest2, ok2 = agree_on_region(3.0 + rank)      # a second region in which every rank succeeds
+    if rank == 0:
+        out.put((slowest, ok, slowest2, ok2))
+    dist.destroy_process_group()
+
+
+def test_a_rank_local_failure_in_an_optional_region_cannot_deadlock():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_region_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    slowest, ok, slowest2, ok2 = q.get()
+    assert ok is False and slowest == 5.0
+    assert ok2 is True and slowest2 == 4.0
+
+
+def test_agree_on_region_single_process():
+    assert agree_on_region(2.5) == (2.5, True)
+    assert agree_on_region(None) == (-1.0, False)
