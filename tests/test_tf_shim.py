@@ -56,4 +56,15 @@ def test_every_registered_op_has_a_gpu_kernel_calling_the_c_abi():
 def test_shim_parses_against_the_c_abi_header():
     out = subprocess.run(["sh", os.path.join(SHIM, "check.sh")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
-    assert out.stdout.count("ok:") == 3
+    assert out.stdout.count("ok:") == 4
+
+
+def test_attention_shim_registers_gpu_kernels_over_the_c_abi():
+    """attention_ops.cc adds ops the reference does not have (its AttentionLayer composes stock TF ops): the contraction,
+    its gradient, and the whole layer on the tensor cores.  They must be GPU kernels that call the C ABI."""
+    text = open(os.path.join(SHIM, "attention_ops.cc")).read()
+    ops = set(re.findall(r'REGISTER_OP\("(\w+)"\)', text))
+    assert ops == {"PointAttentionContract", "PointAttentionContractGrad", "PointAttentionLayer"}
+    assert set(re.findall(r'REGISTER_KERNEL_BUILDER\(Name\("(\w+)"\)\.Device\(DEVICE_GPU\)', text)) == ops
+    for fn in ("pc_attention_fwd", "pc_attention_bwd", "pc_attention_layer_fwd", "pc_attention_layer_workspace_bytes"):
+        assert re.search(r"\b%s\(" % fn, text), fn
