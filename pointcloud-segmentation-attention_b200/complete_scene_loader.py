@@ -121,7 +121,9 @@ class SceneChunks:
         return out
 
     def sample_weights(self, gathered_labels=None):
-        """(C,npoints) float64: label_weights[label] (1 without labels), masked on full chunks only (:66-70,:100-103)."""
+        """(C,npoints) float64: label_weights[label] (1 without labels), masked on full chunks only (:66-70,:100-103).
+        Labels are assumed to lie in 0..20 as ScanNet's do (the reference indexes a 21-entry table with them, :12-13,
+        and would raise IndexError beyond it); here any non-zero label weighs 1."""
         L = _lib.lib()
         lab = None
         if gathered_labels is not None:
