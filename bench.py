@@ -257,6 +257,39 @@ def time_fused_attention_layer(torch, ops, B):
     return out
 
 
+def time_config1(torch, ops, xyz1, feat1, with_cpu):
+    """BASELINE config 1: a single synthetic 8192-point scene, B = 1, SA1 only -- FPS npoint=1024, gather, ball query
+    r=0.1 nsample=32, group_point of xyz and features (sample_and_group, pointnet_util.py:16-58).  GPU: latency of one
+    call through the wrapper (5 launches, eager, CUDA events, median of 20).  CPU: the same ops of the C port, 1 thread."""
+    x, f = xyz1.cuda(), feat1.cuda()
+    for _ in range(3):
+        ops.sample_and_group(1024, 0.1, 32, x, f)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.sample_and_group(1024, 0.1, 32, x, f)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    out = {"workload": "config 1: one 8192-point scene, SA1 only (FPS 1024, ball r=0.1 k=32, group xyz+6ch)",
+           "gpu_ms": sorted(ts)[len(ts) // 2], "gpu_ms_min": min(ts)}
+    if with_cpu:
+        from oracle import cpu  # test infrastructure, used here only as the timed CPU baseline
+        xn, fn = xyz1.numpy(), feat1.numpy()
+        t0 = time.perf_counter()
+        fi = cpu.farthest_point_sample(1024, xn)
+        nx = cpu.gather_point(xn, fi)
+        idx, _ = cpu.query_ball_point(0.1, 32, xn, nx)
+        cpu.group_point(xn, idx)
+        cpu.group_point(fn, idx)
+        out["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["cpu_kind"] = "port (C restatement, 1 thread)"
+        out["speedup_vs_cpu"] = out["cpu_ms"] / out["gpu_ms"]
+    return out
+
+
 def time_steady_state_gathers(torch, ops, hbm_peak):
     """The HBM-bound gathers at a size where launch ramp and tail are amortised: B=64 scenes per launch (config 5's batch),
     8 launches back to back on rotating buffer sets (> 126 MB L2 between reuses), one CUDA-event pair around all of them.
@@ -726,7 +759,7 @@ def main():
                 "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms,
                 "peak_source": "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock)" % (nsm, sm_max)}
 
-    rooflines, op_ms, grid_ms, fused_layer, steady = {}, {}, {}, None, None
+    rooflines, op_ms, grid_ms, fused_layer, steady, config1 = {}, {}, {}, None, None, None
     if not args.skip_probe:
         # Every op's stand-alone duration: one pipeline instance alone, eager, ONE stream.  The table is taken with the
         # reference-signature ops (all-pairs ball query / three_nn, separate gather), whose algorithmic op counts the
@@ -766,6 +799,11 @@ def main():
             steady = time_steady_state_gathers(torch, pcops_b200, hbm_peak)
         except Exception as exc:
             steady = {"error": str(exc)[:200]}
+        try:   # BASELINE config 1: ONE 8192-point scene, SA1 only, through the reference-named wrapper (latency)
+            config1 = time_config1(torch, pcops_b200, host_xyz[0][:1], host_feat[0][:1],
+                                   rank == 0 and world == 1 and not args.skip_cpu)
+        except Exception as exc:
+            config1 = {"error": str(exc)[:200]}
         # The fused AttentionLayer (Dense Q/K/V + contraction on tcgen05, csrc/attention_layer.cu) at the SA1 shape, next
         # to the composition it replaces (three fp32 cuBLAS GEMMs + pc_attention_fwd); GPU time of a CUDA-graph replay.
         try:
@@ -847,6 +885,7 @@ def main():
         "config3_training_step": train,
         "gathers_steady_state": steady,
         "config4_whole_scene": config4,
+        "config1_single_scene_sa1": config1,
         "attention_layer_tcgen05": fused_layer,
         "cpu_baseline": cpu_baseline,
     }
