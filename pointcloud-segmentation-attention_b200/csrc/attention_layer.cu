@@ -5,7 +5,7 @@
 // grouped rows), a RAW reshape to heads, softmax(QK^T / 2) V.  TensorFlow runs that as three cuBLAS GEMMs, two batched
 // GEMMs with M = 1 / K = 4, a softmax and five intermediate tensors; the K and V tensors alone are 268 MB at SA1.
 //
-// Here (C = 64 only in this round; the other widths take the Dense + pc_attention_fwd composition):
+// Here (C = 64; the wider levels, whose weights do not fit shared memory, are attention_layer_wide.cu):
 //   * a persistent CTA per SM keeps W_k | W_v resident in shared memory as the B operand (N = 128, K = 64);
 //   * per tile of 4 neighbourhoods (128 rows) the X rows are loaded once, split into TF32 hi / lo parts and written to
 //     shared memory in the UMMA K-major 128-byte-swizzle layout;
