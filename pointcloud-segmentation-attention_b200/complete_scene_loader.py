@@ -19,8 +19,6 @@ gathers, sample weights, the inverse scatter of predictions -- runs on the GPU. 
 Work per scan: TWO host round trips (per-cell point counts; per-candidate-chunk mask sums -- the reference drops chunks
 with no point inside the un-padded cell, :63,:99) instead of one numpy pass over the whole scan per cell.
 """
-import ctypes
-
 import numpy as np
 import torch
 
