@@ -16,13 +16,19 @@ JSON line on rank 0:
                 different input batch (ring of R batches); one step touches > 500 MB (> 126 MB L2).  Steps are
                 independent batches, so --depth of them are in flight at once, each on its own streams and buffers
                 (FPS is a latency-bound chain on B SMs; the other SMs work on neighbouring batches meanwhile).
-  e2e           same metric through host buffers: per step H2D of the batch from pinned memory, the forward, ONE D2H
-                of the integer geometry results (FPS / ball / three_nn indices, counts) to pinned memory.
+  e2e           same metric through host buffers, one CUDA graph per step: ONE H2D of the packed batch from pinned
+                memory (xyz | normals | colours as the uint8 they are stored as, 27 B/point; the /255 of train.py:95
+                runs on the device), the forward, the integer geometry results (FPS / ball / three_nn indices,
+                counts -- everything a host consumer needs to rebuild any gathered tensor) narrowed to uint16 on
+                the device (lossless: n <= 8192) and ONE D2H into pinned memory.
   roofline      the kernel with the largest share of a step, duration from CUDA events on its own stream, against
                 its own bound; `rooflines` lists every op (probed eager pass of one pipeline instance).
   cpu_baseline  the CPU oracle (C port of the reference algorithms) on this box's host cores, bounded sample.
+Every timed region runs its K steps `repeats` times back to back inside ONE event pair, repeats chosen so the region
+lasts >= --min-seconds (0.5 s) whatever --steps is; ms_per_step = region / (K * repeats).
 Reference arm (--impl reference): the reference's own CPU code (oracle/_ref, compiled from /root/reference sources)
-where the reference has CPU code for an op, the C port elsewhere, on all host threads, same metric.
+where the reference has CPU code for an op, the C port elsewhere, on all host threads, same metric, same config keys,
+honouring --steps / --warmup (a step is a bounded sample of the batch, sized so that the run ends within minutes).
 """
 import argparse
 import json
@@ -60,7 +66,14 @@ def parse():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--attention-layers", type=int, default=1,
                     help="1: also time the forward with the whole AttentionLayer (Dense Q/K/V + contraction on tcgen05) per level")
-    ap.add_argument("--scenes", type=int, default=6, help="whole scans per GPU in the config-4 region (0: skip)")
+    ap.add_argument("--scenes", type=int, default=39,
+                    help="whole scans per GPU in the config-4 region (0: skip); 39 x 8 GPUs = the 312 scans of the validation split")
+    ap.add_argument("--config5", type=int, default=1, help="1: the config-5 sweep (FPS / ball / kNN, N = 16k..1M, npoint 1k..16k, B = 64 sharded)")
+    ap.add_argument("--sweep-batch", type=int, default=64, help="scenes of the config-5 sweep, sharded over the ranks")
+    ap.add_argument("--sweep-max-n", type=int, default=1 << 20)
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="minimum duration of every headline timed region")
+    ap.add_argument("--lib", default="", help="path of an alternative libpcops build (A/B runs of kernel variants)")
+    ap.add_argument("--e2e-legacy", type=int, default=0, help="1: the round-1 e2e path (two fp32 H2D copies, int32 D2H, no graph)")
     ap.add_argument("--train", type=int, default=1, help="1: also time config 3 (forward + the registered gradients)")
     ap.add_argument("--train-depth", type=int, default=4, help="batches in flight for the config-3 region")
     ap.add_argument("--skip-probe", action="store_true")
@@ -456,8 +469,19 @@ def bind_to_gpu_cpus(index):
     return None
 
 
+def base_config(B, world):
+    """The config keys both arms print (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "npoints": NPOINTS, "feature_channels": 6,
+            "parallelism": "scene-sharded x%d, no collective" % world,
+            "l2": "inputs larger than L2: one step streams > 500 MB (K / V / output tensors) through the 126 MB L2 and "
+                  "every step reads a different batch of scenes (ring of batches)"}
+
+
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, all host threads,
+    same metric and config as the own arm.  A step = a bounded sample of the B-scene batch (S scenes, sized from a
+    probe so that warmup + K steps stay within about two minutes); the K*S scenes of the timed region are one stream
+    over the thread pool (one scene per thread), so every thread is busy whatever S is."""
     if rank != 0:
         return 0
     from oracle import cpu, ref
@@ -465,35 +489,206 @@ def run_reference_arm(args, rank, world):
     cpu.lib()
     use_ref = ref.available_cpu()
     threads = host_threads()
-    per_step = max(threads, 8)              # scenes per step: a bounded sample of the B=16 x N-GPU batch
-    xyz, feat = synth.scannet_batch(0, per_step, NPOINTS)
-    for _ in range(min(args.warmup, 1)):
-        cpu_scenes_per_s(xyz[:threads], feat[:threads], threads, use_ref)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_scenes_per_s(xyz, feat, threads, use_ref)
-    dt = time.perf_counter() - t0
-    value = per_step * steps / dt
-    sample = "%d steps x %d scenes of the B=16 workload, %d host threads, one scene per thread" % (steps, per_step, threads)
+    B, K, W = args.batch, max(1, args.steps), max(0, args.warmup)
+    xyz, feat = synth.scannet_batch(0, B, NPOINTS)
+    # probe: one scene per thread -> whole-pool rate
+    probe_n = min(B, threads)
+    rate, _ = cpu_scenes_per_s(xyz[:probe_n], feat[:probe_n], threads, use_ref)
+    budget_s = 100.0
+    S = int(max(1, min(B, budget_s * rate / (K + W))))
+    sel = lambda steps: np_arange_mod(steps * S, B)   # noqa: E731
+    if W:
+        idx = sel(W)
+        cpu_scenes_per_s(xyz[idx], feat[idx], threads, use_ref)
+    idx = sel(K)
+    value, dt = cpu_scenes_per_s(xyz[idx], feat[idx], threads, use_ref)
+    sample = "%d steps x %d of the %d scenes of a batch (%d scenes), %d host threads, one scene per thread, %.1f s" \
+        % (K, S, B, K * S, threads, dt)
+    cfg = base_config(B, world)
+    run_cfg = {"scenes_per_step": S,
+               "note": "host-only arm: ball query / group_point / three_nn / three_interpolate = the reference's own CPU "
+                       "functions compiled from its sources; FPS, gather, attention contraction = C port of the reference "
+                       "CUDA / TF algorithm (the reference has no CPU code for them)"}
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "scenes_per_step": per_step, "npoints": NPOINTS,
-                   "note": "host-only arm: the reference's geometry ops on the CPU (its interpolation ops are CPU-only; "
-                           "ball query / group_point from its standalone CPU programs; FPS, gather, attention contraction: "
-                           "C port of the reference CUDA / TF algorithm, the reference has no CPU code for them)"},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "run_config": run_cfg,
     }
     print(json.dumps(line))
     return 0
 
 
+def np_arange_mod(n, b):
+    import numpy as np
+    return np.arange(n) % b
+
+
 # ------------------------------------------------------------------------------------------------ own arm
+def run_config5(torch, args, rank, world, dev, sharding, fp32_peak_tops):
+    """BASELINE config 5: geometry-op scaling sweep -- FPS, ball query, kNN at N = 16k ... 1M points, npoint 1k ... 16k,
+    B = --sweep-batch (64) scenes sharded over the ranks (uniform clouds, radius chosen for ~32 expected neighbours,
+    nsample = k = 32).  Every entry is ONE launch after a cheap warm-up launch of the same kernel (m = 2), timed with
+    CUDA events on the launching stream; a 512 MB write between entries flushes L2.  Contains NO collective: the
+    per-entry times of all ranks are reduced in one call afterwards (max over ranks)."""
+    import pcops_b200 as ops
+    Bt = args.sweep_batch
+    lo, hi = sharding.shard_bounds(Bt, rank, world)
+    b = hi - lo
+    entries, times = [], []
+    flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1000 + lo)
+
+    def timed(fn):
+        flush.fill_(0.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), out
+
+    for N in (16384, 65536, 262144, 1048576):
+        if N > args.sweep_max_n:
+            continue
+        x = torch.rand((max(b, 1), N, 3), generator=g, device=dev) if b > 0 else None
+        r = (32.0 / N * 3.0 / (4.0 * 3.14159265)) ** (1.0 / 3.0)
+        for m in (1024, 4096, 16384):
+            for op in ("fps", "ball", "knn"):
+                entries.append((op, N, m))
+            if b == 0:
+                times += [0.0, 0.0, 0.0]
+                continue
+            try:
+                ops.farthest_point_sample_and_gather(2, x)                     # warm-up (attributes, code load)
+                t_fps, (fi, q) = timed(lambda: ops.farthest_point_sample_and_gather(m, x))
+            except Exception:
+                times += [-1.0, -1.0, -1.0]
+                continue
+            times.append(t_fps)
+            try:
+                ops.query_ball_point(r, 32, x, q[:, :32].contiguous())
+                t_ball, _ = timed(lambda: ops.query_ball_point(r, 32, x, q))
+            except Exception:
+                t_ball = -1.0
+            times.append(t_ball)
+            try:
+                ops.knn_point(32, x, q[:, :32].contiguous())
+                t_knn, _ = timed(lambda: ops.knn_point(32, x, q))
+            except Exception:
+                t_knn = -1.0
+            times.append(t_knn)
+            del fi, q
+        del x
+        torch.cuda.empty_cache()
+    del flush
+    torch.cuda.empty_cache()
+    return entries, times, Bt
+
+
+def finish_config5(entries, times, Bt, world, fp32_peak_tops):
+    rows = []
+    for (op, N, m), ms in zip(entries, times):
+        row = {"op": op, "n": N, "npoint": m, "ms": ms if ms >= 0 else None}
+        if ms > 0:
+            row["scenes_per_s"] = Bt / (ms * 1e-3)
+            pairs = float(Bt) * N * (m - 1 if op == "fps" else m)
+            row["gpairs_per_s"] = pairs / (ms * 1e-3) / 1e9          # distance evaluations (kNN makes two passes)
+            flops = pairs * (10 if op == "fps" else 11)
+            row["frac_fp32"] = flops / (ms * 1e-3) / 1e12 / (fp32_peak_tops * world)
+        rows.append(row)
+    ok = [r for r in rows if r["ms"]]
+    return {"workload": "config 5: FPS / ball query (r for ~32 neighbours, nsample 32) / kNN (k 32) on uniform clouds, "
+                        "B=%d scenes sharded over %d GPU(s); one launch each, max over ranks; frac_fp32 = algorithmic "
+                        "pair tests x 10 (FPS) or 11 flops / whole-job un-fused fp32 peak" % (Bt, world),
+            "paths": "FPS: one 2..16-CTA cluster per scene up to 262144 points (state on chip), beyond that one CTA per "
+                     "scene streaming the running minima through L2; ball query: all-pairs kernel with early exit "
+                     "above 21088 points (the per-query bitmap of the cell-grid kernel no longer fits shared memory); "
+                     "kNN: fused two-pass kernel, no (b,m,n) matrix",
+            "rows": rows, "total_ms": sum(r["ms"] for r in ok), "failed": len(rows) - len(ok)}
+
+
+def time_reference_gpu_kernels(torch, dev, dev_xyz, dev_feat):
+    """The reference's own CUDA kernels (tf_sampling_g.cu, tf_grouping_g.cu compiled UNMODIFIED for sm_100a with the
+    reference's flags into oracle/_ref/libref_gpu.so; original launch shapes, legacy default stream) timed per op on
+    this GPU at the bench shapes: the GPU-vs-GPU baseline of SURVEY.md 8(d).  Bench-leg use of oracle/ only."""
+    from oracle import ref
+    import pcops_b200 as ops
+    if not ref.available_gpu(nofma=False):
+        return {"unavailable": "oracle/_ref/libref_gpu.so not present"}
+    G = ref.Gpu(nofma=False)
+    x, f = dev_xyz, dev_feat
+    B, n = x.shape[0], x.shape[1]
+    torch.cuda.synchronize(dev)
+
+    def med(fn, iters=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+    out = {"source": "tf_sampling_g.cu:203-205 <<<32,512>>>, tf_grouping_g.cu:125-141 <<<b,256>>>, nvcc -O2 (default fmad), "
+                     "legacy default stream, median of 5, B=%d" % B}
+    with torch.cuda.stream(torch.cuda.default_stream(dev)):
+        temp = torch.empty((32, n), dtype=torch.float32, device=dev)
+        fi = torch.zeros((B, 1024), dtype=torch.int32, device=dev)
+        ref_fps = med(lambda: G.fps_launch(1024, x, temp, fi))
+        ours_fps = med(lambda: ops.farthest_point_sample(1024, x))
+        nx = ops.gather_point(x, ops.farthest_point_sample(1024, x))
+        idx = torch.zeros((B, 1024, 32), dtype=torch.int32, device=dev)
+        cnt = torch.zeros((B, 1024), dtype=torch.int32, device=dev)
+        ref_ball = med(lambda: G.ball_launch(0.1, 32, x, nx, idx, cnt))
+        ours_ball = med(lambda: ops.query_ball_point(0.1, 32, x, nx))
+        bi, _ = ops.query_ball_point(0.1, 32, x, nx)
+        gx = torch.empty((B, 1024, 32, 3), dtype=torch.float32, device=dev)
+        ref_gxyz = med(lambda: G.group_launch(x, bi, gx))
+        ours_gxyz = med(lambda: ops.group_point(x, bi))
+        p64 = torch.randn((B, 1024, 64), device=dev)
+        i2 = torch.randint(0, 1024, (B, 256, 32), dtype=torch.int32, device=dev)
+        g64 = torch.empty((B, 256, 32, 64), dtype=torch.float32, device=dev)
+        ref_g64 = med(lambda: G.group_launch(p64, i2, g64))
+        ours_g64 = med(lambda: ops.group_point(p64, i2))
+    out["ops"] = {
+        "fps_sa1": {"reference_ms": ref_fps, "ours_ms": ours_fps, "speedup": ref_fps / ours_fps},
+        "query_ball_sa1": {"reference_ms": ref_ball, "ours_ms": ours_ball, "speedup": ref_ball / ours_ball},
+        "group_point_xyz_sa1": {"reference_ms": ref_gxyz, "ours_ms": ours_gxyz, "speedup": ref_gxyz / ours_gxyz},
+        "group_point_c64_sa2": {"reference_ms": ref_g64, "ours_ms": ours_g64, "speedup": ref_g64 / ours_g64},
+    }
+    return out
+
+
+def probe_host_links(torch, dev, sharding):
+    """Pinned-host <-> device copy bandwidth of this rank while ALL ranks copy at the same time (64 MB each way): the
+    ceiling of the e2e region at N GPUs.  Returns (h2d GB/s, d2h GB/s) as the MIN over ranks."""
+    n = 64 * 1024 * 1024
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    out = []
+    for direction in (0, 1):
+        (d.copy_(h, non_blocking=True) if direction == 0 else h.copy_(d, non_blocking=True))
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            (d.copy_(h, non_blocking=True) if direction == 0 else h.copy_(d, non_blocking=True))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        gbs = 4 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        out.append(-sharding.max_over_ranks(-gbs))
+    del h, d
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -502,11 +697,15 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
 
+    import math
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import pcops_b200  # noqa: F401  (raises if libpcops.so is missing -- there is no fallback)
+    if args.lib:
+        pcops_b200._lib.LIB_PATH = os.path.abspath(args.lib)
+    pcops_b200._lib.lib()
     from pcops_b200 import sharding, synth
     from pcops_b200.pipeline import ScanNetGeometry
 
@@ -518,16 +717,18 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B, R, K, W = args.batch, max(1, args.ring), args.steps, max(args.warmup, 3)
+    B, R, K, W = args.batch, max(1, args.ring), max(1, args.steps), max(args.warmup, 3)
 
     # scene shards: rank r owns scenes [r*B*R, (r+1)*B*R) of the synthetic scene list
     lo, _hi = sharding.shard_bounds(world * B * R, rank, world)
-    host_xyz, host_feat, dev_xyz, dev_feat = [], [], [], []
+    host_xyz, host_feat, host_packed, dev_xyz, dev_feat = [], [], [], [], []
     for i in range(R):
         x, f = synth.scannet_batch(lo + i * B, B, NPOINTS)
         hx, hf = torch.from_numpy(x).pin_memory(), torch.from_numpy(f).pin_memory()
         host_xyz.append(hx)
         host_feat.append(hf)
+        col, nrm = synth.split_features(f)      # storage form of the data set: colours are bytes (train.py:95)
+        host_packed.append(ScanNetGeometry.pack_host_batch(x, col, nrm))
         dev_xyz.append(hx.to(dev))
         dev_feat.append(hf.to(dev))
 
@@ -540,6 +741,52 @@ def main():
     cur = torch.cuda.current_stream(dev)
     use_graph = bool(args.graph)
 
+    def fork(ps):
+        for pl in ps:
+            pl.main.wait_stream(cur)
+
+    def join(ps):
+        for pl in ps:
+            cur.wait_stream(pl.main)
+
+    def timed_region(step, ps, sampler=None):
+        """K steps x `repeats` inside ONE event pair on `cur` (forked to / joined from the pipelines' streams), repeats
+        agreed over the ranks so that the region lasts >= --min-seconds.  Returns (ms per K-step block, repeats, host
+        enqueue seconds, wall t0, wall t1)."""
+        for i in range(max(3, len(ps))):
+            step(i)
+        torch.cuda.synchronize(dev)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(cur)
+        fork(ps)
+        for i in range(K):
+            step(i)
+        join(ps)
+        p1.record(cur)
+        torch.cuda.synchronize(dev)
+        est = sharding.max_over_ranks(p0.elapsed_time(p1))
+        reps = max(1, int(math.ceil(args.min_seconds * 1e3 / max(est, 1e-3))))
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.25)
+        sharding.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(cur)
+        fork(ps)
+        for _ in range(reps):
+            for i in range(K):
+                step(i)
+        join(ps)
+        e1.record(cur)
+        t_enq = time.time() - t0
+        torch.cuda.synchronize(dev)
+        t1 = time.time()
+        sharding.barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1))
+        return ms / reps, reps, t_enq / reps, t0, t1
+
     def step_resident(i, probes=None, graph=False):
         pl = pipes[i % D]
         pl.set_inputs(dev_xyz[i % R], dev_feat[i % R])
@@ -547,14 +794,6 @@ def main():
             pl.replay()
         else:
             pl.forward(overlap, probes)
-
-    def fork():
-        for pl in pipes:
-            pl.main.wait_stream(cur)
-
-    def join():
-        for pl in pipes:
-            cur.wait_stream(pl.main)
 
     # warm-up (also sets per-device kernel attributes before any graph capture)
     for i in range(max(W, D)):
@@ -570,61 +809,51 @@ def main():
     # ---- timed region 1: inputs resident in HBM ----------------------------------------------------------------
     work = pipe.algorithmic_work()
     top_guess = "fps_sa1"
-    probes = {top_guess: []} if not use_graph else None
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    sharding.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    e0.record(cur)
-    fork()
-    for i in range(K):
-        step_resident(i, probes, use_graph)
-    join()
-    e1.record(cur)
-    t_enq = time.time()
-    torch.cuda.synchronize(dev)
-    t_wall1 = time.time()
-    sharding.barrier()
-    ms_local = e0.elapsed_time(e1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_block, reps, enq_s, t_wall0, t_wall1 = timed_region(lambda i: step_resident(i, None, use_graph), pipes, sampler)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    ms_total = sharding.max_over_ranks(ms_local)
-    value = world * B * K / (ms_total * 1e-3)
+    value = world * B * K / (ms_block * 1e-3)
 
     # ---- timed region 2: end to end through host buffers -------------------------------------------------------
-    # per step: H2D of the batch from pinned memory, the forward, ONE D2H of the result arena into pinned memory
-    host_out = [torch.empty(pl.result_arena().shape, dtype=torch.int32).pin_memory() for pl in pipes]
-    h2d = pipe.input_bytes()
-    d2h = pipe.result_arena().numel() * 4
+    h2d_gbs, d2h_gbs = probe_host_links(torch, dev, sharding)
+    if args.e2e_legacy:
+        host_out = [torch.empty(pl.result_arena().shape, dtype=torch.int32).pin_memory() for pl in pipes]
+        h2d, d2h = pipe.input_bytes(), pipe.result_arena().numel() * 4
 
-    def step_e2e(i):
-        pl = pipes[i % D]
-        pl.set_inputs(host_xyz[i % R], host_feat[i % R], non_blocking=True)
-        if use_graph:
-            pl.replay()
-        else:
-            pl.forward(overlap)
-        pl.read_results(host_out[i % D])
+        def step_e2e(i):
+            pl = pipes[i % D]
+            pl.set_inputs(host_xyz[i % R], host_feat[i % R], non_blocking=True)
+            if use_graph:
+                pl.replay()
+            else:
+                pl.forward(overlap)
+            pl.read_results(host_out[i % D])
+        e2e_launches = pipe.launches_per_step
+    else:
+        host_out = [torch.empty(pl.result_arena().numel(), dtype=torch.int16).pin_memory() for pl in pipes]
+        h2d, d2h = pipe.packed_input_bytes(), pipe.result_bytes_u16()
+        e2e_graphs = {}
+        if use_graph:   # one graph per (pipeline instance, input slot): H2D + prologue + forward + narrowing + D2H
+            for d_ in range(D):
+                for r_ in sorted({i % R for i in range(d_, D * R, D)}):
+                    e2e_graphs[(d_, r_)] = pipes[d_].capture_e2e(host_packed[r_], host_out[d_], overlap)
 
-    for i in range(max(3, D)):
-        step_e2e(i)
-    torch.cuda.synchronize(dev)
-    sharding.barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(cur)
-    fork()
-    for i in range(K):
-        step_e2e(i)
-    join()
-    f1.record(cur)
-    torch.cuda.synchronize(dev)
-    sharding.barrier()
-    e2e_ms = sharding.max_over_ranks(f0.elapsed_time(f1))
-    e2e_value = world * B * K / (e2e_ms * 1e-3)
-    checksum = int(sum(int(h.to(torch.int64).sum()) for h in host_out))
+        def step_e2e(i):
+            pl = pipes[i % D]
+            if use_graph:
+                with torch.cuda.stream(pl.main):
+                    e2e_graphs[(i % D, i % R)].replay()
+            else:
+                pl.set_inputs_packed(host_packed[i % R])
+                pl.forward(overlap)
+                pl.read_results_u16(host_out[i % D])
+        e2e_launches = pipe.launches_per_step + 2
+    e2e_block, e2e_reps, e2e_enq, _, _ = timed_region(step_e2e, pipes)
+    e2e_value = world * B * K / (e2e_block * 1e-3)
+    checksum = int(sum(int(h.view(torch.uint16).to(torch.int64).sum()) if h.dtype == torch.int16
+                       else int(h.to(torch.int64).sum()) for h in host_out))
+    if use_graph and not args.e2e_legacy:
+        e2e_graphs.clear()
 
     # ---- timed region 3: config 3, a training step's geometry (forward + GroupPointGrad / ThreeInterpolateGrad /
     # attention-contraction backward), inputs resident ----------------------------------------------------------
@@ -648,26 +877,12 @@ def main():
                 pl.replay()
             else:
                 pl.forward(overlap, train=True)
-        for i in range(max(3, TD)):
-            step_train(i)
-        torch.cuda.synchronize(dev)
-        sharding.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(cur)
-        fork()
-        for i in range(K):
-            step_train(i)
-        join()
-        g1.record(cur)
-        torch.cuda.synchronize(dev)
-        sharding.barrier()
-        tr_ms = sharding.max_over_ranks(g0.elapsed_time(g1))
-        train = {"workload": "config 3: attention model with 6-ch features, forward + registered gradients "
-                             "(GroupPointGrad SA2-4, ThreeInterpolateGrad FP1-4, attention contraction backward SA1-4), "
-                             "B=%d x %d" % (B, NPOINTS),
-                 "value": world * B * K / (tr_ms * 1e-3), "unit": UNIT, "ms_per_step": tr_ms / K,
-                 "batches_in_flight": TD, "gpu_launches": tp[0].launches_per_train_step * K * world}
-        if use_graph:   # back to the forward-only graphs for the probes below
+        tr_block, tr_reps, _, _, _ = timed_region(step_train, tp)
+        train = {"workload": "config 3: forward + registered gradients (GroupPointGrad SA2-4, ThreeInterpolateGrad FP1-4, "
+                             "attention contraction backward SA1-4), B=%d x %d" % (B, NPOINTS),
+                 "value": world * B * K / (tr_block * 1e-3), "unit": UNIT, "ms_per_step": tr_block / K, "repeats": tr_reps,
+                 "batches_in_flight": TD, "gpu_launches": tp[0].launches_per_train_step * K * tr_reps * world}
+        if use_graph:   # back to the forward-only graphs for the regions below
             for pl in tp:
                 pl.capture(overlap)
 
@@ -693,27 +908,12 @@ def main():
                 pl.replay()
             else:
                 pl.forward(overlap)
-        for i in range(max(3, LD)):
-            step_layers(i)
-        torch.cuda.synchronize(dev)
-        sharding.barrier()
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        h0.record(cur)
-        for pl in lp:
-            pl.main.wait_stream(cur)
-        for i in range(K):
-            step_layers(i)
-        for pl in lp:
-            cur.wait_stream(pl.main)
-        h1.record(cur)
-        torch.cuda.synchronize(dev)
-        sharding.barrier()
-        lay_ms = sharding.max_over_ranks(h0.elapsed_time(h1))
+        lay_block, lay_reps, _, _, _ = timed_region(step_layers, lp)
         with_layers = {"workload": "the same forward with pc_attention_layer_fwd (Dense Q/K/V as 3xTF32 tcgen05 UMMA + "
-                                   "contraction, K and V never stored) at all four levels instead of the contraction on "
-                                   "stand-in K / V; 25.8 GFLOP of projections per step added",
-                       "value": world * B * K / (lay_ms * 1e-3), "unit": UNIT, "ms_per_step": lay_ms / K,
-                       "batches_in_flight": LD, "gpu_launches": lp[0].launches_per_step * K * world}
+                                   "contraction, K and V never stored) at all four levels; +25.8 GFLOP per step",
+                       "value": world * B * K / (lay_block * 1e-3), "unit": UNIT, "ms_per_step": lay_block / K,
+                       "repeats": lay_reps, "batches_in_flight": LD,
+                       "gpu_launches": lp[0].launches_per_step * K * lay_reps * world}
         del lp
         torch.cuda.empty_cache()
 
@@ -733,10 +933,10 @@ def main():
                 config4 = {"error": "the config-4 region failed on another rank"}
             else:
                 S4 = config4["scans_per_gpu"]
+                config4["scans_total"] = world * S4
                 config4["value"] = world * S4 / (c4_max * 1e-3)
                 config4["ms_per_scan"] = c4_max / S4
 
-    # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -748,18 +948,33 @@ def main():
     nsm = pcops_b200._lib.lib().pc_num_sms()
     fp32_peak_tops = nsm * 128 * sm_max * 1e6 / 1e12   # un-fused fp32 instructions/s (one op per lane per clock)
 
+    # ---- region 5: config 5, the geometry-op scaling sweep (no collective inside; one vector reduce after) ------
+    config5 = None
+    if args.config5:
+        for pl in pipes[1:]:
+            pass
+        try:
+            entries, times, Bt = run_config5(torch, args, rank, world, dev, sharding, fp32_peak_tops)
+        except Exception as exc:
+            entries, times, Bt = None, None, args.sweep_batch
+            config5 = {"error": repr(exc)[:300]}
+        n_entries = 3 * 3 * sum(1 for N in (16384, 65536, 262144, 1048576) if N <= args.sweep_max_n)
+        vec = sharding.max_vector_over_ranks(times if times is not None and len(times) == n_entries else [-1.0] * n_entries)
+        if entries is not None and len(entries) == n_entries:
+            config5 = finish_config5(entries, vec, Bt, world, fp32_peak_tops)
+
+    # ---- probed pass: every op's duration (separate region; events perturb overlap) ----------------------------
     def roof(name, ms):
         wk = work[name]
         if wk["kind"] == "bytes":
             ach = wk["amount"] / (ms * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "ms": ms, "peak_source": peak_src}
+                    "frac": ach / hbm_peak, "traffic": None, "ms": ms}
         ach = wk["amount"] / (ms * 1e-3) / 1e12
         return {"kernel": name, "bound": "fp32", "achieved": ach, "peak": fp32_peak_tops, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms,
-                "peak_source": "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock)" % (nsm, sm_max)}
+                "frac": ach / fp32_peak_tops, "traffic": None, "ms": ms}
 
-    rooflines, op_ms, grid_ms, fused_layer, steady, config1 = {}, {}, {}, None, None, None
+    rooflines, op_ms, grid_ms, fused_layer, steady, config1, ref_gpu = {}, {}, {}, None, None, None, None
     if not args.skip_probe:
         # Every op's stand-alone duration: one pipeline instance alone, eager, ONE stream.  The table is taken with the
         # reference-signature ops (all-pairs ball query / three_nn, separate gather), whose algorithmic op counts the
@@ -767,7 +982,7 @@ def main():
         # beside them in `grid_variants_ms`.
         def probe(pl):
             allp = {n: [] for n in pl.op_names()}
-            for i in range(min(K, 10)):
+            for i in range(10):
                 pl.set_inputs(dev_xyz[i % R], dev_feat[i % R])
                 pl.forward(False, allp)
                 torch.cuda.synchronize(dev)
@@ -788,7 +1003,7 @@ def main():
         if train is not None:      # the gradient ops alone (single stream, eager), against the HBM roofline
             bw = pipe.backward_work()
             allp = {n: [] for n in pipe.backward_op_names()}
-            for i in range(min(K, 10)):
+            for i in range(10):
                 pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
                 pipe.forward(False, allp, train=True)
                 torch.cuda.synchronize(dev)
@@ -804,18 +1019,18 @@ def main():
                                    rank == 0 and world == 1 and not args.skip_cpu)
         except Exception as exc:
             config1 = {"error": str(exc)[:200]}
-        # The fused AttentionLayer (Dense Q/K/V + contraction on tcgen05, csrc/attention_layer.cu) at the SA1 shape, next
-        # to the composition it replaces (three fp32 cuBLAS GEMMs + pc_attention_fwd); GPU time of a CUDA-graph replay.
         try:
             fused_layer = time_fused_attention_layer(torch, pcops_b200, B)
         except Exception as exc:  # reported, never fatal for the headline numbers
             fused_layer = {"error": str(exc)[:200]}
-    if probes:
-        d = [a.elapsed_time(b) for a, b in probes[top_guess]]
-        top_ms = sum(d) / len(d)
-    elif top_guess in op_ms:
-        top_ms = op_ms[top_guess]
-    else:                                 # --skip-probe under graph replay: time the dominant kernel alone
+        if rank == 0:
+            try:   # GPU-vs-GPU: the reference's own CUDA kernels, recompiled unmodified, on this GPU
+                ref_gpu = time_reference_gpu_kernels(torch, dev, dev_xyz[0], dev_feat[0])
+            except Exception as exc:
+                ref_gpu = {"error": str(exc)[:200]}
+    if top_guess in op_ms:
+        top_ms = grid_ms.get(top_guess, op_ms[top_guess])
+    else:                                 # --skip-probe: time the dominant kernel alone
         solo = {top_guess: []}
         for i in range(5):
             pipe.set_inputs(dev_xyz[i % R], dev_feat[i % R])
@@ -824,20 +1039,37 @@ def main():
         d = sorted(a.elapsed_time(b) for a, b in solo[top_guess]) or [float("inf")]
         top_ms = d[len(d) // 2]
     roofline = roof(top_guess, top_ms)
-    try:  # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top_guess, {})
-        if B == 16 and tr.get("bytes") is not None:
-            roofline["traffic"] = tr["bytes"]
-            roofline["traffic_source"] = tr.get("capture")
+    roofline["peak_source"] = "%d SMs x 128 fp32 lanes x %.0f MHz, un-fused (1 flop per lane-clock); no fp32 peak in " \
+        "MEASURED_PEAKS.json -- scripts/ubench/fp32_rate.cu measures 127 flop/clk/SM on this part" % (nsm, sm_max)
+    roofline["algorithmic_bytes"] = work[top_guess].get("bytes")
+    roofline["kernel_sms"] = min(B, nsm)   # one scene per SM: a B-scene launch cannot occupy more
+    # ncu evidence of the TIMED kernel (committed capture of this round; static, labelled with its source)
+    try:
+        ev = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(top_guess, {})
+        if B == 16 and ev:
+            roofline["traffic"] = ev.get("dram_bytes")
+            roofline["ncu"] = {k: ev.get(k) for k in ("kernel", "capture", "duration_us", "issue_slots_busy_pct",
+                                                      "top_pipe", "top_pipe_pct", "cycles_per_round", "registers")}
     except Exception:
         pass
-    roofline["algorithmic_bytes"] = work[top_guess].get("bytes")
-    roofline["occupied_sms"] = min(B, nsm)
-    roofline["frac_of_occupied_sms"] = roofline["frac"] * nsm / min(B, nsm)   # FPS runs one scene per SM
-    roofline["share_of_step"] = top_ms / sum(op_ms.values()) if op_ms else None
-    roofline["timed"] = "CUDA events around each launch on its stream, inside the value region (mean of %d)" % K \
-        if probes else "CUDA events around each launch in a probed single-stream eager pass right after the value " \
-                       "region (graph replay hides single launches); share = its time / sum of all op times"
+    # the pipelined step as a whole: where its SM-time and its HBM bytes go
+    step_ms = ms_block / K
+    step_bytes = sum(w.get("bytes", w["amount"]) if w["kind"] != "bytes" else w["amount"]
+                     for n_, w in work.items() if n_ in set(pipe.op_names()))
+    fps_names = [n_ for n_ in pipe.op_names() if n_.startswith("fps")]
+    src_ms = grid_ms if grid_ms else op_ms
+    step_shape = {"ms_per_step": step_ms, "algorithmic_bytes_per_step": step_bytes,
+                  "step_hbm_frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak if step_ms > 0 else None}
+    if src_ms:
+        fps_sm_ms = sum(src_ms.get(n_, 0.0) for n_ in fps_names) * min(B, nsm)
+        step_shape["fps_sm_time_share"] = fps_sm_ms / (nsm * step_ms)
+        step_shape["note"] = "fps_sm_time_share = (SMs an FPS launch holds x its duration, 4 levels) / (all SMs x ms_per_step); " \
+                             "HBM-byte shares per op = rooflines[op] bytes / algorithmic_bytes_per_step"
+        att_bytes = sum(work[n_]["amount"] for n_ in pipe.op_names() if n_.startswith("attention"))
+        step_shape["attention_kv_byte_share"] = att_bytes / step_bytes
+    roofline["step"] = step_shape
+    roofline["timed"] = "CUDA events around each launch on its stream in a probed single-stream eager pass right after " \
+                        "the value region (graph replay hides single launches)"
 
     if rank != 0:
         if world > 1:
@@ -863,32 +1095,53 @@ def main():
                                   % (x.shape[0], threads, dtN),
                         "single_thread": {"value": v1, "cores": 1, "sample": "2 scenes, %.1f s" % dt1}}
 
+    def brief(d, keys):
+        return {k: d.get(k) for k in keys} if isinstance(d, dict) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "host_enqueue_ms_per_step": 1e3 * (t_enq - t_wall0) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "npoints": NPOINTS, "feature_channels": 6,
-                   "parallelism": "scene-sharded x%d, no collective" % world, "rank_cpu_affinity": numa, "streams_per_batch": 5 if overlap else 1,
-                   "cuda_graph": use_graph, "input_ring": R, "batches_in_flight": D,
-                   "neighbour_search": "cell grid" if args.grid else "all pairs",
-                   "l2": "inputs larger than L2: one step streams >500 MB (K/V/out tensors) through a 126 MB L2; "
-                         "each step reads a different batch of scenes"},
+        "ms_per_step": ms_block / K, "timed_repeats": reps, "steps_timed": K * reps,
+        "host_enqueue_ms_per_step": 1e3 * enq_s / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": base_config(B, world),
+        "run_config": {"rank_cpu_affinity": numa, "streams_per_batch": 5 if overlap else 1, "cuda_graph": use_graph,
+                       "input_ring": R, "batches_in_flight": D, "neighbour_search": "cell grid" if args.grid else "all pairs",
+                       "min_seconds": args.min_seconds, "lib": os.path.basename(pcops_b200._lib.LIB_PATH)},
         "fps_us_per_scene": {"sa1_batch_latency_us": top_ms * 1e3, "sa1_us_per_scene_throughput": top_ms * 1e3 / B},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K, "result_checksum": checksum},
-        "gpu_launches": pipe.launches_per_step * K * world,
+                "ms_per_step": e2e_block / K, "repeats": e2e_reps, "result_checksum": checksum,
+                "host_enqueue_ms_per_step": 1e3 * e2e_enq / K,
+                "h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
+                "link_floor_ms_per_step": 1e3 * (h2d / (h2d_gbs * 1e9) + d2h / (d2h_gbs * 1e9)) if not args.e2e_legacy else None,
+                "what": ("round-1 path: two fp32 H2D copies, int32 result arena" if args.e2e_legacy else
+                         "one CUDA graph per step: H2D of ONE packed arena (xyz | normals | colours uint8 = 27 B/point), "
+                         "pc_unpack_features, forward, pc_narrow_indices_u16, ONE D2H of the integer decisions (FPS / ball / "
+                         "three_nn indices + counts as uint16; grouped / interpolated tensors stay on the GPU for their "
+                         "on-GPU consumer); h2d_gbs / d2h_gbs = pinned-copy bandwidth with all ranks copying at once, "
+                         "min over ranks")},
+        "gpu_launches": pipe.launches_per_step * K * reps * world,
+        "gpu_launches_e2e": e2e_launches * K * e2e_reps * world,
         "clocks": clocks,
         "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
         "rooflines": rooflines,
         "grid_variants_ms": grid_ms,
+        "gathers_steady_state": steady,
+        "attention_layer_tcgen05": fused_layer,
+        "reference_gpu_kernels": ref_gpu,
+        "config1_single_scene_sa1": config1,
         "with_attention_layers": with_layers,
         "config3_training_step": train,
-        "gathers_steady_state": steady,
         "config4_whole_scene": config4,
-        "config1_single_scene_sa1": config1,
-        "attention_layer_tcgen05": fused_layer,
-        "cpu_baseline": cpu_baseline,
+        "config5_sweep": config5,
     }
+    # the numbers of every config once more, last in the line, so that they survive a truncated log tail
+    line["summary"] = {
+        "config2_value": value, "config2_e2e": e2e_value, "n_gpus": world,
+        "config3": brief(train, ("value", "ms_per_step")),
+        "config4": brief(config4, ("value", "ms_per_scan", "scans_total", "chunker_ms_per_scan", "error")),
+        "config5": brief(config5, ("total_ms", "failed", "error")),
+        "with_attention_layers": brief(with_layers, ("value",)),
+        "roofline_frac": roofline["frac"], "step_hbm_frac": step_shape["step_hbm_frac"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -272,6 +272,19 @@ PC_API int pc_scene_sample_weights(int nchunks, int npoints, const int *desc, co
 PC_API int pc_map_back_winner(size_t rows, int nres, const long long *orig_idx, const unsigned char *mask, int *winner,
                        pc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-boundary packing (csrc/io_pack.cu)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* The feature prologue of the reference's input pipeline (attention_points/train.py:95-98):
+ * feat (rows,6) f32 = concat(float(colors (rows,3) u8) / 255, normals (rows,3) f32).  IEEE fp32 division: the same
+ * bits as tf.div / numpy.  Lets a host ship colours as the bytes they are stored as. */
+PC_API int pc_unpack_features(size_t rows, const unsigned char *colors, const float *normals, float *feat,
+                       pc_stream_t stream);
+/* dst[i] = (uint16) src[i] for index tensors whose values are < 65536 (indices into clouds of at most 65536 points,
+ * pts_cnt <= nsample); values outside [0, 65535] saturate.  Halves the device-to-host bytes of integer results. */
+PC_API int pc_narrow_indices_u16(size_t count, const int *src, unsigned short *dst, pc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ There is NO fallback: if the shared library is missing, or an op is handed a non
 torch is used for device memory and the current stream only.
 """
 import ctypes
+import functools
 import os
 
 import torch
@@ -61,6 +62,8 @@ SIGNATURES = {
     "pc_gather_rows_bytes": (_i, [_sz, _i, _vp, _vp, _vp, _vp]),
     "pc_scene_sample_weights": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_map_back_winner": (_i, [_sz, _i, _vp, _vp, _vp, _vp]),
+    "pc_unpack_features": (_i, [_sz, _vp, _vp, _vp, _vp]),
+    "pc_narrow_indices_u16": (_i, [_sz, _vp, _vp, _vp]),
 }
 
 
@@ -97,7 +100,39 @@ def check(rc, what, invalid_message=None):
 
 
 def stream():
+    """The current stream of the CURRENT device.  Every wrapper that launches runs under on_tensor_device, so the
+    current device is the one its tensor arguments live on."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_devices(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                yield a.device
+        elif isinstance(a, (list, tuple)):
+            for d in _cuda_devices(a):
+                yield d
+
+
+def on_tensor_device(fn):
+    """Decorator of every op wrapper: all CUDA tensor arguments must share ONE device, and the call (stream lookup,
+    workspace allocation, kernel launch, per-device kernel attributes inside libpcops.so) runs with that device
+    current -- not whatever device happens to be current in the calling thread."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = None
+        for d in _cuda_devices(list(args) + list(kw.values())):
+            if dev is None:
+                dev = d
+            elif d != dev:
+                raise PcopsError("%s: all tensor arguments must live on one CUDA device, got %s and %s"
+                                 % (fn.__name__, dev, d))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapped
 
 
 def ptr(t):

@@ -13,6 +13,7 @@ from . import _lib
 
 class _AttentionContract(torch.autograd.Function):
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, Q, K, V, H, D):
         G, S, HD = K.shape
         out = torch.empty((G, HD), dtype=torch.float32, device=K.device)
@@ -24,6 +25,7 @@ class _AttentionContract(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, dout):
         Q, K, V = ctx.saved_tensors
         H, D = ctx.hd
@@ -39,6 +41,7 @@ class _AttentionContract(torch.autograd.Function):
 FUSED_LAYER = True  # AttentionLayer.forward uses pc_attention_layer_fwd where it applies (no-grad, S = 32, C = 64)
 
 
+@_lib.on_tensor_device
 def attention_contract(Q, K, V, num_heads, key_dim):
     """Q (..., HD), K (..., S, HD), V (..., S, HD) -> (..., HD) with HD = num_heads*key_dim."""
     HD = int(num_heads) * int(key_dim)
@@ -53,6 +56,7 @@ def attention_contract(Q, K, V, num_heads, key_dim):
     return out.reshape(*lead, HD)
 
 
+@_lib.on_tensor_device
 def attention_layer_fused(xq, x, wq, bq, wk, bk, wv, bv):
     """The whole AttentionLayer.call (attention_layer.py:29-45) in one tcgen05 kernel (csrc/attention_layer.cu):
     xq (G,C) query rows, x (G,S,C) grouped rows, Dense kernels w* as (C_in, C_out) like Keras, biases (C) or None
@@ -94,6 +98,7 @@ class AttentionLayer(torch.nn.Module):
         self.key_net = torch.nn.Linear(cin, hd)
         self.value_net = torch.nn.Linear(cin, self.output_dim * self.num_heads)
 
+    @_lib.on_tensor_device
     def forward(self, inputs):
         inp, query = inputs
         if self.query_net is None:

@@ -228,7 +228,12 @@ def get_all_subsets_with_all_points_for_scene_numpy_test(points, colors, normals
 def map_back(values, original_idx, mask, res_shape):
     """generate_predictions.py:19-37: res = zeros(res_shape); res[original_idx[mask]] = values[mask] (the last
     occurrence of an index wins, as in numpy).  numpy in -> float64 numpy out like the reference; torch CUDA in ->
-    a CUDA tensor of values' dtype."""
+    a CUDA tensor of values' dtype.
+
+    ``mask`` may have any number of leading dimensions (numpy boolean indexing: it consumes the first ``mask.ndim``
+    dimensions of ``values`` and ``original_idx``), e.g. the (chunks, npoints) arrays the chunker returns.  An index
+    outside [0, res_shape[0]) raises IndexError for numpy inputs, as numpy does; for CUDA tensors the check would cost
+    a host round trip, so such rows are dropped instead (documented difference)."""
     L = _lib.lib()
     as_numpy = isinstance(values, np.ndarray)
     dev = torch.device("cuda", torch.cuda.current_device()) if as_numpy else values.device
@@ -236,12 +241,25 @@ def map_back(values, original_idx, mask, res_shape):
     nres = shape[0]
     with torch.cuda.device(dev):
         v = _dev(values, dev)
-        o = _dev(original_idx, dev).to(torch.int64).contiguous()
-        m = _dev(mask, dev).to(torch.uint8).contiguous()
-        rows = int(o.numel())
-        if v.shape[0] != rows or m.numel() != rows or tuple(v.shape[1:]) != shape[1:]:
+        o = _dev(original_idx, dev)
+        m = _dev(mask, dev)
+        k = m.dim()
+        if tuple(o.shape) != tuple(m.shape):
+            raise IndexError("boolean index did not match indexed array: original_idx has shape %s, mask %s"
+                             % (tuple(o.shape), tuple(m.shape)))
+        if tuple(v.shape[:k]) != tuple(m.shape) or tuple(v.shape[k:]) != shape[1:]:
             raise ValueError("shape mismatch: value array of shape %s could not be broadcast to indexing result"
                              % (tuple(v.shape),))
+        rows = int(m.numel())
+        v = v.reshape((rows,) + tuple(v.shape[k:])).contiguous()
+        o = o.reshape(rows).to(torch.int64).contiguous()
+        m = m.reshape(rows).to(torch.uint8).contiguous()
+        if as_numpy and rows:
+            sel = o[m.bool()]
+            if sel.numel() and (int(sel.max()) >= nres or int(sel.min()) < -nres):
+                raise IndexError("index %d is out of bounds for axis 0 with size %d"
+                                 % (int(sel.max()) if int(sel.max()) >= nres else int(sel.min()), nres))
+            o = torch.where(o < 0, o + nres, o)    # numpy's negative indices
         winner = torch.empty(max(1, nres), dtype=torch.int32, device=dev)
         _lib.check(L.pc_map_back_winner(rows, nres, _lib.ptr(o), _lib.ptr(m), _lib.ptr(winner), _lib.stream()),
                    "map_back_winner")

@@ -18,7 +18,6 @@
 // fp32 pipe needs 512: 8192 points x 8 un-fused flops / 128 lanes), winner resolution + barrier + broadcast ~300-450.
 // A scene cannot go faster on one SM, and splitting it over a cluster buys less than the DSMEM exchange costs at this
 // size -- so throughput comes from running scenes, and batches, side by side.
-#include <stdlib.h>
 #include <cooperative_groups.h>
 #include "common.cuh"
 
@@ -201,8 +200,14 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
 // P/2 packed updates.  After a few dozen samples a centre only touches the 2-3 patches around it, so the fp32 work of a
 // round drops by 3-4x while every output index stays bit-identical (ties use the ORIGINAL index through a slot ->
 // index table in shared memory; the sort order itself never shows in the result).
+// Register cap of the default shape (16 warps x 16 points): the state is 64 registers per thread; ptxas needs 116 when
+// left alone and compiles without spills down to 88.  A lower cap leaves register file on an FPS-occupied SM for
+// co-resident CTAs of the streaming kernels (the FPS round issues in < 50 % of its cycles).
+#ifndef PCOPS_FPS_PRUNED_REGS
+#define PCOPS_FPS_PRUNED_REGS 120
+#endif
 template <int P, int T>
-__global__ void __maxnreg__(T >= 1024 ? 64 : (T >= 512 ? 120 : 200))
+__global__ void __maxnreg__(T >= 1024 ? 64 : (T >= 512 ? PCOPS_FPS_PRUNED_REGS : 200))
 fps_pruned_kernel(int b, int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out,
                   float *__restrict__ out_xyz) {
   extern __shared__ float s_dyn[];                       // xyz (n*3 floats) | hist (4096 ints) | perm (T*P ushorts)
@@ -671,17 +676,12 @@ extern "C" int pc_fps_gather(int b, int n, int m, const float *xyz, void *worksp
     if (n <= 2048) return pc::launch_onchip<16, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     if (n <= 4096) return pc::launch_onchip<32, 128>(b, n, m, xyz, out_idx, out_xyz, st);
     // 4097..8192 points (measured on B200, 16 ScanNet-shaped scenes x 8192 -> 1024, one launch alone):
-    //   default            pruned kernel, 16 warps x 16 points per thread                      539 us
-    //   PCOPS_FPS_SHAPE=256   un-pruned, 8 warps x 32 points, one barrier, 168 registers          645 us
-    //   PCOPS_FPS_SHAPE=512   un-pruned, 16 warps x 16 points, two-barrier tail                   584 us
-    //   PCOPS_FPS_SHAPE=1256  pruned, 8 warps x 32 points                                         618 us
-    // All give the same indices; with 8 batches in flight the whole-pipeline throughput is the same for all four.
-    static int shape = -1;
-    if (shape < 0) { const char *e = getenv("PCOPS_FPS_SHAPE"); shape = e ? atoi(e) : 1512; }
-    if (shape == 1512) return pc::launch_pruned<16, 512>(b, n, m, xyz, out_idx, out_xyz, st);
-    if (shape == 1256) return pc::launch_pruned<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
-    if (shape == 512) return pc::launch_onchip<16, 512, false, 128>(b, n, m, xyz, out_idx, out_xyz, st);
-    return pc::launch_onchip<32, 256>(b, n, m, xyz, out_idx, out_xyz, st);
+    //   pruned kernel, 16 warps x 16 points per thread (this one)                  539 us
+    //   un-pruned, 8 warps x 32 points, one barrier, 168 registers                 645 us
+    //   un-pruned, 16 warps x 16 points, two-barrier tail                          584 us
+    //   pruned, 8 warps x 32 points                                                618 us
+    // All give the same indices.
+    return pc::launch_pruned<16, 512>(b, n, m, xyz, out_idx, out_xyz, st);
   }
   if (n <= pc::kMaxClusterPoints && (long long)b * 16 < 0x7fffffffLL) {  // one cluster of 2 / 4 / 8 / 16 CTAs per scene
     const int slices = (n + pc::kSlice - 1) / pc::kSlice;

@@ -89,8 +89,10 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float v = __ldg(p + k * 3 + c);
-      lo[c] = fminf(lo[c], v);
-      hi[c] = fmaxf(hi[c], v);
+      if (fabsf(v) <= 3.0e38f) {  // non-finite coordinates never hit anything (reference: d < r / d < best is false)
+        lo[c] = fminf(lo[c], v);  // and must not stretch the box: an infinite extent has no cell size
+        hi[c] = fmaxf(hi[c], v);
+      }
     }
   }
 #pragma unroll
@@ -99,7 +101,12 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
     hi[c] = block_reduce(hi[c], true, s_red);
   }
   if (tid == 0) {
-    const float ex = fmaxf(hi[0] - lo[0], 0.f), ey = fmaxf(hi[1] - lo[1], 0.f), ez = fmaxf(hi[2] - lo[2], 0.f);
+    // finite by construction (box over finite coordinates; a scene without any gets a 1-cell grid at the origin)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (!(lo[c] <= hi[c])) lo[c] = hi[c] = 0.f;
+    const float ex = fminf(fmaxf(hi[0] - lo[0], 0.f), 3.0e38f), ey = fminf(fmaxf(hi[1] - lo[1], 0.f), 3.0e38f),
+                ez = fminf(fmaxf(hi[2] - lo[2], 0.f), 3.0e38f);
     float h = min_edge;
     if (mode == 1) {  // ~4 points per cell in volume terms, never finer than the surface / line density suggests: the
       // third neighbour must lie within one cell edge for a lane to be certified without the whole-cloud scan
@@ -108,11 +115,12 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
       h = fmaxf(h, min_edge);
     }
     if (!(h > 0.f) || !isfinite(h)) h = 1.0f;
-    int nx, ny, nz;
-    for (;;) {  // coarsen until the grid fits the histogram
+    int nx = 1, ny = 1, nz = 1;
+    for (int it = 0; it < 1024; ++it) {  // coarsen until the grid fits the histogram (1.25^1024 > FLT_MAX: bounded)
       const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
       if (fx * fy * fz <= (float)kMaxCells) { nx = (int)fx; ny = (int)fy; nz = (int)fz; break; }
       h *= 1.25f;
+      if (!isfinite(h)) { h = 3.0e38f; break; }  // one cell
     }
     s_hdr.ox = lo[0]; s_hdr.oy = lo[1]; s_hdr.oz = lo[2];
     s_hdr.h = h; s_hdr.inv_h = 1.0f / h;

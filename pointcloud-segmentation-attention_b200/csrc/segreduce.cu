@@ -111,17 +111,17 @@ csr_build_kernel(int nkeys, int npos, int W, int part, int nbits, const int *__r
         dst[u] = -1;
         if (act == 0) continue;
         const unsigned peers = same_key_lanes(act, kreg[u], nbits);
-        if (valid) {
+        // full-mask shuffle executed by every lane: a *_sync with a run-time lane mask makes nvcc emit its own MATCH.ANY
+        // convergence check (the very instruction same_key_lanes avoids)
+        const int leader = valid ? __ffs(peers) - 1 : lane;
+        int slot = 0;
+        if (valid && lane == leader) {
           const int key = kreg[u];
-          const int leader = __ffs(peers) - 1;
-          int slot = 0;
-          if (lane == leader) {
-            slot = c[key];
-            c[key] = slot + __popc(peers);
-          }
-          slot = __shfl_sync(peers, slot, leader);
-          dst[u] = slot + __popc(peers & lt);
+          slot = c[key];
+          c[key] = slot + __popc(peers);
         }
+        slot = __shfl_sync(PC_FULL_MASK, slot, leader);
+        if (valid) dst[u] = slot + __popc(peers & lt);
         __syncwarp();  // orders this step's counter stores before the next step's loads
       }
       // the scattered global stores of the batch go out together, AFTER its warp barriers: a barrier with stores in
@@ -291,6 +291,109 @@ csr_reduce_scalar_kernel(int nkeys, int npos, int c, int div, FastDiv fc, FastDi
   }
 }
 
+
+// Entry-stream form of the segmented reduction (the default for c % 32 == 0).  The thread-per-(key, 4 channels) kernels
+// above keep `row length` loads in flight per thread and most rows are short (a ball's real hits: 1-5 entries; only a
+// first-hit key collects ~30), so their memory-level parallelism follows the row-length histogram.  Here a WARP owns KW
+// consecutive keys = ONE contiguous run of list entries [row_ptr[k0], row_ptr[k0+KW]) and walks it as a stream: U
+// contributor rows are in flight per lane at all times, across row boundaries (the next batch's list entries are
+// fetched under the current batch's row loads), and the 32 lanes span 32*V consecutive channels of the row -- one
+// coalesced 128*V-byte segment per contributor.  The additions stay strictly in list order, one accumulator per key,
+// flushed at the row boundary (a warp-uniform compare against the row_ptr values the lanes hold): bit-identical to
+// the serial reference loops.  Empty rows fall out as zero stores of the same flush.
+template <int V, bool WEIGHTED>
+struct VecT;
+template <bool W> struct VecT<4, W> { typedef float4 T; };
+template <bool W> struct VecT<2, W> { typedef float2 T; };
+template <bool W> struct VecT<1, W> { typedef float T; };
+
+template <int V>
+__device__ __forceinline__ void vload(const float *p, float (&v)[V]) {
+  if constexpr (V == 4) { const float4 t = __ldg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else if constexpr (V == 2) { const float2 t = __ldg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
+  else { v[0] = __ldg(p); }
+}
+template <int V>
+__device__ __forceinline__ void vstore(float *p, const float (&v)[V]) {
+  if constexpr (V == 4) *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else if constexpr (V == 2) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+  else *p = v[0];
+}
+
+constexpr int kStreamWarps = 8;
+template <int V, bool WEIGHTED>
+__global__ void __launch_bounds__(kStreamWarps * 32, 3)
+csr_reduce_stream_kernel(int nkeys, int npos, int c, int KW, FastDiv fdiv, const float *__restrict__ src,
+                         const float *__restrict__ w, const int *__restrict__ ws, float *__restrict__ out) {
+  constexpr int U = 8;
+  const int scene = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k0 = (blockIdx.x * kStreamWarps + warp) * KW;
+  if (k0 >= nkeys) return;
+  const int nk = min(KW, nkeys - k0);
+  const int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
+  const int *list = row_ptr + nkeys + 1;
+  const int choff = blockIdx.z * 32 * V + lane * V;
+  const float *s = src + (size_t)scene * (npos / fdiv.d) * c + choff;
+  const float *ww = WEIGHTED ? w + (size_t)scene * npos : nullptr;
+  float *o = out + ((size_t)scene * nkeys + k0) * c + choff;
+  const int rp = row_ptr[k0 + min(lane, nk)];                  // lane l holds the start of local key l (l <= nk)
+  const int E0 = __shfl_sync(PC_FULL_MASK, rp, 0), E1 = __shfl_sync(PC_FULL_MASK, rp, nk);
+  int kk = 0, next_end = __shfl_sync(PC_FULL_MASK, rp, 1);
+  float acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  int pn[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) pn[u] = (E0 + u < E1) ? __ldg(list + E0 + u) : -1;
+  for (int e = E0; e < E1; e += U) {
+    float g[U][V], wt[U];
+    int on[U];
+    // unconditional loads (missing entries re-read position 0): all U issue before the first addition
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      on[u] = pn[u] >= 0;
+      const int pp = on[u] ? pn[u] : 0;
+      vload<V>(s + (size_t)fdiv.div((uint32_t)pp) * c, g[u]);
+      wt[u] = WEIGHTED ? __ldg(ww + pp) : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) pn[u] = (e + U + u < E1) ? __ldg(list + e + U + u) : -1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (on[u]) {                                              // warp-uniform
+        while (e + u == next_end) {                             // row boundary (possibly several empty rows): flush
+          vstore<V>(o + (size_t)kk * c, acc);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = 0.f;
+          ++kk;
+          next_end = __shfl_sync(PC_FULL_MASK, rp, kk + 1);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = __fadd_rn(acc[v], WEIGHTED ? __fmul_rn(g[u][v], wt[u]) : g[u][v]);
+      }
+    }
+  }
+  for (; kk < nk; ++kk) {                                       // the last row and any trailing empty rows
+    vstore<V>(o + (size_t)kk * c, acc);
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  }
+}
+
+template <int V>
+int launch_stream(int b, int nkeys, int npos, int c, int div, const float *src, const float *w, const int *workspace,
+                  float *out, cudaStream_t st) {
+  const int cb = c / (32 * V);
+  // keys per warp: enough warps to fill the chip several times over, never more than 16 keys (a lane holds one start)
+  long long warps_at_1 = (long long)b * nkeys * cb;
+  int KW = (int)(warps_at_1 / ((long long)num_sms() * 48));
+  KW = KW < 1 ? 1 : (KW > 16 ? 16 : KW);
+  dim3 grid((unsigned)((nkeys + KW * kStreamWarps - 1) / (KW * kStreamWarps)), (unsigned)b, (unsigned)cb);
+  if (w) csr_reduce_stream_kernel<V, true><<<grid, kStreamWarps * 32, 0, st>>>(nkeys, npos, c, KW, FastDiv((uint32_t)div), src, w, workspace, out);
+  else   csr_reduce_stream_kernel<V, false><<<grid, kStreamWarps * 32, 0, st>>>(nkeys, npos, c, KW, FastDiv((uint32_t)div), src, w, workspace, out);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
 }  // namespace
 
 size_t csr_workspace_bytes(int b, int nkeys, int npos) {
@@ -325,6 +428,11 @@ int csr_build(int b, int nkeys, int npos, const int *idx, int *workspace, cudaSt
 int csr_reduce(int b, int nkeys, int npos, int c, int div, const float *src, const float *w, const int *workspace,
                float *out, cudaStream_t st) {
   const int sms = num_sms();
+  if (b <= 65535 && c >= 32 && c / 32 <= 65535 * 4) {  // entry-stream kernel: 32 lanes x V floats per channel block
+    if (c % 128 == 0 && aligned16(src) && aligned16(out)) return launch_stream<4>(b, nkeys, npos, c, div, src, w, workspace, out, st);
+    if (c % 64 == 0 && aligned16(src) && aligned16(out)) return launch_stream<2>(b, nkeys, npos, c, div, src, w, workspace, out, st);
+    if (c % 32 == 0) return launch_stream<1>(b, nkeys, npos, c, div, src, w, workspace, out, st);
+  }
   if (c % 4 == 0 && aligned16(src) && aligned16(out)) {
     const size_t total = (size_t)nkeys * (c / 4);
     unsigned gx = (unsigned)((total + 255) / 256);

@@ -36,11 +36,10 @@ KEY_DIM = 4  # attention_layer.py:256-258: heads = C // 4, key_dim = output_dim 
 
 class ScanNetGeometry:
     def __init__(self, batch, npoints=8192, feat_channels=6, device="cuda", attention=True, seed=0, own_streams=False,
-                 grid=True, fuse_gather=True, fuse_layers=False, attention_layers=False):
+                 grid=True, fuse_gather=True, fuse_layers=False, attention_layers=False, parts=("fps", "side")):
         self.B, self.N, self.CF = batch, npoints, feat_channels
-        # development knob (scripts only): which parts of the forward to enqueue, e.g. PCOPS_PIPE_PARTS=fps
-        import os
-        self.parts = os.environ.get("PCOPS_PIPE_PARTS", "fps,side").split(",")
+        # diagnostics only: which parts of the forward to enqueue ("fps": the FPS chain, "side": everything else)
+        self.parts = tuple(parts)
         self.fuse_gather = fuse_gather  # pc_fps_gather instead of pc_fps + pc_gather_point
         # pc_sa_group (group xyz + centre + group features + concat) and pc_fp_interpolate (weights + interpolate)
         # instead of two GroupPoint calls / weights + ThreeInterpolate: what sample_and_group / pointnet_fp_module need.
@@ -76,7 +75,14 @@ class ScanNetGeometry:
         def rnd(*shape):
             return torch.randn(*shape, generator=g, dtype=f32, device=dev)
 
-        self.xyz0 = torch.zeros((batch, npoints, 3), dtype=f32, device=dev)
+        # Packed input arena (host batches, set_inputs_packed): [xyz f32 | normals f32 | colours u8], one H2D copy of
+        # 27 bytes per point; xyz0 IS the arena's first section, feat0 is produced by pc_unpack_features
+        # (colours / 255 | normals, train.py:95-98).  Device-resident callers keep using set_inputs().
+        npts = batch * npoints
+        self._in_arena = torch.zeros(npts * 27 + 16, dtype=torch.uint8, device=dev)
+        self.xyz0 = self._in_arena[:npts * 12].view(f32).view(batch, npoints, 3)
+        self._in_normals = self._in_arena[npts * 12:npts * 24].view(f32).view(batch, npoints, 3)
+        self._in_colors = self._in_arena[npts * 24:npts * 27].view(batch, npoints, 3)
         self.feat0 = torch.zeros((batch, npoints, feat_channels), dtype=f32, device=dev)
         self.levels = []
         n, cin = npoints, feat_channels
@@ -132,6 +138,7 @@ class ScanNetGeometry:
             sum(3 + (2 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps) + \
             (2 * len(self.levels) if self.attention_layers else 0)   # fused layer = operand prep + Q + main kernel
         self._graph = None
+        self._arena16 = None
         self.training = False
 
     # ---- inputs / outputs ----------------------------------------------------------------------------------
@@ -148,6 +155,72 @@ class ScanNetGeometry:
 
     def input_bytes(self):
         return self.xyz0.numel() * 4 + self.feat0.numel() * 4
+
+    # ---- host batches: one packed copy in, one narrowed copy out -------------------------------------------------
+    def packed_input_bytes(self):
+        return self.B * self.N * 27
+
+    @staticmethod
+    def pack_host_batch(xyz, colors_u8, normals, pinned=True):
+        """(B,N,3) f32 xyz, (B,N,3) u8 colours, (B,N,3) f32 normals -> ONE pinned uint8 host arena in the device
+        arena's layout."""
+        npts = xyz.shape[0] * xyz.shape[1]
+        host = torch.empty(npts * 27, dtype=torch.uint8)
+        if pinned:
+            host = host.pin_memory()
+        host[:npts * 12].view(torch.float32).copy_(torch.as_tensor(xyz).reshape(-1))
+        host[npts * 12:npts * 24].view(torch.float32).copy_(torch.as_tensor(normals).reshape(-1))
+        host[npts * 24:].copy_(torch.as_tensor(colors_u8).reshape(-1))
+        return host
+
+    def set_inputs_packed(self, host_arena, non_blocking=True):
+        """ONE host-to-device copy of a pack_host_batch() arena, then the feature prologue on the device."""
+        if self.CF != 6:
+            raise ValueError("the packed input path carries colours + normals (6 feature channels)")
+        st = self.stream()
+        with torch.cuda.stream(st):
+            self._in_arena[:host_arena.numel()].copy_(host_arena, non_blocking=non_blocking)
+            _c(self.L.pc_unpack_features(self.B * self.N, _lib.ptr(self._in_colors), _lib.ptr(self._in_normals),
+                                         _lib.ptr(self.feat0), ctypes.c_void_p(st.cuda_stream)))
+
+    def result_bytes_u16(self):
+        return self._arena_off * 2
+
+    def read_results_u16(self, host_arena_u16, non_blocking=True):
+        """The result arena narrowed to uint16 on the device (every index of this pipeline is < 8192, every count
+        <= 32: lossless) and ONE device-to-host copy of half the bytes."""
+        if self._arena16 is None:
+            self._arena16 = torch.empty(self._arena_off, dtype=torch.int16, device=self.dev)
+        st = self.stream()
+        with torch.cuda.stream(st):
+            _c(self.L.pc_narrow_indices_u16(self._arena_off, _lib.ptr(self._arena), _lib.ptr(self._arena16),
+                                            ctypes.c_void_p(st.cuda_stream)))
+            host_arena_u16.copy_(self._arena16, non_blocking=non_blocking)
+
+    def capture_e2e(self, host_in, host_out_u16, overlap=True):
+        """One CUDA graph for a whole host-to-host step: H2D of the packed batch, feature prologue, the forward,
+        index narrowing, D2H -- a single graph launch per step instead of two copies, two launches and a replay."""
+        if self.npoints_over_u16():
+            raise ValueError("indices do not fit uint16")
+        if self._arena16 is None:
+            self._arena16 = torch.empty(self._arena_off, dtype=torch.int16, device=self.dev)
+        self.set_inputs_packed(host_in)
+        self.forward(overlap)
+        self.read_results_u16(host_out_u16)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        saved, self.main = self.main, None
+        try:
+            with torch.cuda.graph(g, stream=saved):
+                self.set_inputs_packed(host_in)
+                self.forward(overlap)
+                self.read_results_u16(host_out_u16)
+        finally:
+            self.main = saved
+        return g
+
+    def npoints_over_u16(self):
+        return self.N > 65536
 
     def result_tensors(self):
         """The integer geometry decisions of a forward (what a host-side consumer reads back; together with the inputs

@@ -25,6 +25,7 @@ class _SAGroup(torch.autograd.Function):
     (tf_grouping.py:42-46) -- xyz is not differentiated on this path."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, xyz, points, idx, new_xyz):
         b, n, _ = xyz.shape
         _, m, ns = idx.shape
@@ -40,6 +41,7 @@ class _SAGroup(torch.autograd.Function):
         return new_points, grouped_xyz
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, g_new_points, _g_grouped_xyz):
         (idx,) = ctx.saved_tensors
         n, c = ctx.shape
@@ -56,6 +58,7 @@ class _FPInterpolate(torch.autograd.Function):
     tf_interpolate.py:29-34) and points1 (slice)."""
 
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, dist, idx, points2, points1):
         b, n, _ = idx.shape
         m, c2 = points2.shape[1], points2.shape[2]
@@ -70,6 +73,7 @@ class _FPInterpolate(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, g_out):
         idx, weight = ctx.saved_tensors
         m, c2, c1 = ctx.dims
@@ -82,6 +86,7 @@ class _FPInterpolate(torch.autograd.Function):
         return None, None, g2, g1
 
 
+@_lib.on_tensor_device
 def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True):
     """Same inputs / outputs as pointnet_util.py:16-58:
     returns new_xyz (B,npoint,3), new_points (B,npoint,nsample,3+C), idx (B,npoint,nsample), grouped_xyz."""
@@ -110,6 +115,7 @@ def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=Tr
     return new_xyz, new_points, idx, grouped_xyz
 
 
+@_lib.on_tensor_device
 def sample_and_group_all(xyz, points, use_xyz=True):
     """pointnet_util.py:61-87: one group holding every point, centroid (0,0,0)."""
     b, n, _ = xyz.shape
@@ -124,6 +130,7 @@ def sample_and_group_all(xyz, points, use_xyz=True):
     return new_xyz, new_points, idx, grouped_xyz
 
 
+@_lib.on_tensor_device
 def fp_interpolate(xyz1, xyz2, points1, points2):
     """Front half of pointnet_fp_module (pointnet_util.py:218-226): three_nn -> inverse-distance weights ->
     three_interpolate -> concat with the skip features.  Returns (B, n1, C2 [+ C1])."""

@@ -42,6 +42,22 @@ def sum_over_ranks(value, device=None):
     return _reduce(value, dist.ReduceOp.SUM, device)
 
 
+def max_vector_over_ranks(values, device=None):
+    """Element-wise max over ranks of a fixed-length list of floats: ONE collective for a whole optional region (each
+    rank passes -1 where its own measurement failed; see agree_on_region for why the region itself holds none)."""
+    vals = [float(v) for v in values]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not vals:
+        return vals
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    hi = torch.tensor(vals, dtype=torch.float64, device=device)
+    lo = -hi.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MAX)   # -min: an entry that failed anywhere (-1) is reported as failed
+    lo = -lo
+    return [float(h) if float(l) >= 0 else -1.0 for h, l in zip(hi.tolist(), lo.tolist())]
+
+
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

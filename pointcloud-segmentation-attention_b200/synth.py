@@ -84,6 +84,15 @@ def scannet_batch(first_scene, b, n=8192):
     return np.stack(xs, 0), np.stack(fs, 0)
 
 
+def split_features(feats):
+    """(…,6) float32 features of scannet_batch -> (colours uint8 (…,3), normals float32 (…,3)): the storage form of
+    the reference's data set (colours are bytes; train.py:95 divides by 255 after loading).  Exact: the features were
+    made as uint8 / 255 and float32(round(f * 255)) / 255 gives the same bits back (asserted)."""
+    col = np.rint(feats[..., :3] * np.float32(255.0)).astype(np.uint8)
+    assert np.array_equal(col.astype(np.float32) / np.float32(255.0), feats[..., :3])
+    return col, np.ascontiguousarray(feats[..., 3:6])
+
+
 def uniform_cube(seed, *shape):
     return np.random.RandomState(seed).random_sample(shape).astype(np.float32)
 

@@ -6,19 +6,19 @@ gradient (:42-46 -> ``[GroupPointGrad, None]``) and ``knn_point(k, xyz1, xyz2)``
 kernel instead of a TF graph over a (b,m,n,c) tile.  Shape / attribute errors carry the reference OpKernel's
 messages (tf_grouping.cpp:70-74,79-85,112-118,149-157,180-191).
 """
-import os
-
 import torch
 
 from . import _lib
 
 
-# Module switch between the two implementations (identical outputs, tests run both): the all-pairs kernel has the lower
-# single-call latency at PointNet++ sizes (default for these eager wrappers); the cell-grid path issues far fewer
-# instructions and wins when many batches are in flight (pipeline.ScanNetGeometry uses it) or when clouds are large.
-USE_GRID = os.environ.get("PCOPS_USE_GRID", "0") == "1"
+# Module switch between the two implementations (identical outputs, tests run both).  ONE default everywhere -- these
+# wrappers, pipeline.ScanNetGeometry and the TF shim (INTEGRATION.md) all call the cell-grid entry points, which issue
+# far fewer pair tests; set it to False to get the all-pairs kernels behind the reference launchers' exact signatures
+# (slightly lower latency for one small call on an idle GPU).
+USE_GRID = True
 
 
+@_lib.on_tensor_device
 def query_ball_point(radius, nsample, xyz1, xyz2):
     """xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32."""
     if not float(radius) > 0:
@@ -47,6 +47,7 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
+@_lib.on_tensor_device
 def select_top_k(k, dist):
     """dist (b,m,n) -> (outi (b,m,n) i32, out (b,m,n) f32); first k columns are the k smallest."""
     if int(k) <= 0:
@@ -64,6 +65,7 @@ def select_top_k(k, dist):
 
 class _GroupPoint(torch.autograd.Function):
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, points, idx):
         b, n, c = points.shape
         _, m, ns = idx.shape
@@ -75,12 +77,14 @@ class _GroupPoint(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
         n, c = ctx.nc
         return _group_point_grad(n, c, idx, grad_out), None
 
 
+@_lib.on_tensor_device
 def _group_point_grad(n, c, idx, grad_out):
     grad_out = _lib.cuda_f32(grad_out, "grad_out")
     b, m, ns = idx.shape
@@ -93,6 +97,7 @@ def _group_point_grad(n, c, idx, grad_out):
     return gp
 
 
+@_lib.on_tensor_device
 def group_point(points, idx):
     """points (b,n,c) f32, idx (b,m,nsample) i32 -> (b,m,nsample,c)."""
     if points.dim() != 3:
@@ -102,6 +107,7 @@ def group_point(points, idx):
     return _GroupPoint.apply(_lib.cuda_f32(points, "points"), _lib.cuda_i32(idx, "idx"))
 
 
+@_lib.on_tensor_device
 def group_point_grad(points, idx, grad_out):
     """The GroupPointGrad op itself (tf_grouping.cpp:55-63,174-208): `points` is used for its shape only."""
     if points.dim() != 3:
@@ -114,6 +120,7 @@ def group_point_grad(points, idx, grad_out):
     return _group_point_grad(n, c, _lib.cuda_i32(idx, "idx"), grad_out)
 
 
+@_lib.on_tensor_device
 def knn_point(k, xyz1, xyz2):
     """xyz1 (b,n,c) dataset, xyz2 (b,m,c) queries -> (val (b,m,k) f32 squared L2, idx (b,m,k) i32)."""
     if int(k) <= 0:

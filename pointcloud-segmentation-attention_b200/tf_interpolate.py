@@ -7,19 +7,19 @@ Mirrors pointnet2_tensorflow/tf_ops/interpolation_3d/tf_interpolate.py: ``three_
 (tf_interpolate.cpp:163-168,197-206,231-243).  ``three_weights`` is pointnet_fp_module's inverse-distance weighting
 (pointnet_util.py:219-222) as one kernel.
 """
-import os
-
 import torch
 
 from . import _lib
 
 
-# Module switch between the two implementations (identical outputs, tests run both): the all-pairs kernel has the lower
-# single-call latency at PointNet++ sizes (default for these eager wrappers); the cell-grid path issues far fewer
-# instructions and wins when many batches are in flight (pipeline.ScanNetGeometry uses it) or when clouds are large.
-USE_GRID = os.environ.get("PCOPS_USE_GRID", "0") == "1"
+# Module switch between the two implementations (identical outputs, tests run both).  ONE default everywhere -- these
+# wrappers, pipeline.ScanNetGeometry and the TF shim (INTEGRATION.md) all call the cell-grid entry points, which issue
+# far fewer pair tests; set it to False to get the all-pairs kernels behind the reference launchers' exact signatures
+# (slightly lower latency for one small call on an idle GPU).
+USE_GRID = True
 
 
+@_lib.on_tensor_device
 def three_nn(xyz1, xyz2):
     """xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) f32 squared, idx (b,n,3) i32."""
     if xyz1.dim() != 3 or xyz1.shape[2] != 3:
@@ -43,6 +43,7 @@ def three_nn(xyz1, xyz2):
     return dist, idx
 
 
+@_lib.on_tensor_device
 def three_weights(dist):
     """dist (...,3) -> weight (...,3): max(dist,1e-10) -> normalised inverse distances (pointnet_util.py:219-222)."""
     if dist.shape[-1] != 3:
@@ -56,6 +57,7 @@ def three_weights(dist):
 
 class _ThreeInterpolate(torch.autograd.Function):
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, points, idx, weight):
         b, m, c = points.shape
         n = idx.shape[1]
@@ -68,12 +70,14 @@ class _ThreeInterpolate(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, grad_out):
         idx, weight = ctx.saved_tensors
         m, c = ctx.mc
         return _three_interpolate_grad(m, c, idx, weight, grad_out), None, None
 
 
+@_lib.on_tensor_device
 def _three_interpolate_grad(m, c, idx, weight, grad_out):
     grad_out = _lib.cuda_f32(grad_out, "grad_out")
     b, n, _ = idx.shape
@@ -86,6 +90,7 @@ def _three_interpolate_grad(m, c, idx, weight, grad_out):
     return gp
 
 
+@_lib.on_tensor_device
 def three_interpolate(points, idx, weight):
     """points (b,m,c), idx (b,n,3) i32, weight (b,n,3) -> (b,n,c)."""
     if points.dim() != 3:
@@ -99,6 +104,7 @@ def three_interpolate(points, idx, weight):
                                    _lib.cuda_f32(weight.detach(), "weight"))
 
 
+@_lib.on_tensor_device
 def three_interpolate_grad(points, idx, weight, grad_out):
     """The ThreeInterpolateGrad op itself (tf_interpolate.cpp:37-46,225-262): `points` is used for its shape only."""
     if points.dim() != 3:

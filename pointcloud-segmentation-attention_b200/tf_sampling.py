@@ -10,6 +10,7 @@ import torch
 from . import _lib
 
 
+@_lib.on_tensor_device
 def farthest_point_sample(npoint, inp):
     """inp (b,n,3) f32 -> (b,npoint) i32.  FarthestPointSample, tf_sampling.cpp:28-40,95-123."""
     if int(npoint) <= 0:
@@ -26,6 +27,7 @@ def farthest_point_sample(npoint, inp):
     return out
 
 
+@_lib.on_tensor_device
 def farthest_point_sample_and_gather(npoint, inp):
     """farthest_point_sample followed by gather_point on the same cloud (pointnet_util.py:34) in ONE kernel launch:
     inp (b,n,3) -> (idx (b,npoint) i32, new_xyz (b,npoint,3) f32).  No gradient flows to inp (as for FPS)."""
@@ -46,6 +48,7 @@ def farthest_point_sample_and_gather(npoint, inp):
 
 class _GatherPoint(torch.autograd.Function):
     @staticmethod
+    @_lib.on_tensor_device
     def forward(ctx, inp, idx):
         b, n, _ = inp.shape
         m = idx.shape[1]
@@ -57,11 +60,13 @@ class _GatherPoint(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_lib.on_tensor_device
     def backward(ctx, out_g):
         (idx,) = ctx.saved_tensors
         return gather_point_grad_shape(ctx.n, idx, out_g), None
 
 
+@_lib.on_tensor_device
 def gather_point_grad_shape(n, idx, out_g):
     out_g = _lib.cuda_f32(out_g, "out_g")
     b, m = idx.shape
@@ -73,6 +78,7 @@ def gather_point_grad_shape(n, idx, out_g):
     return inp_g
 
 
+@_lib.on_tensor_device
 def gather_point(inp, idx):
     """inp (b,n,3) f32, idx (b,m) i32 -> (b,m,3).  GatherPoint, tf_sampling.cpp:41-54,126-148."""
     if inp.dim() != 3 or inp.shape[2] != 3:
@@ -82,6 +88,7 @@ def gather_point(inp, idx):
     return _GatherPoint.apply(_lib.cuda_f32(inp, "inp"), _lib.cuda_i32(idx, "idx"))
 
 
+@_lib.on_tensor_device
 def gather_point_grad(inp, idx, out_g):
     """The GatherPointGrad op itself (tf_sampling.cpp:55-63,151-178): (inp, idx, out_g) -> inp_g (b,n,3)."""
     if inp.dim() != 3 or inp.shape[2] != 3:
@@ -93,6 +100,7 @@ def gather_point_grad(inp, idx, out_g):
     return gather_point_grad_shape(inp.shape[1], _lib.cuda_i32(idx, "idx"), out_g)
 
 
+@_lib.on_tensor_device
 def prob_sample(inp, inpr):
     """inp (b,ncategory) f32 weights, inpr (b,npoints) f32 uniforms -> (b,npoints) i32.  ProbSample,
     tf_sampling.py:14-23 / tf_sampling.cpp:14-27,66-92; NoGradient (tf_sampling.py:23)."""
@@ -111,6 +119,7 @@ def prob_sample(inp, inpr):
     return out
 
 
+@_lib.on_tensor_device
 def cumsum(inp):
     """(b,n) f32 -> (b,n) cumulative sums in the reference's summation order (cumsumLauncher, tf_sampling_g.cu:193-195)."""
     if inp.dim() != 2:

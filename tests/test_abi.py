@@ -108,3 +108,42 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh", ".cc")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("# oracle-free", ""), os.path.join(dirpath, f)
+
+
+def test_library_reads_no_environment_variables():
+    """include/pcops.h promises a re-entrant library without global knobs: no getenv in the kernel sources (the
+    statically linked CUDA runtime imports the symbol for its own use, so the check is on the sources), no os.environ
+    in the Python package."""
+    pkg = os.path.join(ROOT, "pointcloud-segmentation-attention_b200")
+    for f in os.listdir(os.path.join(pkg, "csrc")):
+        assert "getenv" not in open(os.path.join(pkg, "csrc", f)).read(), f
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert "os.environ" not in open(os.path.join(pkg, f)).read(), f
+
+
+def test_wrappers_reject_tensors_on_different_devices_without_a_gpu():
+    """on_tensor_device only inspects CUDA tensors; on this CPU box the wrapper must still reach its own checks."""
+    import torch
+    with pytest.raises(_lib.PcopsError, match="CUDA tensor"):
+        pcops_b200.gather_point(torch.zeros(1, 4, 3), torch.zeros(1, 2, dtype=torch.int32))
+
+
+@pytest.mark.gpu
+def test_ops_run_on_the_device_of_their_tensors_not_the_current_one():
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import cpu, synth
+    xyz, _ = synth.scannet_batch(5, 2, 1024)
+    torch.cuda.set_device(0)
+    x1 = torch.from_numpy(xyz).to("cuda:1")
+    idx = pcops_b200.farthest_point_sample(64, x1)
+    assert idx.device == x1.device and np.array_equal(idx.cpu().numpy(), cpu.farthest_point_sample(64, xyz))
+    nx = pcops_b200.gather_point(x1, idx)
+    bi, _ = pcops_b200.query_ball_point(0.3, 16, x1, nx)
+    assert np.array_equal(bi.cpu().numpy(), cpu.query_ball_point(0.3, 16, xyz, nx.cpu().numpy())[0])
+    with pytest.raises(_lib.PcopsError, match="one CUDA device"):
+        pcops_b200.gather_point(x1, idx.to("cuda:0"))
+    assert torch.cuda.current_device() == 0

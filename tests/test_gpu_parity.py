@@ -186,7 +186,7 @@ def test_ball_query_matches_reference_cuda_kernel(refgpu):
 
 
 # ---------------------------------------------------------------------------------------- group_point (a5, a6)
-@pytest.mark.parametrize("c", [1, 3, 6, 9, 64, 128, 256, 512])
+@pytest.mark.parametrize("c", [1, 3, 6, 9, 32, 64, 96, 128, 192, 256, 512])
 def test_group_point_and_grad_match_oracle(c):
     n, m, ns = 600, 130, 32
     xyz = synth.uniform_cube(c, 2, n, 3)
@@ -235,6 +235,28 @@ def test_group_point_grad_popular_point_and_big_key_range():
     go = synth.features(3, b, m, ns, c)
     pts = np.zeros((b, n, c), np.float32)
     assert same(ops.group_point_grad(cu(pts), cu(idx), cu(go)), cpu.group_point_grad(pts, idx, go))
+
+
+def test_gradients_at_bench_shapes_many_keys_per_warp():
+    """The entry-stream reduce gives a warp KW = 1..16 consecutive keys depending on the size of the launch; the
+    small shapes above all run with KW = 1.  Bench shapes (B = 16): SA1-like 8192 keys (KW = 16, most rows empty or
+    1-5 entries, first-hit keys ~30), SA2 (KW = 2), FP4 interpolation gradient (weighted form, KW = 2)."""
+    b = 16
+    xyz, _ = synth.scannet_batch(40, b, 8192)
+    fi = cpu.farthest_point_sample(1024, xyz, omp=True)
+    nx = cpu.gather_point(xyz, fi)
+    for (cloud, q, r, c) in ((xyz, nx, 0.1, 64), (nx, nx[:, :256].copy(), 0.2, 64), (nx, nx[:, :256].copy(), 0.2, 128)):
+        idx, _ = cpu.query_ball_point(r, 32, cloud, q, omp=True)
+        go = synth.features(c, b, q.shape[1], 32, c)
+        pts = np.zeros((b, cloud.shape[1], c), np.float32)
+        assert same(ops.group_point_grad(cu(pts), cu(idx), cu(go)), cpu.group_point_grad(pts, idx, go, omp=True))
+    od, oi = cpu.three_nn(xyz, nx, omp=True)
+    ow = cpu.three_weights(od)
+    for c in (128, 64, 32):
+        go = synth.features(c + 3, b, 8192, c)
+        pts = np.zeros((b, 1024, c), np.float32)
+        assert same(ops.three_interpolate_grad(cu(pts), cu(oi), cu(ow), cu(go)),
+                    cpu.three_interpolate_grad(pts, oi, ow, go, omp=True))
 
 
 # ------------------------------------------------------------------------------------ selection sort / kNN (a7)
@@ -466,6 +488,26 @@ def test_grid_paths_on_adversarial_clouds():
     nx = cpu.gather_point(xyz, fi)
     for r in (0.1, 0.2, 0.4, 0.8):
         _check_ball_and_nn(xyz, nx, r, 32)
+
+
+@pytest.mark.timeout(300)
+def test_non_finite_and_huge_coordinates_do_not_hang_and_match_the_oracle():
+    """A +/-inf, NaN or 1e30 coordinate used to make grid_build_kernel's coarsening loop spin for ever (the extent was
+    inf, so no cell size ever fitted); the reference and the all-pairs kernels simply never hit such points."""
+    rng = np.random.default_rng(9)
+    for bad in (np.inf, -np.inf, 1e30, -3e38, np.nan):
+        u = rng.random((2, 400, 3)).astype(np.float32)
+        q = rng.random((2, 64, 3)).astype(np.float32)
+        u[0, 7, 1] = bad
+        u[1, 399, 0] = bad
+        u[1, 100] = bad
+        q[0, 3, 2] = bad
+        with np.errstate(all="ignore"):
+            _check_ball_and_nn(u, q, 0.15, 16)
+    # a scene without a single finite coordinate
+    u = np.full((1, 96, 3), np.inf, np.float32)
+    with np.errstate(all="ignore"):
+        _check_ball_and_nn(u, rng.random((1, 40, 3)).astype(np.float32), 0.2, 8)
 
 
 # -------------------------------------------------------------------- fused layer front ends (csrc/fused.cu)

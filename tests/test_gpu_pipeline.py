@@ -130,3 +130,37 @@ def test_pipeline_with_whole_attention_layers():
     torch.cuda.synchronize()
     for lv, a in zip(pipe.levels[1:], eager):
         assert torch.equal(lv["att"], a)
+
+
+def test_packed_host_batch_and_narrowed_results_are_lossless():
+    """The end-to-end path of bench.py: one packed pinned input arena (xyz | normals | colours as uint8, 27 bytes per
+    point; the / 255 of train.py:95 runs on the device) and the integer results narrowed to uint16 before the
+    device-to-host copy -- same features bit for bit, same indices, eager and as ONE captured graph per step."""
+    B = 2
+    xyz_np, feat_np = synth.scannet_batch(700, B, 8192)
+    col, nrm = synth.split_features(feat_np)
+    pipe = ScanNetGeometry(B, own_streams=True)
+    host_in = ScanNetGeometry.pack_host_batch(xyz_np, col, nrm)
+    assert host_in.is_pinned() and host_in.numel() == pipe.packed_input_bytes() == B * 8192 * 27
+    pipe.set_inputs_packed(host_in)
+    pipe.forward(overlap=True)
+    host16 = torch.empty(pipe.result_arena().numel(), dtype=torch.int16).pin_memory()
+    pipe.read_results_u16(host16)
+    torch.cuda.synchronize()
+    assert np.array_equal(npy(pipe.xyz0), xyz_np) and np.array_equal(npy(pipe.feat0), feat_np)
+    check_against_oracle(pipe, xyz_np, feat_np)
+    want = npy(pipe.result_arena())
+    assert want.min() >= 0 and want.max() < 65536
+    assert np.array_equal(host16.numpy().view(np.uint16).astype(np.int32), want)
+    assert pipe.result_bytes_u16() * 2 == pipe.result_arena().numel() * 4
+    # the whole host-to-host step as one graph, on a different batch
+    xyz2, feat2 = synth.scannet_batch(800, B, 8192)
+    col2, nrm2 = synth.split_features(feat2)
+    host_in2 = ScanNetGeometry.pack_host_batch(xyz2, col2, nrm2)
+    g = pipe.capture_e2e(host_in2, host16)
+    host16.zero_()
+    with torch.cuda.stream(pipe.stream()):
+        g.replay()
+    torch.cuda.synchronize()
+    check_against_oracle(pipe, xyz2, feat2)
+    assert np.array_equal(host16.numpy().view(np.uint16).astype(np.int32), npy(pipe.result_arena()))

@@ -120,6 +120,17 @@ def test_chunker_matches_oracle_on_a_full_size_scan_device_tensors():
     m = torch.tensor([1, 1, 1, 1, 0, 1], dtype=torch.bool, device=dev)
     want = oracle_sc.map_back(vals.cpu().numpy(), o.cpu().numpy(), m.cpu().numpy(), (4,))
     assert np.array_equal(csl.map_back(vals, o, m, (4,)).cpu().numpy(), want.astype(np.float32))
+    # N-D masks, exactly the (chunks, npoints) arrays the chunker returns (numpy boolean indexing consumes mask.ndim
+    # leading dimensions), numpy in -> float64 numpy out; an out-of-range index raises like numpy
+    pts_np, m_np, o_np = got[0].cpu().numpy(), got[5].cpu().numpy(), got[6].cpu().numpy()
+    want = oracle_sc.map_back(pts_np.reshape(-1, 3), o_np.reshape(-1), m_np.reshape(-1), (len(p), 3))
+    got_nd = csl.map_back(pts_np, o_np, m_np, (len(p), 3))
+    assert got_nd.dtype == np.float64 and np.array_equal(got_nd, want)
+    assert torch.equal(csl.map_back(got[0], got[6], got[5], (len(p), 3)).cpu(), torch.from_numpy(p))
+    with pytest.raises(IndexError):
+        csl.map_back(np.ones(3, np.float32), np.array([0, 9, 1]), np.array([True, True, True]), (4,))
+    with pytest.raises(IndexError):
+        csl.map_back(np.ones((2, 3), np.float32), np.zeros(6, np.int64), np.ones((2, 3), bool), (4,))
 
 
 @pytest.mark.gpu

@@ -80,6 +80,10 @@ def _region_worker(rank, world, port, out):
         pass
     slowest, ok = agree_on_region(local)
     slowest2, ok2 = agree_on_region(3.0 + rank)      # a second region in which every rank succeeds
+    # a whole sweep in ONE collective: entry 1 failed on rank 1 only -> reported as failed, the others as the max
+    from importlib import import_module
+    vec = import_module("pcops_b200.sharding").max_vector_over_ranks([1.0 + rank, -1.0 if rank == 1 else 7.0, 2.0 - rank])
+    assert vec == [2.0, -1.0, 2.0], vec
     if rank == 0:
         out.put((slowest, ok, slowest2, ok2))
     dist.destroy_process_group()
@@ -99,6 +103,12 @@ def test_a_rank_local_failure_in_an_optional_region_cannot_deadlock():
     slowest, ok, slowest2, ok2 = q.get()
     assert ok is False and slowest == 5.0
     assert ok2 is True and slowest2 == 4.0
+
+
+def test_vector_reduce_single_process():
+    from pcops_b200.sharding import max_vector_over_ranks
+    assert max_vector_over_ranks([1.5, -1.0]) == [1.5, -1.0]
+    assert max_vector_over_ranks([]) == []
 
 
 def test_agree_on_region_single_process():

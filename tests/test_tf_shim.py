@@ -39,8 +39,36 @@ def parse_registry():
     return reg
 
 
+REF_TF_OPS = "/root/reference/pointnet2_tensorflow/tf_ops"
+REF_SOURCES = ("sampling/tf_sampling.cpp", "grouping/tf_grouping.cpp", "interpolation_3d/tf_interpolate.cpp")
+
+
+def parse_reference_registry():
+    """The op registry as the reference's own sources state it (REGISTER_OP blocks of tf_sampling.cpp:14-63,
+    tf_grouping.cpp:13-63, tf_interpolate.cpp:12-46), parsed where /root/reference is mounted."""
+    reg = {}
+    for f in REF_SOURCES:
+        text = open(os.path.join(REF_TF_OPS, f)).read()
+        for m in re.finditer(r'REGISTER_OP\("(\w+)"\)(.*?)\.SetShapeFn', text, re.S):
+            body = m.group(2)
+            reg[m.group(1)] = (re.findall(r'\.Attr\("([^"]+)"\)', body), re.findall(r'\.Input\("([^"]+)"\)', body),
+                               re.findall(r'\.Output\("([^"]+)"\)', body))
+    return reg
+
+
 def test_shim_registers_the_reference_ops_exactly():
     assert parse_registry() == REFERENCE_REGISTRY
+
+
+def test_hand_typed_registry_equals_the_one_parsed_from_the_reference_sources():
+    """REFERENCE_REGISTRY above travels to the GPU box (no /root/reference there); here, where the reference is
+    mounted, it is checked against the REGISTER_OP blocks of the reference's own .cpp files, and so is the shim."""
+    import pytest
+    if not os.path.isdir(REF_TF_OPS):
+        pytest.skip("/root/reference is not mounted")
+    ref = parse_reference_registry()
+    assert ref == REFERENCE_REGISTRY
+    assert parse_registry() == ref
 
 
 def test_every_registered_op_has_a_gpu_kernel_calling_the_c_abi():
