@@ -7,7 +7,7 @@
 A "step" is one pass of the hot path over one batch of B=16 synthetic 8192-point ScanNet-shaped chunks (xyz + 6
 feature channels), BASELINE.json configs[1] plus the attention contraction the metric names: per SA level
 FPS -> gather_point -> query_ball_point -> group_point(xyz) -> group_point(features) -> attention contraction, per FP
-level three_nn -> weights -> three_interpolate (36 reference-signature op calls; 46 kernel launches with the cell-grid
+level three_nn -> weights -> three_interpolate (36 reference-signature op calls; 39 kernel launches with the cell-grid
 neighbour search and the fused FPS+gather; pointcloud-segmentation-attention_b200/pipeline.py).
 
 Own arm (default).  One process per GPU, scenes sharded by rank, no data-path collective (weak scaling).  Prints ONE
@@ -531,30 +531,37 @@ def np_arange_mod(n, b):
 def run_config5(torch, args, rank, world, dev, sharding, fp32_peak_tops):
     """BASELINE config 5: geometry-op scaling sweep -- FPS, ball query, kNN at N = 16k ... 1M points, npoint 1k ... 16k,
     B = --sweep-batch (64) scenes sharded over the ranks (uniform clouds, radius chosen for ~32 expected neighbours,
-    nsample = k = 32).  Every entry is ONE launch after a cheap warm-up launch of the same kernel (m = 2), timed with
-    CUDA events on the launching stream; a 512 MB write between entries flushes L2.  Contains NO collective: the
+    nsample = k = 32).  Every entry is ONE call through the C ABI with pre-allocated outputs and workspaces (no
+    allocation inside the timed region), after a cheap warm-up call of the same kernel (2 samples / 32 queries), timed
+    with CUDA events on the launching stream; a 512 MB write between entries flushes L2.  Contains NO collective: the
     per-entry times of all ranks are reduced in one call afterwards (max over ranks)."""
+    import ctypes
     import pcops_b200 as ops
+    L, p, ws_of = ops._lib.lib(), ops._lib.ptr, ops._lib.workspace
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     Bt = args.sweep_batch
     lo, hi = sharding.shard_bounds(Bt, rank, world)
     b = hi - lo
     entries, times = [], []
     flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev).manual_seed(1000 + lo)
+    f32, i32 = torch.float32, torch.int32
 
     def timed(fn):
         flush.fill_(0.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = fn()
+        rc = fn()
         e1.record()
         torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1), out
+        if rc != 0:
+            raise RuntimeError("pcops rc %d" % rc)
+        return e0.elapsed_time(e1)
 
     for N in (16384, 65536, 262144, 1048576):
         if N > args.sweep_max_n:
             continue
-        x = torch.rand((max(b, 1), N, 3), generator=g, device=dev) if b > 0 else None
+        x = torch.rand((b, N, 3), generator=g, device=dev) if b > 0 else None
         r = (32.0 / N * 3.0 / (4.0 * 3.14159265)) ** (1.0 / 3.0)
         for m in (1024, 4096, 16384):
             for op in ("fps", "ball", "knn"):
@@ -563,25 +570,32 @@ def run_config5(torch, args, rank, world, dev, sharding, fp32_peak_tops):
                 times += [0.0, 0.0, 0.0]
                 continue
             try:
-                ops.farthest_point_sample_and_gather(2, x)                     # warm-up (attributes, code load)
-                t_fps, (fi, q) = timed(lambda: ops.farthest_point_sample_and_gather(m, x))
+                fi = torch.empty((b, m), dtype=i32, device=dev)
+                q = torch.empty((b, m, 3), dtype=f32, device=dev)
+                fws = ws_of(L.pc_fps_workspace_bytes(b, N, m), dev)
+                idx = torch.empty((b, m, 32), dtype=i32, device=dev)
+                cnt = torch.empty((b, m), dtype=i32, device=dev)
+                bws = ws_of(L.pc_query_ball_grid_workspace_bytes(b, N, m), dev)
+                val = torch.empty((b, m, 32), dtype=f32, device=dev)
+                L.pc_fps_gather(b, N, 2, p(x), p(fws), p(fi), p(q), st)              # warm-up (attributes, code load)
+                t_fps = timed(lambda: L.pc_fps_gather(b, N, m, p(x), p(fws), p(fi), p(q), st))
             except Exception:
                 times += [-1.0, -1.0, -1.0]
                 continue
             times.append(t_fps)
             try:
-                ops.query_ball_point(r, 32, x, q[:, :32].contiguous())
-                t_ball, _ = timed(lambda: ops.query_ball_point(r, 32, x, q))
+                L.pc_query_ball_grid(b, N, 32, r, 32, p(x), p(q), p(idx), p(cnt), p(bws), st)
+                t_ball = timed(lambda: L.pc_query_ball_grid(b, N, m, r, 32, p(x), p(q), p(idx), p(cnt), p(bws), st))
             except Exception:
                 t_ball = -1.0
             times.append(t_ball)
             try:
-                ops.knn_point(32, x, q[:, :32].contiguous())
-                t_knn, _ = timed(lambda: ops.knn_point(32, x, q))
+                L.pc_knn(b, N, 32, 32, 3, p(x), p(q), p(val), p(idx), st)
+                t_knn = timed(lambda: L.pc_knn(b, N, m, 32, 3, p(x), p(q), p(val), p(idx), st))
             except Exception:
                 t_knn = -1.0
             times.append(t_knn)
-            del fi, q
+            del fi, q, fws, idx, cnt, bws, val
         del x
         torch.cuda.empty_cache()
     del flush
@@ -604,9 +618,10 @@ def finish_config5(entries, times, Bt, world, fp32_peak_tops):
     return {"workload": "config 5: FPS / ball query (r for ~32 neighbours, nsample 32) / kNN (k 32) on uniform clouds, "
                         "B=%d scenes sharded over %d GPU(s); one launch each, max over ranks; frac_fp32 = algorithmic "
                         "pair tests x 10 (FPS) or 11 flops / whole-job un-fused fp32 peak" % (Bt, world),
-            "paths": "FPS: one 2..16-CTA cluster per scene up to 262144 points (state on chip), beyond that one CTA per "
-                     "scene streaming the running minima through L2; ball query: all-pairs kernel with early exit "
-                     "above 21088 points (the per-query bitmap of the cell-grid kernel no longer fits shared memory); "
+            "paths": "FPS: one 2..16-CTA cluster per scene up to 262144 points (state on chip, DSMEM exchange), beyond that "
+                     "a cooperative grid of 16384-point CTAs (state on chip, winners exchanged through global memory); "
+                     "ball query: cell grid up to 21088 points (frac_fp32 may exceed 1: pruned pairs), all-pairs kernel "
+                     "above (the per-query bitmap over original indices no longer fits shared memory); "
                      "kNN: fused two-pass kernel, no (b,m,n) matrix",
             "rows": rows, "total_ms": sum(r["ms"] for r in ok), "failed": len(rows) - len(ok)}
 

@@ -42,7 +42,7 @@ struct BallSmem {
 };
 
 __global__ void __launch_bounds__(kSeg * 32, 2)
-ball_query_kernel(int n, int m, float s_star, int nsample, float one, const float *__restrict__ xyz1,
+ball_query_kernel(int n, int m, float s_star, float radius, int nsample, float one, const float *__restrict__ xyz1,
                   const float *__restrict__ xyz2, int *__restrict__ idx, int *__restrict__ pts_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BallSmem &sm = *reinterpret_cast<BallSmem *>(smem_raw);
@@ -57,17 +57,20 @@ ball_query_kernel(int n, int m, float s_star, int nsample, float one, const floa
   bool live[kQ];
   f32x2 qx2[kQ], qy2[kQ], qz2[kQ];
   int *row[kQ];
+  bool qbad = false;  // a non-finite query coordinate: distances may be NaN, which the reference COUNTS as a hit
 #pragma unroll
   for (int u = 0; u < kQ; ++u) {
     q[u] = blockIdx.x * kQPB + u * 32 + lane;
     live[u] = q[u] < m;
     const float *qp = xyz2 + ((size_t)scene * m + (live[u] ? q[u] : 0)) * 3;
+    qbad = qbad || !(fabsf(qp[0]) < inf) || !(fabsf(qp[1]) < inf) || !(fabsf(qp[2]) < inf);
     qx2[u] = pack2(qp[0], qp[0]); qy2[u] = pack2(qp[1], qp[1]); qz2[u] = pack2(qp[2], qp[2]);
     row[u] = idx + ((size_t)scene * m + (live[u] ? q[u] : 0)) * nsample;
     total[u] = live[u] ? 0 : nsample;  // hits in all earlier chunks (dead slots count as full)
     first[u] = INT_MAX;                // first hit so far (absolute index)
   }
   float(*st)[kStageRow] = sm.stage[warp];
+  const bool warp_qbad = __any_sync(PC_FULL_MASK, qbad);
 
   for (int c0 = 0; c0 < n; c0 += kChunk) {
     const int cn = min(kChunk, n - c0);
@@ -80,13 +83,17 @@ ball_query_kernel(int n, int m, float s_star, int nsample, float one, const floa
     // the current one is being tested, so global latency never stalls the warp.
     constexpr int kLoads = kStage * 3 / 32;
     float pre[kLoads];
+    bool pre_bad = false;  // a non-finite candidate coordinate among this lane's fetched values
     auto fetch = [&](int t0) {
       const int tn = min(kStage, s_hi - t0);
       const float *src = data + (size_t)(c0 + t0) * 3;
+      pre_bad = false;
 #pragma unroll
       for (int u = 0; u < kLoads; ++u) {
         const int i = lane + 32 * u;
-        pre[u] = (i < tn * 3) ? __ldg(src + i) : inf;  // slots past tn become +inf (never hit)
+        const bool in = i < tn * 3;
+        pre[u] = in ? __ldg(src + i) : inf;  // slots past tn become +inf (never hit)
+        pre_bad = pre_bad || (in && !(fabsf(pre[u]) < inf));
       }
     };
     if (s_lo < s_hi) fetch(s_lo);
@@ -99,6 +106,10 @@ ball_query_kernel(int n, int m, float s_star, int nsample, float one, const floa
         const int i = lane + 32 * u, k = i / 3, c = i - k * 3;
         st[c][k] = pre[u];
       }
+      // Non-finite coordinates (never in real clouds): the reference's test is max(sqrtf(d2),1e-20f) < radius with
+      // CUDA's max = fmaxf (tf_grouping_g.cu:24), which turns a NaN distance into 1e-20 -- a HIT -- so the bit-pattern
+      // compare below (NaN never hits) is replaced for this stage by the literal expression, candidate by candidate.
+      const bool exact = warp_qbad || __any_sync(PC_FULL_MASK, pre_bad);
       __syncwarp();
       if (t0 + kStage < s_hi) fetch(t0 + kStage);
       const int nwords = (tn + 31) / 32;
@@ -106,6 +117,19 @@ ball_query_kernel(int n, int m, float s_star, int nsample, float one, const floa
         unsigned word[kQ];
 #pragma unroll
         for (int u = 0; u < kQ; ++u) word[u] = 0;
+        if (exact) {
+          for (int e = 0; e < 32; ++e) {
+            const int k = w * 32 + e;
+            if (k >= tn) break;
+#pragma unroll
+            for (int u = 0; u < kQ; ++u) {
+              float qx, qy, qz, dup;
+              unpack2(qx2[u], qx, dup); unpack2(qy2[u], qy, dup); unpack2(qz2[u], qz, dup);
+              const float d2 = sqdist3(qx, qy, qz, st[0][k], st[1][k], st[2][k]);
+              if (fmaxf(sqrtf(d2), 1e-20f) < radius) word[u] |= 0x80000000u >> e;  // bit 31-e, as the fast path
+            }
+          }
+        } else
 #pragma unroll
         for (int g = 0; g < 8; ++g) {  // 4 candidates per step
           const int k = w * 32 + g * 4;
@@ -215,6 +239,6 @@ extern "C" int pc_query_ball(int b, int n, int m, float radius, int nsample, con
   const size_t smem = sizeof(pc::BallSmem);
   PC_CUDA_TRY(pc::allow_smem(pc::ball_query_kernel, smem));
   dim3 grid((m + pc::kQPB - 1) / pc::kQPB, b);
-  pc::ball_query_kernel<<<grid, pc::kSeg * 32, smem, st>>>(n, m, s_star, nsample, 1.0f, xyz1, xyz2, idx, pts_cnt);
+  pc::ball_query_kernel<<<grid, pc::kSeg * 32, smem, st>>>(n, m, s_star, radius, nsample, 1.0f, xyz1, xyz2, idx, pts_cnt);
   PC_RETURN_LAUNCH_STATUS();
 }

@@ -202,9 +202,11 @@ fps_onchip_kernel(int b, int n, int m, float one, const float *__restrict__ xyz,
 // index table in shared memory; the sort order itself never shows in the result).
 // Register cap of the default shape (16 warps x 16 points): the state is 64 registers per thread; ptxas needs 116 when
 // left alone and compiles without spills down to 88.  A lower cap leaves register file on an FPS-occupied SM for
-// co-resident CTAs of the streaming kernels (the FPS round issues in < 50 % of its cycles).
+// co-resident CTAs of the streaming kernels (the FPS round issues in < 50 % of its cycles).  Measured on B200, 8 batches
+// in flight: cap 120 -> 61.0 k scenes/s (FPS alone 543 us), 96 -> 63.0 k (553 us), 88 -> 63.9 k (567 us): the lone
+// launch gets 4 % slower, the pipeline 5 % faster.
 #ifndef PCOPS_FPS_PRUNED_REGS
-#define PCOPS_FPS_PRUNED_REGS 120
+#define PCOPS_FPS_PRUNED_REGS 88
 #endif
 template <int P, int T>
 __global__ void __maxnreg__(T >= 1024 ? 64 : (T >= 512 ? PCOPS_FPS_PRUNED_REGS : 200))
@@ -416,19 +418,29 @@ constexpr int kSlice = 8192;
 constexpr int kMaxClusterPoints = 16 * 16384;
 struct __align__(16) FpsRec { int value, key; float x, y; float z; int pad[3]; };
 
+// CL > 0: one cluster of CL CTAs per scene, records exchanged through distributed shared memory (above).
+// CL == 0 (n > 262144): `cps` CTAs per scene in a COOPERATIVE launch (all resident), records exchanged through global
+// memory: CTA r publishes its (value, key, x, y, z) record of round j as three 8-byte words in grec[scene][parity][r],
+// the last one carrying the round number with release semantics; warp 0 of every CTA polls the cps records of the
+// round with acquire loads, reduces them and hands the next centre to the CTA through shared memory.  Slot reuse two
+// rounds later is safe for the same reason as in the cluster protocol: nobody can publish round j+2 before it has
+// read every peer's round j+1 record, which that peer wrote after reading round j.  One L2 round trip (~1.5 us) per
+// round instead of streaming 16 n bytes of running minima through L2 (fps_stream_kernel): N = 1 M points, m = 1024,
+// 64 scenes 730 ms -> see DESIGN.md.
 template <int CL, int P, int PS>
 __global__ void __maxnreg__((PS > 0) ? 255 : 200)
 fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *__restrict__ out,
-                   float *__restrict__ out_xyz) {
+                   float *__restrict__ out_xyz, int cps, int scene0, unsigned long long *__restrict__ grec) {
   constexpr int T = 256, H = P / 2, HR = (P - PS) / 2, G = 8, NG = P / G, nwarps = T / 32, kSlice = P * T;
+  constexpr bool kGlobal = (CL == 0);
   using Map = FpsMap<P, T>;
   extern __shared__ float s_xyz[];  // this CTA's slice, up to kSlice * 3
   __shared__ int2 s_pair[2][32];
   __shared__ FpsRec s_rec[2][16];
   __shared__ __align__(8) uint64_t s_mb[2];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int scene = blockIdx.x / CL;
+  __shared__ float s_next[4];       // kGlobal: next centre (x, y, z) and its index, written by warp 0
+  const int rank = kGlobal ? (int)(blockIdx.x % (unsigned)cps) : (int)cg::this_cluster().block_rank();
+  const int scene = kGlobal ? scene0 + (int)(blockIdx.x / (unsigned)cps) : (int)(blockIdx.x / (CL > 0 ? CL : 1));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const f32x2 one2 = pack2(one, one);
   const float *p = xyz + (size_t)scene * n * 3;
@@ -464,12 +476,16 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
     if (h < HR) { px[h] = pack2(x[0], x[1]); py[h] = pack2(y[0], y[1]); pz[h] = pack2(z[0], z[1]); }
   }
   const uint32_t mb_local[2] = {(uint32_t)__cvta_generic_to_shared(&s_mb[0]), (uint32_t)__cvta_generic_to_shared(&s_mb[1])};
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_local[0]), "r"(1u));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_local[1]), "r"(1u));
-    asm volatile("fence.mbarrier_init.release.cluster;");
+  if constexpr (!kGlobal) {
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_local[0]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb_local[1]), "r"(1u));
+      asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    cg::this_cluster().sync();  // every CTA's s_rec / s_mb is initialised and addressable before the first remote store
   }
-  cluster.sync();  // every CTA's s_rec / s_mb is initialised and addressable before the first remote store
+  unsigned long long *myrec = nullptr;
+  if constexpr (kGlobal) myrec = grec + (size_t)(scene - scene0) * 2 * cps * 3;  // [parity][cps][3 words] per scene
 
   int par = 1;
   for (int j = 1; j < m; ++j) {
@@ -517,6 +533,54 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
     const int2 pr = s_pair[par][lane < nwarps ? lane : 0];
     const int cmax = __reduce_max_sync(PC_FULL_MASK, pr.x);
     const int ckey = __reduce_min_sync(PC_FULL_MASK, pr.x == cmax ? pr.y : INT_MAX);
+    if constexpr (kGlobal) {
+      unsigned long long *slot = myrec + (size_t)par * cps * 3;
+      if (tid == 0) {
+        int rx = 0, ry = 0, rz = 0;
+        if (cmax >= 0) {
+          const int kl = tie_key_to_index(ckey) - base;
+          rx = __float_as_int(s_xyz[kl * 3 + 0]); ry = __float_as_int(s_xyz[kl * 3 + 1]); rz = __float_as_int(s_xyz[kl * 3 + 2]);
+        }
+        unsigned long long *w = slot + (size_t)rank * 3;
+        w[0] = ((unsigned long long)(unsigned)cmax << 32) | (unsigned)ckey;
+        w[1] = ((unsigned long long)(unsigned)rx << 32) | (unsigned)ry;
+        const unsigned long long w2 = ((unsigned long long)(unsigned)rz << 32) | (unsigned)j;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(w + 2), "l"(w2) : "memory");
+      }
+      if (warp == 0) {
+        int bv = INT_MIN, bk = INT_MAX;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        for (int r = lane; r < cps; r += 32) {
+          const unsigned long long *w = slot + (size_t)r * 3;
+          unsigned long long w2;
+          unsigned spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w2) : "l"(w + 2) : "memory");
+            if ((unsigned)w2 != (unsigned)j && ++spins > (1u << 24)) __trap();
+          } while ((unsigned)w2 != (unsigned)j);
+          const unsigned long long w0 = __ldcg(w), w1 = __ldcg(w + 1);  // L2, ordered after the acquire
+          const int v = (int)(w0 >> 32), k = (int)(unsigned)w0;
+          if (v > bv || (v == bv && k < bk)) {
+            bv = v; bk = k;
+            bx = __int_as_float((int)(w1 >> 32)); by = __int_as_float((int)(unsigned)w1); bz = __int_as_float((int)(w2 >> 32));
+          }
+        }
+        const int gmax = __reduce_max_sync(PC_FULL_MASK, bv);
+        const int gkey = __reduce_min_sync(PC_FULL_MASK, bv == gmax ? bk : INT_MAX);
+        const int src = __ffs(__ballot_sync(PC_FULL_MASK, bv == gmax && bk == gkey)) - 1;
+        bx = __shfl_sync(PC_FULL_MASK, bx, src); by = __shfl_sync(PC_FULL_MASK, by, src); bz = __shfl_sync(PC_FULL_MASK, bz, src);
+        if (lane == 0) { s_next[0] = bx; s_next[1] = by; s_next[2] = bz; s_next[3] = __int_as_float(gkey); }
+      }
+      __syncthreads();
+      cx = s_next[0]; cy = s_next[1]; cz = s_next[2];
+      const int gkey = __float_as_int(s_next[3]);
+      par ^= 1;
+      if (rank == 0 && tid == 0) {
+        o[j] = tie_key_to_index(gkey);
+        if (oxyz) { oxyz[j * 3 + 0] = cx; oxyz[j * 3 + 1] = cy; oxyz[j * 3 + 2] = cz; }
+      }
+      continue;  // (the next round's first barrier orders the s_next reads before warp 0 overwrites it)
+    }
     // Exchange without a cluster barrier: thread i sends this CTA's 32-byte record straight into slot [par][rank] of
     // CTA i with two st.async (16 bytes each) that complete transaction bytes on CTA i's mbarrier s_mb[par]; every CTA
     // armed that barrier for CL * 32 bytes and simply waits for its phase.
@@ -565,7 +629,7 @@ fps_cluster_kernel(int n, int m, float one, const float *__restrict__ xyz, int *
       if (oxyz) { oxyz[j * 3 + 0] = cx; oxyz[j * 3 + 1] = cy; oxyz[j * 3 + 2] = cz; }
     }
   }
-  cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
+  if constexpr (!kGlobal) cg::this_cluster().sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 template <int CL, int P = 32, int PS = 0>
@@ -585,7 +649,39 @@ int launch_cluster(int b, int n, int m, const float *xyz, int *out, float *out_x
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, n, m, 1.0f, xyz, out, out_xyz));
+  PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, n, m, 1.0f, xyz, out, out_xyz, 0, 0, (unsigned long long *)nullptr));
+  return PC_OK;
+}
+
+// n > 262144: cooperative launches of `spw` scenes x `cps` CTAs (16384-point slices, all resident), one after the other
+// on the stream; the record area (workspace) is cleared first so that no stale round number can match.
+constexpr int kCoopSlice = 16384;
+inline int coop_cps(int n) { return (n + kCoopSlice - 1) / kCoopSlice; }
+inline size_t coop_rec_bytes(int scenes, int cps) { return (size_t)scenes * 2 * cps * 3 * sizeof(unsigned long long); }
+
+int launch_coop(int b, int n, int m, const float *xyz, int *out, float *out_xyz, void *workspace, cudaStream_t st) {
+  auto kernel = fps_cluster_kernel<0, 64, 32>;
+  const size_t smem = (size_t)kCoopSlice * 3 * sizeof(float);
+  PC_CUDA_TRY(allow_smem(kernel, smem));
+  const int cps = coop_cps(n);
+  int spw = num_sms() / cps;  // scenes per launch: every CTA of a launch must be resident (1 CTA per SM: 192 KB smem)
+  if (spw < 1) return PC_ERR_UNSUPPORTED;
+  if (spw > b) spw = b;
+  for (int s0 = 0; s0 < b; s0 += spw) {
+    const int ns = (b - s0 < spw) ? b - s0 : spw;
+    PC_CUDA_TRY(cudaMemsetAsync(workspace, 0, coop_rec_bytes(ns, cps), st));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ns * cps));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, n, m, 1.0f, xyz, out, out_xyz, cps, s0, (unsigned long long *)workspace));
+  }
   return PC_OK;
 }
 
@@ -653,6 +749,8 @@ int launch_onchip(int b, int n, int m, const float *xyz, int *out, float *out_xy
 extern "C" size_t pc_fps_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 0;
   if (n <= pc::kMaxClusterPoints) return 0;  // single CTA or one thread-block cluster per scene: all state on chip
+  const int cps = pc::coop_cps(n);
+  if (cps <= 148) return pc::coop_rec_bytes(b < 148 / cps ? b : 148 / cps, cps);  // cooperative grid: records only
   return (size_t)b * n * sizeof(float);
 }
 
@@ -692,6 +790,8 @@ extern "C" int pc_fps_gather(int b, int n, int m, const float *xyz, void *worksp
     return pc::launch_cluster<16, 64, 32>(b, n, m, xyz, out_idx, out_xyz, st);  // 16384-point slices
   }
   if (!workspace) return PC_ERR_WORKSPACE;
+  if (pc::coop_cps(n) <= 148 && pc::coop_cps(n) <= pc::num_sms())
+    return pc::launch_coop(b, n, m, xyz, out_idx, out_xyz, workspace, st);
   pc::fps_stream_kernel<<<b, 1024, 0, st>>>(b, n, m, xyz, (float *)workspace, out_idx);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }

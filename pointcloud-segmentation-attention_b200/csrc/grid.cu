@@ -31,7 +31,8 @@ constexpr int kHdrInts = 16;
 struct GridHdr {  // 16 x 4 bytes, first thing in a scene's workspace
   float ox, oy, oz, inv_h, h;
   int nx, ny, nz, ncells;
-  int pad[7];
+  int nonfinite;  // the cloud holds a +/-inf or NaN coordinate (ball query then scans every cell with the literal test)
+  int pad[6];
 };
 static_assert(sizeof(GridHdr) == kHdrInts * 4, "GridHdr layout");
 
@@ -60,38 +61,38 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float *s_red
   return r;
 }
 
-// mode 0: cell edge = min_edge (ball query, min_edge = r'); mode 1: cell edge from the point density (three_nn);
-// mode 2: bin with the header of another grid (hdr_ws, hdr_n points per scene): the QUERY cloud sorted by the cells
-// of the candidate grid, so that 32 consecutive sorted queries are spatial neighbours.
+// mode 0: cell edge = min_edge (ball query, min_edge = r'); mode 1: cell edge from the point density (three_nn).
+// ONE launch bins both clouds of an op, grid (scenes, 2): CTA (s, 0) bins the candidate cloud of scene s into its grid;
+// CTA (s, 1) bins the QUERY cloud by the same cells (so that 32 consecutive sorted queries are spatial neighbours) --
+// it derives the grid header from the candidates itself (the same reduction over the same data gives the same bits;
+// one extra pass over 12 n bytes) instead of waiting for a second launch behind the first.
 __global__ void __launch_bounds__(kBuildThreads, 1)
-grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz, int *__restrict__ ws,
-                  const int *__restrict__ hdr_ws, int hdr_n) {
+grid_build_kernel(int nc, int nq, float min_edge, int mode, const float *__restrict__ xyz_c,
+                  const float *__restrict__ xyz_q, int *__restrict__ ws_c, int *__restrict__ ws_q) {
   extern __shared__ int s_cnt[];  // kMaxCells
   __shared__ float s_red[32];
   __shared__ GridHdr s_hdr;
   __shared__ int s_warp[32];
   __shared__ int s_carry;
-  const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float *p = xyz + (size_t)scene * n * 3;
-  int *base = ws + (size_t)scene * grid_scene_ints(n);
+  const int scene = blockIdx.x, role = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *hp = xyz_c + (size_t)scene * nc * 3;                       // the cloud that defines the grid
+  const int n = role ? nq : nc;                                           // the cloud this CTA bins
+  const float *p = role ? xyz_q + (size_t)scene * nq * 3 : hp;
+  int *base = role ? ws_q + (size_t)scene * grid_scene_ints(nq) : ws_c + (size_t)scene * grid_scene_ints(nc);
   int *cell_start = base + kHdrInts;
   float4 *sorted = reinterpret_cast<float4 *>(base + grid_sorted_offset_ints());
 
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (mode == 2) {
-    if (tid == 0) {
-      s_hdr = *reinterpret_cast<const GridHdr *>(hdr_ws + (size_t)scene * grid_scene_ints(hdr_n));
-      *reinterpret_cast<GridHdr *>(base) = s_hdr;
-      s_carry = 0;
-    }
-  } else {
-  for (int k = tid; k < n; k += kBuildThreads) {
+  float bad = 0.0f;
+  for (int k = tid; k < nc; k += kBuildThreads) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float v = __ldg(p + k * 3 + c);
-      if (fabsf(v) <= 3.0e38f) {  // non-finite coordinates never hit anything (reference: d < r / d < best is false)
-        lo[c] = fminf(lo[c], v);  // and must not stretch the box: an infinite extent has no cell size
-        hi[c] = fmaxf(hi[c], v);
+      const float v = __ldg(hp + k * 3 + c);
+      if (fabsf(v) <= 3.0e38f) {  // non-finite coordinates must not stretch the box: an infinite extent has no cell
+        lo[c] = fminf(lo[c], v);  // size.  three_nn never selects them (d < best is false); ball query does count a
+        hi[c] = fmaxf(hi[c], v);  // NaN distance as a hit (fmaxf, tf_grouping_g.cu:24): flagged below
+      } else {
+        bad = 1.0f;
       }
     }
   }
@@ -100,6 +101,7 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
     lo[c] = block_reduce(lo[c], false, s_red);
     hi[c] = block_reduce(hi[c], true, s_red);
   }
+  bad = block_reduce(bad, true, s_red);
   if (tid == 0) {
     // finite by construction (box over finite coordinates; a scene without any gets a 1-cell grid at the origin)
 #pragma unroll
@@ -111,7 +113,7 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
     if (mode == 1) {  // ~4 points per cell in volume terms, never finer than the surface / line density suggests: the
       // third neighbour must lie within one cell edge for a lane to be certified without the whole-cloud scan
       const float vol = ex * ey * ez, area = fmaxf(ex * ey, fmaxf(ex * ez, ey * ez)), len = fmaxf(ex, fmaxf(ey, ez));
-      h = fmaxf(fmaxf(1.6f * cbrtf(vol / n), 1.1f * sqrtf(area / n)), fmaxf(2.0f * len / n, 1e-12f));
+      h = fmaxf(fmaxf(1.6f * cbrtf(vol / nc), 1.1f * sqrtf(area / nc)), fmaxf(2.0f * len / nc, 1e-12f));
       h = fmaxf(h, min_edge);
     }
     if (!(h > 0.f) || !isfinite(h)) h = 1.0f;
@@ -125,9 +127,9 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
     s_hdr.ox = lo[0]; s_hdr.oy = lo[1]; s_hdr.oz = lo[2];
     s_hdr.h = h; s_hdr.inv_h = 1.0f / h;
     s_hdr.nx = nx; s_hdr.ny = ny; s_hdr.nz = nz; s_hdr.ncells = nx * ny * nz;
+    s_hdr.nonfinite = bad > 0.0f;
     *reinterpret_cast<GridHdr *>(base) = s_hdr;
     s_carry = 0;
-  }
   }
   __syncthreads();
   const GridHdr g = s_hdr;
@@ -184,7 +186,9 @@ grid_build_kernel(int n, float min_edge, int mode, const float *__restrict__ xyz
 // (tf_interpolate.cpp:74-89), i.e. keeps the 3 smallest by (distance, index); here the visiting order is arbitrary.
 __device__ __forceinline__ bool before(float d, int k, float bd, int bi) { return d < bd || (d == bd && k < bi); }
 __device__ __forceinline__ void nn_insert_lex(float d, int k, float &b1, float &b2, float &b3, int &i1, int &i2, int &i3) {
-  if (before(d, k, b3, i3)) {
+  // d < inf: the reference starts from best = 1e40 in double (tf_interpolate.cpp:66) and inserts on strict '<', so an
+  // infinite (or NaN) distance -- a non-finite coordinate on either side -- never enters the list, whatever its index
+  if (d < __int_as_float(0x7f800000) && before(d, k, b3, i3)) {
     if (before(d, k, b1, i1)) {
       b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
     } else if (before(d, k, b2, i2)) {
@@ -215,8 +219,8 @@ struct TileSmem {
         y(x + kCap), z(y + kCap), i(base + 3 * kMaxRows + 3 * kCap) {}
 };
 
-// Stages the candidates of the cell box [X0..X1] x [Y0..Y1] x [Z0..Z1] batch by batch and calls process(count) with
-// `count` (a multiple of 32, padded with +inf points) candidates in the stage.  Collective over NW warps that share
+// Stages the candidates of the cell box [X0..X1] x [Y0..Y1] x [Z0..Z1] batch by batch and calls process(count, real)
+// with `count` (a multiple of 32; the first `real` are candidates, the rest +inf padding) candidates in the stage.  Collective over NW warps that share
 // `st` (NW == 1: one warp, __syncwarp; NW > 1: the whole CTA of NW warps, __syncthreads).
 template <int NW, class F>
 __device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__restrict__ cell_start,
@@ -291,7 +295,7 @@ __device__ __forceinline__ void for_each_batch(const GridHdr &g, const int *__re
       const int bp = (bn + 31) & ~31;
       for (int f = bn + t; f < bp; f += NT) { st.x[f] = inf; st.y[f] = inf; st.z[f] = inf; st.i[f] = 0; }
       sync();
-      process(bp);
+      process(bp, bn);
       sync();
     }
   }
@@ -331,8 +335,9 @@ __device__ __forceinline__ unsigned filter_word(const TileSmem &st, int w0, f32x
 // memory per resident warp); warp 0 then extracts the rows.
 constexpr int kBallWarps = 4;
 __global__ void __launch_bounds__(kBallWarps * 32)
-ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, float one, const int *__restrict__ ws_c,
-                       const int *__restrict__ ws_q, int *__restrict__ idx, int *__restrict__ pts_cnt) {
+ball_query_tile_kernel(int n, int m, float s_star, float radius, float reach, int nsample, float one,
+                       const int *__restrict__ ws_c, const int *__restrict__ ws_q, int *__restrict__ idx,
+                       int *__restrict__ pts_cnt) {
   extern __shared__ __align__(16) int s_tile[];  // TileSmem | bitmap (nwords + nsumm) * 32
   TileSmem st(s_tile);
   const int nwords = (n + 31) >> 5, nsumm = (nwords + 31) >> 5;
@@ -357,15 +362,30 @@ ball_query_tile_kernel(int n, int m, float s_star, float reach, int nsample, flo
     const int qi = __float_as_int(qv.w);
     const f32x2 qx2 = pack2(qv.x, qv.x), qy2 = pack2(qv.y, qv.y), qz2 = pack2(qv.z, qv.z);
     // cell box of this lane's ball (dead lanes copy the tile's first query) and the tile's union box
-    const int X0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.x - reach, g.ox, g.inv_h, g.nx));
-    const int X1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.x + reach, g.ox, g.inv_h, g.nx));
-    const int Y0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.y - reach, g.oy, g.inv_h, g.ny));
-    const int Y1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.y + reach, g.oy, g.inv_h, g.ny));
-    const int Z0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.z - reach, g.oz, g.inv_h, g.nz));
-    const int Z1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.z + reach, g.oz, g.inv_h, g.nz));
-    for_each_batch<kBallWarps>(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
+    int X0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.x - reach, g.ox, g.inv_h, g.nx));
+    int X1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.x + reach, g.ox, g.inv_h, g.nx));
+    int Y0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.y - reach, g.oy, g.inv_h, g.ny));
+    int Y1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.y + reach, g.oy, g.inv_h, g.ny));
+    int Z0 = __reduce_min_sync(PC_FULL_MASK, cell_coord(qv.z - reach, g.oz, g.inv_h, g.nz));
+    int Z1 = __reduce_max_sync(PC_FULL_MASK, cell_coord(qv.z + reach, g.oz, g.inv_h, g.nz));
+    // Non-finite coordinates (never in real clouds) on either side: a NaN distance is a HIT in the reference
+    // (max = fmaxf, tf_grouping_g.cu:24), wherever the point was binned -- the tile then meets EVERY cell and uses the
+    // literal hit expression instead of the bit-pattern compare.
+    const float inf = __int_as_float(0x7f800000);
+    const bool exact = g.nonfinite ||
+                       __any_sync(PC_FULL_MASK, !(fabsf(qv.x) < inf) || !(fabsf(qv.y) < inf) || !(fabsf(qv.z) < inf));
+    if (exact) { X0 = Y0 = Z0 = 0; X1 = g.nx - 1; Y1 = g.ny - 1; Z1 = g.nz - 1; }
+    for_each_batch<kBallWarps>(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count, int real) {
       for (int w0 = warp * 32; w0 < count; w0 += kBallWarps * 32) {  // the CTA's warps take alternate words
-        unsigned word = filter_word(st, w0, qx2, qy2, qz2, one2, thr, true);
+        unsigned word = 0;
+        if (exact) {
+          for (int e = 0; e < 32 && w0 + e < real; ++e) {  // the +inf padding would meet an infinite query as NaN
+            const float d2 = sqdist3(qv.x, qv.y, qv.z, st.x[w0 + e], st.y[w0 + e], st.z[w0 + e]);
+            if (fmaxf(sqrtf(d2), 1e-20f) < radius) word |= 1u << e;
+          }
+        } else {
+          word = filter_word(st, w0, qx2, qy2, qz2, one2, thr, true);
+        }
         while (word) {  // record each hit at its ORIGINAL index (other warps may touch the same bitmap word)
           const int k = st.i[w0 + __ffs(word) - 1], w = k >> 5;
           word &= word - 1;
@@ -437,7 +457,7 @@ three_nn_tile_kernel(int n, int m, float one, const int *__restrict__ ws_c, cons
     const int Z0 = max(__reduce_min_sync(PC_FULL_MASK, cz) - 1, 0), Z1 = min(__reduce_max_sync(PC_FULL_MASK, cz) + 1, g.nz - 1);
     float b1 = inf, b2 = inf, b3 = inf;
     int i1 = INT_MAX, i2 = INT_MAX, i3 = INT_MAX;
-    for_each_batch<1>(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count) {
+    for_each_batch<1>(g, cell_start, sorted, X0, X1, Y0, Y1, Z0, Z1, st, [&](int count, int) {
       for (int w0 = 0; w0 < count; w0 += 32) {
         // stale filter d <= b3 (ties on the distance may still win on the index); exact replay of the survivors
         const int thr = (b3 == inf) ? 0x7f800000 : __float_as_int(b3) + 1;
@@ -489,11 +509,11 @@ three_nn_tile_kernel(int n, int m, float one, const int *__restrict__ ws_c, cons
   }
 }
 
-int build(int b, int n, float min_edge, int mode, const float *xyz, int *ws, const int *hdr_ws, int hdr_n,
-          cudaStream_t st) {
+int build_pair(int b, int nc, int nq, float min_edge, int mode, const float *xyz_c, const float *xyz_q, int *ws_c,
+               int *ws_q, cudaStream_t st) {
   const size_t smem = (size_t)kMaxCells * sizeof(int);
   PC_CUDA_TRY(allow_smem(grid_build_kernel, smem));
-  grid_build_kernel<<<b, kBuildThreads, smem, st>>>(n, min_edge, mode, xyz, ws, hdr_ws, hdr_n);
+  grid_build_kernel<<<dim3(b, 2), kBuildThreads, smem, st>>>(nc, nq, min_edge, mode, xyz_c, xyz_q, ws_c, ws_q);
   PC_RETURN_LAUNCH_STATUS();
 }
 
@@ -522,14 +542,12 @@ extern "C" int pc_query_ball_grid(int b, int n, int m, float radius, int nsample
   const float s_star = pc::ball_threshold(radius);
   const float reach = radius * 1.0001f + 1e-30f;  // conservative: fp32 rounding of the distance is ~1e-7 relative
   int *ws_c = (int *)workspace, *ws_q = ws_c + (size_t)b * pc::grid_scene_ints(n);
-  int rc = pc::build(b, n, reach, 0, xyz1, ws_c, nullptr, 0, st);
-  if (rc) return rc;
-  rc = pc::build(b, m, 0.0f, 2, xyz2, ws_q, ws_c, n, st);  // queries sorted by the candidates' cells
+  int rc = pc::build_pair(b, n, m, reach, 0, xyz1, xyz2, ws_c, ws_q, st);  // candidates + queries, one launch
   if (rc) return rc;
   PC_CUDA_TRY(pc::allow_smem(pc::ball_query_tile_kernel, smem));
   const int ntiles = (m + 31) / 32;
   dim3 grid(ntiles < 64 ? ntiles : 64, b);
-  pc::ball_query_tile_kernel<<<grid, pc::kBallWarps * 32, smem, st>>>(n, m, s_star, reach, nsample, 1.0f, ws_c, ws_q, idx, pts_cnt);
+  pc::ball_query_tile_kernel<<<grid, pc::kBallWarps * 32, smem, st>>>(n, m, s_star, radius, reach, nsample, 1.0f, ws_c, ws_q, idx, pts_cnt);
   PC_RETURN_LAUNCH_STATUS();
 }
 
@@ -547,9 +565,7 @@ extern "C" int pc_three_nn_grid(int b, int n, int m, const float *xyz1, const fl
   if (!workspace) return PC_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   int *ws_c = (int *)workspace, *ws_q = ws_c + (size_t)b * pc::grid_scene_ints(m);
-  int rc = pc::build(b, m, 0.0f, 1, xyz2, ws_c, nullptr, 0, st);
-  if (rc) return rc;
-  rc = pc::build(b, n, 0.0f, 2, xyz1, ws_q, ws_c, m, st);  // dense points sorted by the known cloud's cells
+  int rc = pc::build_pair(b, m, n, 0.0f, 1, xyz2, xyz1, ws_c, ws_q, st);  // known cloud + dense points, one launch
   if (rc) return rc;
   const size_t smem = (size_t)pc::kNNTileWarps * pc::kTileWarpInts * sizeof(int);
   PC_CUDA_TRY(pc::allow_smem(pc::three_nn_tile_kernel, smem));

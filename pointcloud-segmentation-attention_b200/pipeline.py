@@ -131,11 +131,11 @@ class ScanNetGeometry:
         self.main = torch.cuda.Stream(device=dev, priority=-1) if own_streams else None
         self.sides = [torch.cuda.Stream(device=dev) for _ in self.levels]
         self.side = self.sides[0]
-        # kernels per forward: FPS, gather, ball (+ grid build), group x2, attention per SA level; three_nn (+ grid build
-        # when the known cloud has >= 64 points), weights, interpolate per FP level
-        self.launches_per_step = len(self.levels) * ((6 if attention else 5) + (2 if grid else 0) -
+        # kernels per forward: FPS, gather, ball (+ ONE grid build binning both clouds), group x2, attention per SA level;
+        # three_nn (+ one grid build when the known cloud has >= 64 points), weights, interpolate per FP level
+        self.launches_per_step = len(self.levels) * ((6 if attention else 5) + (1 if grid else 0) -
                                                      (1 if fuse_gather else 0) - (1 if fuse_layers else 0)) + \
-            sum(3 + (2 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps) + \
+            sum(3 + (1 if grid and fp["m"] >= 64 else 0) - (1 if fuse_layers else 0) for fp in self.fps) + \
             (2 * len(self.levels) if self.attention_layers else 0)   # fused layer = operand prep + Q + main kernel
         self._graph = None
         self._arena16 = None

@@ -54,7 +54,10 @@ def test_workspace_queries_are_pure_host_functions():
     assert L.pc_fps_workspace_bytes(16, 8192, 1024) == 0            # state stays on chip
     assert L.pc_fps_workspace_bytes(2, 100000, 64) == 0               # one 16-CTA cluster per scene, still on chip
     assert L.pc_fps_workspace_bytes(2, 200000, 64) == 0  # up to 262144 points: one 16-CTA cluster per scene
-    assert L.pc_fps_workspace_bytes(2, 300000, 64) == 2 * 300000 * 4  # beyond: streamed min-distances
+    # beyond: a cooperative grid of 16384-point CTAs exchanging 24-byte records through global memory (2 parities)
+    assert L.pc_fps_workspace_bytes(2, 300000, 64) == 2 * 2 * 19 * 24
+    assert L.pc_fps_workspace_bytes(64, 1 << 20, 1024) == 2 * 2 * 64 * 24          # two scenes per launch
+    assert L.pc_fps_workspace_bytes(2, 3000000, 64) == 2 * 3000000 * 4              # > 148 slices: streamed minima
     assert L.pc_group_point_grad_workspace_bytes(16, 1024, 64, 256, 32) == 16 * (1024 + 1 + 256 * 32) * 4
     assert L.pc_three_interpolate_grad_workspace_bytes(16, 8192, 128, 1024) == 16 * (1024 + 1 + 8192 * 3) * 4
     assert L.pc_gather_point_grad_workspace_bytes(4, 512, 128) == 4 * (512 + 1 + 128) * 4

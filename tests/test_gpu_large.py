@@ -127,10 +127,11 @@ def test_three_nn_large_clouds(mode, kind, n, m, b):
     assert np.array_equal(npy(d), od)
 
 
-@pytest.mark.parametrize("n,m,b", [(16384, 4096, 2), (65536, 1024, 2), (131072, 512, 2), (262144, 256, 1), (300000, 64, 1),
-                                   (1048576, 48, 1)])
+@pytest.mark.parametrize("n,m,b", [(16384, 4096, 2), (65536, 1024, 2), (131072, 512, 2), (262144, 256, 1), (262145, 40, 2),
+                                   (300000, 64, 3), (1048576, 48, 3), (1100000, 24, 1)])
 def test_fps_large_clouds(n, m, b):
-    """Cluster path (2 / 8 / 16 CTAs, 16 x 16384-point slices) and, beyond 262 144 points, the multi-CTA streamed path."""
+    """Cluster path (2 / 8 / 16 CTAs, 16 x 16384-point slices) and, beyond 262 144 points, the cooperative grid whose
+    CTAs exchange their winners through global memory (b = 3 at 1 M points = two launches: scenes {0, 1} and {2})."""
     xyz = np.stack([synth.whole_scene(900 + i + n % 61, n)[0] for i in range(b)], 0)
     got = ops.farthest_point_sample(m, cu(xyz))
     assert np.array_equal(npy(got), cpu.farthest_point_sample(m, xyz, omp=True))
