@@ -273,6 +273,32 @@ PC_API int pc_map_back_winner(size_t rows, int nres, const long long *orig_idx, 
                        pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Dense layers of the path on the tcgen05 tensor cores (csrc/gemm_tf32.cu), 3xTF32 split precision: fp32 in / out,
+ * ~2e-6 of the output scale against a float64 product.  Reference: the 1x1 conv2d + batch norm + ReLU stack and the
+ * max over nsample of pointnet_sa_module (utils/pointnet_util.py:119-135, utils/tf_util.py:120-186,512-530: stock cuDNN
+ * layers there), the Dense projections of AttentionLayer (attention_layer.py:24-34) and their gradients.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of the tensor-core weight image of a (K, N) layer (TF32 hi / lo parts, 128-byte-swizzled K blocks). */
+PC_API size_t pc_dense_image_bytes(int K, int N);
+/* Builds the image once per set of weights (cache it across calls).  transpose = 0: w is (K, N) row-major, the layer
+ * computes X w (Keras / tf.layers kernel layout [in][out]); transpose = 1: w is (N, K) row-major and the layer computes
+ * X w^T -- the input-gradient product dX = dY W^T of a layer whose kernel W is (N_in = N here, ...) see INTEGRATION.md.
+ * N % 16 == 0, N <= 1024. */
+PC_API int pc_dense_prepare(int K, int N, const float *w, int transpose, void *image, pc_stream_t stream);
+/* y (rows, N; row stride ldy) = act(x (rows, K; row stride ldx) . W + bias), act = ReLU when relu != 0, bias (N) or NULL.
+ * A batch norm in inference mode folds into W and bias on the caller's side. */
+PC_API int pc_dense_fwd(size_t rows, int K, int N, const float *x, size_t ldx, const void *image, const float *bias,
+                        int relu, float *y, size_t ldy, pc_stream_t stream);
+/* The same layer followed by the maximum over each group of group_size (= 32 = nsample) consecutive rows
+ * (pointnet_util.py:134-135): y_pooled (groups, N).  y_full = NULL: the (groups * 32, N) activation is never written
+ * (pointnet_sa_module); y_full != NULL: it is written as well (pointnet_sa_module_attention_and_pooling needs both,
+ * attention_layer.py:306-323). */
+PC_API int pc_dense_pool_fwd(size_t groups, int group_size, int K, int N, const float *x, size_t ldx, const void *image,
+                             const float *bias, int relu, float *y_full, size_t ldy, float *y_pooled, size_t ldp,
+                             pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Host-boundary packing (csrc/io_pack.cu)
  * ------------------------------------------------------------------------------------------------------------- */
 

@@ -233,3 +233,72 @@ def attention_layer(x, xq, Wq, bq, Wk, bk, Wv, bv, heads, key_dim):
     K = dense(x, Wk, bk)
     V = dense(x, Wv, bv)
     return attention_fwd(Q, K, V, heads, key_dim)
+
+
+# ---- the shared-MLP block of a set-abstraction level (float64 numpy restatement; TF absent -> source-pinned) ----------
+def batch_norm_inference(x, gamma, beta, moving_mean, moving_var, eps=1e-3):
+    """tf.contrib.layers.batch_norm(center=True, scale=True, is_training=False) as tf_util.batch_norm_template calls it
+    (utils/tf_util.py:512-530; the layer's default epsilon is 0.001), float64."""
+    x = np.asarray(x, np.float64)
+    return (x - np.asarray(moving_mean, np.float64)) / np.sqrt(np.asarray(moving_var, np.float64) + eps) * \
+        np.asarray(gamma, np.float64) + np.asarray(beta, np.float64)
+
+
+def conv2d_1x1(x, W, b, bn=None, relu=True):
+    """tf_util.conv2d with kernel [1,1], stride 1, VALID (utils/tf_util.py:120-186): tf.nn.conv2d -> bias_add -> batch norm
+    (inference) -> ReLU, over the last axis.  x (..., cin), W (cin, cout) = the conv kernel [1,1,cin,cout] squeezed;
+    bn = (gamma, beta, moving_mean, moving_var) or None.  float64 accumulation, float64 result."""
+    y = np.asarray(x, np.float64) @ np.asarray(W, np.float64)
+    if b is not None:
+        y = y + np.asarray(b, np.float64)
+    if bn is not None:
+        y = batch_norm_inference(y, *bn)
+    return np.maximum(y, 0.0) if relu else y
+
+
+def shared_mlp(new_points, layers):
+    """The 'Point Feature Embedding' loop of pointnet_sa_module (utils/pointnet_util.py:119-131): layers = [(W, b, bn)]."""
+    y = np.asarray(new_points, np.float64)
+    for W, b, bn in layers:
+        y = conv2d_1x1(y, W, b, bn, True)
+    return y
+
+
+def sa_module_tail(new_points, layers, pooling="max"):
+    """MLP + 'Pooling in Local Regions' (pointnet_util.py:119-135): (B,m,ns,C) -> (B,m,mlp[-1])."""
+    y = shared_mlp(new_points, layers)
+    assert pooling == "max"
+    return y.max(axis=2)
+
+
+def sa_attention_tail(new_points, layers, Wq, bq, Wk, bk, Wv, bv, bn_out=None, and_pooling=False):
+    """pointnet_sa_module_attention (attention_layer.py:227-263) after sample_and_group: MLP -> AttentionLayer with
+    query = sample 0 (:259), heads = mlp[-1] // 4, key_dim = output_dim = 4 (:255-258) -> batch norm (:263); the
+    _and_pooling variant (:306-323) adds the max over nsample of the MLP output AFTER that batch norm (:323).
+    float64 throughout (attention_layer_f64)."""
+    y = shared_mlp(new_points, layers)                       # (B,m,ns,C)
+    B, m, ns, C = y.shape
+    x = y.reshape(B * m, ns, C)
+    att = attention_layer_f64(x, x[:, 0, :], Wq, bq, Wk, bk, Wv, bv, C // 4, 4).reshape(B, m, C)
+    if bn_out is not None:
+        att = batch_norm_inference(att, *bn_out)
+    if and_pooling:
+        att = att + y.max(axis=2)
+    return att
+
+
+def attention_layer_f64(x, xq, Wq, bq, Wk, bk, Wv, bv, heads, key_dim):
+    """AttentionLayer.call (attention_layer.py:29-45) in float64 numpy with the reference's RAW reshape (:35)."""
+    f = np.float64
+    x, xq = np.asarray(x, f), np.asarray(xq, f)
+    G, S, _ = x.shape
+    Q = xq @ np.asarray(Wq, f) + (0 if bq is None else np.asarray(bq, f))
+    K = x @ np.asarray(Wk, f) + (0 if bk is None else np.asarray(bk, f))
+    V = x @ np.asarray(Wv, f) + (0 if bv is None else np.asarray(bv, f))
+    Qh = Q.reshape(G, heads, 1, key_dim)
+    Kh = K.reshape(G, heads, S, key_dim)                     # raw reshape of the (S, heads*key_dim) buffer
+    Vh = V.reshape(G, heads, S, key_dim)
+    w = Qh @ Kh.transpose(0, 1, 3, 2) / np.sqrt(float(key_dim))
+    w = np.exp(w - w.max(-1, keepdims=True))
+    w = w / w.sum(-1, keepdims=True)
+    return (w @ Vh).reshape(G, heads * key_dim)

@@ -62,6 +62,10 @@ SIGNATURES = {
     "pc_gather_rows_bytes": (_i, [_sz, _i, _vp, _vp, _vp, _vp]),
     "pc_scene_sample_weights": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_map_back_winner": (_i, [_sz, _i, _vp, _vp, _vp, _vp]),
+    "pc_dense_image_bytes": (_sz, [_i, _i]),
+    "pc_dense_prepare": (_i, [_i, _i, _vp, _i, _vp, _vp]),
+    "pc_dense_fwd": (_i, [_sz, _i, _i, _vp, _sz, _vp, _vp, _i, _vp, _sz, _vp]),
+    "pc_dense_pool_fwd": (_i, [_sz, _i, _i, _i, _vp, _sz, _vp, _vp, _i, _vp, _sz, _vp, _sz, _vp]),
     "pc_unpack_features": (_i, [_sz, _vp, _vp, _vp, _vp]),
     "pc_narrow_indices_u16": (_i, [_sz, _vp, _vp, _vp]),
 }

@@ -1,0 +1,418 @@
+// Dense layers of the path on the tcgen05 tensor cores: Y = epilogue(X . W + b) in 3xTF32 split precision.
+//
+// What it replaces.  Everything between the geometry ops in the reference is a 1x1 convolution / Dense layer over
+// (B*m*nsample) rows -- tf_util.conv2d with kernel [1,1] + batch norm + ReLU three times in pointnet_sa_module
+// (utils/pointnet_util.py:119-131, tf_util.py:120-186,512-530) followed by a max over nsample (:134-135), and the three
+// Dense projections of AttentionLayer (attention_layer.py:24-34) with their gradients under minimize
+// (attention_points/train.py:337-339).  TensorFlow runs them as cuDNN / cuBLAS calls with every intermediate in HBM.
+//
+// One engine, three uses:
+//   * pc_dense_fwd       Y (rows, N) = act(X (rows, K) . W (K, N) + bias)           shared-MLP layer (inference: batch norm
+//                        folded into W / bias by the caller), Dense K | V projection of a training forward
+//   * pc_dense_pool_fwd  Y (rows/32, N) = max over each group of 32 rows of the above   last MLP layer + the max-pool of
+//                        pointnet_sa_module, pooled straight out of TMEM: the (rows, N) tensor is never written
+//   * pc_dense_bwd_input dX (rows, K) = dY (rows, N) . W^T                              same kernel, weight image built
+//                        from W with swapped strides
+// and pc_dense_bwd_weight dW (K, N) = X^T . dY, db = column sums of dY             a second kernel whose producers
+//                        transpose both operands on the way into shared memory (split over row ranges, partials
+//                        summed in a fixed order: deterministic).
+//
+// Precision: fp32 in, fp32 out.  Plain TF32 (10-bit mantissa) misses the path's 1e-5 bound, so every operand is split
+// x = hi + lo (both TF32) and each product is issued as hi*hi + hi*lo + lo*hi into an fp32 TMEM accumulator -- the
+// same scheme, descriptors and swizzled layout as attention_layer_wide.cu (measured there: 2e-6 of the output scale).
+//
+// Schedule (one persistent CTA per SM, 288 threads): work item = (tile of 128 rows, chunk of <= 256 output columns).
+//   warps 0-3  producers: per K block of 32 input columns, X rows global -> registers (two blocks ahead) -> hi / lo ->
+//              128-byte-swizzled A stage; one thread starts the bulk copy (cp.async.bulk + mbarrier complete_tx) of the
+//              pre-split, pre-swizzled B block of the weight image
+//   warp  8    one thread issues 12 tcgen05.mma (M128 N<=256 K8 kind::tf32) per K block; tcgen05.commit frees the stage
+//   warps 4-7  epilogue: tcgen05.ld 32 columns at a time, bias (+ ReLU), then either a transposed pass through a 4 KB
+//              shared-memory patch so that the global stores are row-contiguous 128-bit transactions, or the warp-wide
+//              maximum per column (an epilogue warp's 32 TMEM lanes ARE the 32 samples of one neighbourhood)
+// Two TMEM accumulators (2 x 256 columns): the next item's MMAs run under this item's epilogue.
+#include <math.h>
+#include "common.cuh"
+
+namespace pc {
+namespace {
+
+constexpr int kRows = 128;                 // M: rows per tile
+constexpr int kMaxNc = 256;                // N per item
+constexpr int kKB = 32;                    // tf32 elements per K block (one 128-byte swizzled row)
+constexpr int kSBO = 1024;                 // bytes between 8-row groups
+constexpr int kABlock = kRows * 128;       // 16 KB: A K-block (hi or lo)
+constexpr int kBBlock = kMaxNc * 128;      // 32 KB: B K-block (hi or lo) at full width
+constexpr int kStage = 2 * kABlock + 2 * kBBlock;   // 96 KB: A_hi | A_lo | B_hi | B_lo
+constexpr int kThreads = 288;
+constexpr int kMaxN = 1024;                // bias staged in shared memory
+constexpr int kPatch = 32 * 36;            // floats per epilogue warp: 32 rows x 32 columns, rows padded to 36
+
+__host__ __device__ inline int block_offset(int row, int k) {  // byte offset of (row, k) inside one K block, k < 32
+  return (row >> 3) * kSBO + (row & 7) * 128 + (((k >> 2) ^ (row & 7)) << 4) + (k & 3) * 4;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Weight image: for column chunk j and K block kb a 64 KB slot [B_hi | B_lo] (each nc x 128 bytes used) laid out as
+// shared memory wants it.  Row n of a block is output column 256 j + n; element (n, kl) = W[(32 kb + kl) * sk + (256 j +
+// n) * sn], zero beyond K / N.  (sk, sn) = (ldw, 1) for Y = X W with W stored [in][out]; (1, ldw) for dX = dY W^T.
+__global__ void dense_prep_kernel(int K, int N, size_t sk, size_t sn, const float *__restrict__ w,
+                                  unsigned char *__restrict__ image) {
+  const int nkb = (K + kKB - 1) / kKB, nchunk = (N + kMaxNc - 1) / kMaxNc;
+  const size_t total = (size_t)nchunk * nkb * kMaxNc * kKB;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int kl = (int)(t % kKB);
+    const int n = (int)((t / kKB) % kMaxNc);
+    const int kb = (int)((t / ((size_t)kKB * kMaxNc)) % nkb);
+    const int j = (int)(t / ((size_t)kKB * kMaxNc * nkb));
+    const int k = kb * kKB + kl, col = j * kMaxNc + n;
+    const float v = (k < K && col < N) ? w[(size_t)k * sk + (size_t)col * sn] : 0.f;
+    const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+    unsigned char *blk = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
+    *reinterpret_cast<float *>(blk + block_offset(n, kl)) = hi;
+    *reinterpret_cast<float *>(blk + kBBlock + block_offset(n, kl)) = lo;
+  }
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B, SBO = 1024
+  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (1u << 16);
+  const uint32_t hi = (uint32_t)(kSBO >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+#define PCG_TMEM_LD32(addr, v)                                                                                            \
+  asm volatile(                                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                           \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),        \
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),            \
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),           \
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                          \
+      : "r"(addr))
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost arrival
+  } while (!ok);
+}
+
+// kPool: 0 = store Y (rows, N) to out; 1 = store the maximum over each group of 32 rows, (rows / 32, N), to pooled;
+// 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
+template <int kPool>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, int vec_x,
+                  const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
+                  float *__restrict__ out, float *__restrict__ pooled) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stage_buf = smem;                                          // [2][A_hi | A_lo | B_hi | B_lo]
+  float *s_bias = reinterpret_cast<float *>(smem + 2 * kStage);             // kMaxN
+  float *s_patch = s_bias + kMaxN;                                          // 4 x kPatch
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_patch + 4 * kPatch);     // full[2], empty[2], t_full[2], t_empty[2]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+  const uint32_t full[2] = {bar0, bar0 + 8}, empty[2] = {bar0 + 16, bar0 + 24};
+  const uint32_t t_full[2] = {bar0 + 32, bar0 + 40}, t_empty[2] = {bar0 + 48, bar0 + 56};
+
+  if (warp == 8) {  // the whole TMEM: two 256-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(128u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty[s]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full[s]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty[s]), "r"(128u));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  for (int i = tid; i < N; i += kThreads) s_bias[i] = bias ? __ldg(bias + i) : 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+
+  const int nkb = (K + kKB - 1) / kKB, nchunk = (N + kMaxNc - 1) / kMaxNc;
+  const int ntiles = (int)((rows + kRows - 1) / kRows);
+  const int nitems = ntiles * nchunk;                 // item = tile * nchunk + j: a tile's chunks run on neighbouring CTAs
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage_buf);
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producers
+    const int my_items = blockIdx.x < nitems ? (nitems - 1 - blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_it = my_items * nkb;
+    auto fetch = [&](float4 (&buf)[8], int it_) {   // thread t takes float4 t + 128 i -> row (i4 >> 3), quad i4 & 7
+      const int w = it_ / nkb, kb = it_ - w * nkb;
+      const int tile = (blockIdx.x + w * (int)gridDim.x) / nchunk;
+      const size_t row0 = (size_t)tile * kRows;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+        const int k0 = kb * kKB + kq * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it_ < n_it && row0 + row < rows && k0 < K) {
+          const float *src = x + (row0 + row) * ldx + k0;
+          if (vec_x && k0 + 3 < K) {
+            v = __ldg(reinterpret_cast<const float4 *>(src));
+          } else {  // row stride or base not 16-byte aligned (K = 9, 67, 131, 259: the [xyz | features] inputs), or K tail
+            v.x = __ldg(src);
+            if (k0 + 1 < K) v.y = __ldg(src + 1);
+            if (k0 + 2 < K) v.z = __ldg(src + 2);
+            if (k0 + 3 < K) v.w = __ldg(src + 3);
+          }
+        }
+        buf[i] = v;
+      }
+    };
+    auto produce = [&](const float4 (&buf)[8], int it_) {
+      const int w = it_ / nkb, kb = it_ - w * nkb;
+      const int j = (blockIdx.x + w * (int)gridDim.x) % nchunk;
+      const int nc = min(kMaxNc, N - j * kMaxNc);
+      const int s = it_ & 1;
+      mbar_wait(empty[s], ((it_ >> 1) & 1) ^ 1);       // the MMAs that read this stage two blocks ago have completed
+      unsigned char *st = stage_buf + s * kStage;
+      if (tid == 0) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
+        const unsigned char *src = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
+        const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
+        const uint32_t bytes = (uint32_t)nc * 128u;
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(bytes), "r"(full[s])
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + kBBlock),
+                     "l"(src + kBBlock), "r"(bytes), "r"(full[s])
+                     : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+        const float4 v = buf[i];
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        const int off = block_offset(row, kq * 4);
+        *reinterpret_cast<float4 *>(st + off) = h;
+        *reinterpret_cast<float4 *>(st + kABlock + off) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
+    };
+    float4 bufA[8], bufB[8];
+    fetch(bufA, 0);
+    fetch(bufB, 1);
+    for (int it = 0; it < n_it; it += 2) {
+      produce(bufA, it);
+      fetch(bufA, it + 2);
+      if (it + 1 < n_it) {
+        produce(bufB, it + 1);
+        fetch(bufB, it + 3);
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int it = 0, w = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
+        const int a = w & 1, j = item % nchunk;
+        const int nc = min(kMaxNc, N - j * kMaxNc);
+        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nc >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        mbar_wait(t_empty[a], ((w >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it & 1;
+          mbar_wait(full[s], (it >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = stage_s + s * kStage, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + kBBlock;
+#pragma unroll
+          for (int split = 0; split < 3; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi
+            const uint32_t as = (split == 2) ? a_lo : a_hi, bs = (split == 1) ? b_lo : b_hi;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              mma_tf32(tmem + a * kMaxNc, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
+              acc = 1;
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty[s]) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_full[a]) : "memory");
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (warps 4-7: TMEM lane quarters 0-3)
+    const int qtr = warp & 3;
+    float *patch = s_patch + qtr * kPatch;
+    int w = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
+      const int a = w & 1, tile = item / nchunk, j = item - tile * nchunk;
+      const int nc = min(kMaxNc, N - j * kMaxNc);
+      const size_t row0 = (size_t)tile * kRows + qtr * 32;    // this warp's 32 rows
+      mbar_wait(t_full[a], (w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * kMaxNc;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        uint32_t v[32];
+        PCG_TMEM_LD32(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float *cb = s_bias + j * kMaxNc + c0;
+        float y[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          y[t] = __uint_as_float(v[t]) + cb[t];
+          if (relu) y[t] = fmaxf(y[t], 0.f);
+        }
+        if (kPool) {
+          // the warp's 32 lanes are the 32 samples of neighbourhood row0 / 32: maximum per column, lane t keeps column t
+          const bool live = row0 + lane < rows;
+          float mine = 0.f;
+          if (relu) {  // values >= 0 order like their bit patterns: one redux per column
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const int m = __reduce_max_sync(PC_FULL_MASK, live ? __float_as_int(fmaxf(y[t], 0.f)) : 0);
+              if (lane == t) mine = __int_as_float(m);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              float m = live ? y[t] : -INFINITY;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(PC_FULL_MASK, m, o));
+              if (lane == t) mine = m;
+            }
+          }
+          if (row0 < rows && c0 + lane < nc) pooled[(row0 >> 5) * ldp + (size_t)j * kMaxNc + c0 + lane] = mine;
+        }
+        if (kPool != 1) {
+          // transpose through the patch: thread = row writes its 32 columns, then 8 lanes cover one row's 128 bytes
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            *reinterpret_cast<float4 *>(patch + lane * 36 + 4 * t) = make_float4(y[4 * t], y[4 * t + 1], y[4 * t + 2], y[4 * t + 3]);
+          __syncwarp();
+          const int rr = lane >> 3, cq = (lane & 7) * 4;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int r = 4 * t + rr;
+            const float4 val = *reinterpret_cast<const float4 *>(patch + r * 36 + cq);
+            if (row0 + r < rows && c0 + cq < nc) {
+              float *dst = out + (row0 + r) * ldo + (size_t)j * kMaxNc + c0 + cq;
+              if ((ldo & 3) == 0 && c0 + cq + 3 < nc) {
+                *reinterpret_cast<float4 *>(dst) = val;
+              } else {
+                dst[0] = val.x;
+                if (c0 + cq + 1 < nc) dst[1] = val.y;
+                if (c0 + cq + 2 < nc) dst[2] = val.z;
+                if (c0 + cq + 3 < nc) dst[3] = val.w;
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the accumulator is handed back
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty[a]) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+size_t image_bytes(int K, int N) {
+  return (size_t)((N + kMaxNc - 1) / kMaxNc) * ((K + kKB - 1) / kKB) * (2 * kBBlock);
+}
+
+int launch_prep(int K, int N, size_t sk, size_t sn, const float *w, unsigned char *image, cudaStream_t st) {
+  const size_t elems = image_bytes(K, N) / 8;
+  const unsigned blocks = (unsigned)((elems + 255) / 256 < 4096 ? (elems + 255) / 256 : 4096);
+  dense_prep_kernel<<<blocks, 256, 0, st>>>(K, N, sk, sn, w, image);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, const float *x,
+                 const unsigned char *image, const float *bias, float *out, float *pooled, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)kStage + (kMaxN + 4 * kPatch) * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+  const int ntiles = (int)((rows + kRows - 1) / kRows);
+  const int nitems = ntiles * ((N + kMaxNc - 1) / kMaxNc);
+  const int grid = nitems < num_sms() ? nitems : num_sms();
+  const int vec_x = (ldx % 4 == 0) && aligned16(x);
+  if (pool == 1) {
+    PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
+    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, x, image, bias, out, pooled);
+  } else if (pool == 2) {
+    PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
+    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, x, image, bias, out, pooled);
+  } else {
+    PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
+    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, x, image, bias, out, pooled);
+  }
+  PC_RETURN_LAUNCH_STATUS();
+}
+
+bool dense_shape_ok(size_t rows, int K, int N) {
+  return rows > 0 && rows < (1ull << 31) * 64 && K >= 1 && K <= 65536 && N >= 16 && N <= kMaxN && N % 16 == 0;
+}
+
+}  // namespace
+}  // namespace pc
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" size_t pc_dense_image_bytes(int K, int N) {
+  if (K <= 0 || N <= 0) return 0;
+  return pc::image_bytes(K, N);
+}
+
+extern "C" int pc_dense_prepare(int K, int N, const float *w, int transpose, void *image, pc_stream_t stream) {
+  if (K <= 0 || N <= 0 || !w || !image) return PC_ERR_INVALID_ARGUMENT;
+  if (N > pc::kMaxN || N % 16 != 0) return PC_ERR_UNSUPPORTED;
+  // transpose = 0: w is (K, N) row-major, Y = X w.   transpose = 1: w is (N, K) row-major, Y = X w^T (input gradients)
+  return pc::launch_prep(K, N, transpose ? 1 : (size_t)N, transpose ? (size_t)K : 1, w, (unsigned char *)image,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int pc_dense_fwd(size_t rows, int K, int N, const float *x, size_t ldx, const void *image, const float *bias,
+                            int relu, float *y, size_t ldy, pc_stream_t stream) {
+  if (rows == 0) return PC_OK;
+  if (!x || !image || !y || ldx < (size_t)K || ldy < (size_t)N) return PC_ERR_INVALID_ARGUMENT;
+  if (!pc::dense_shape_ok(rows, K, N)) return PC_ERR_UNSUPPORTED;
+  return pc::launch_dense(0, rows, K, ldx, N, ldy, 0, relu, x, (const unsigned char *)image, bias, y, nullptr,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int pc_dense_pool_fwd(size_t groups, int group_size, int K, int N, const float *x, size_t ldx, const void *image,
+                                 const float *bias, int relu, float *y_full, size_t ldy, float *y_pooled, size_t ldp,
+                                 pc_stream_t stream) {
+  if (groups == 0) return PC_OK;
+  if (!x || !image || !y_pooled || ldx < (size_t)K || ldp < (size_t)N || (y_full && ldy < (size_t)N))
+    return PC_ERR_INVALID_ARGUMENT;
+  if (group_size != 32 || !pc::dense_shape_ok(groups * 32, K, N)) return PC_ERR_UNSUPPORTED;
+  return pc::launch_dense(y_full ? 2 : 1, groups * 32, K, ldx, N, ldy, ldp, relu, x, (const unsigned char *)image, bias,
+                          y_full, y_pooled, (cudaStream_t)stream);
+}

