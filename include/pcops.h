@@ -226,6 +226,15 @@ PC_API size_t pc_attention_layer_workspace_bytes(int G, int S, int C);
 PC_API int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq, const float *bq,
                            const float *wk, const float *bk, const float *wv, const float *bv, float *out,
                            void *workspace, pc_stream_t stream);
+/* The same layer in two steps for callers that keep the workspace across calls: _prepare builds the tensor-core operand
+ * image of the weights at the start of the workspace (once per set of weights), _fwd_prepared runs the layer on it
+ * without rebuilding (the weight / bias pointers are still read by the Q projection and the epilogue).  The
+ * workspace must have been sized for the largest G used: pc_attention_layer_workspace_bytes(G_max, S, C). */
+PC_API int pc_attention_layer_prepare(int S, int C, const float *wq, const float *bq, const float *wk, const float *bk,
+                               const float *wv, const float *bv, void *workspace, pc_stream_t stream);
+PC_API int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, const float *x, const float *wq,
+                                    const float *bq, const float *wk, const float *bk, const float *wv, const float *bv,
+                                    float *out, void *workspace, pc_stream_t stream);
 
 /* Gradient of pc_attention_fwd w.r.t. Q, K, V given dout (G,HD); dQ (G,HD), dK and dV (G,S,HD) fully overwritten. */
 PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, const float *dout,
@@ -284,7 +293,7 @@ PC_API size_t pc_dense_image_bytes(int K, int N);
 /* Builds the image once per set of weights (cache it across calls).  transpose = 0: w is (K, N) row-major, the layer
  * computes X w (Keras / tf.layers kernel layout [in][out]); transpose = 1: w is (N, K) row-major and the layer computes
  * X w^T -- the input-gradient product dX = dY W^T of a layer whose kernel W is (N_in = N here, ...) see INTEGRATION.md.
- * N % 16 == 0, N <= 1024. */
+ * N <= 1024 (any K; widths that are not multiples of 16 / 32 are zero-padded inside the image). */
 PC_API int pc_dense_prepare(int K, int N, const float *w, int transpose, void *image, pc_stream_t stream);
 /* y (rows, N; row stride ldy) = act(x (rows, K; row stride ldx) . W + bias), act = ReLU when relu != 0, bias (N) or NULL.
  * A batch norm in inference mode folds into W and bias on the caller's side. */
@@ -297,6 +306,14 @@ PC_API int pc_dense_fwd(size_t rows, int K, int N, const float *x, size_t ldx, c
 PC_API int pc_dense_pool_fwd(size_t groups, int group_size, int K, int N, const float *x, size_t ldx, const void *image,
                              const float *bias, int relu, float *y_full, size_t ldy, float *y_pooled, size_t ldp,
                              pc_stream_t stream);
+
+/* Weight and bias gradients of the layer: dw (K, N) = x^T . dy, db (N) = column sums of dy (db may be NULL), x (rows, K; row
+ * stride ldx), dy (rows, N; row stride ldy).  Same 3xTF32 tensor-core scheme; the reduction over the rows is split
+ * over the chip and the partial products are added in a fixed order (deterministic, no float atomics).  The input
+ * gradient dx = dy . W^T is pc_dense_fwd with an image prepared with transpose = 1. */
+PC_API size_t pc_dense_bwd_weight_workspace_bytes(size_t rows, int K, int N);
+PC_API int pc_dense_bwd_weight(size_t rows, int K, int N, const float *x, size_t ldx, const float *dy, size_t ldy,
+                               float *dw, float *db, void *workspace, pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-boundary packing (csrc/io_pack.cu)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "pc_fp_interpolate": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_layer_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_attention_layer_fwd": (_i, [_i, _i, _i] + [_vp] * 11),
+    "pc_attention_layer_prepare": (_i, [_i, _i] + [_vp] * 8),
+    "pc_attention_layer_fwd_prepared": (_i, [_i, _i, _i] + [_vp] * 11),
     "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_scene_cells_workspace_bytes": (_sz, [_i, _i]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "pc_dense_prepare": (_i, [_i, _i, _vp, _i, _vp, _vp]),
     "pc_dense_fwd": (_i, [_sz, _i, _i, _vp, _sz, _vp, _vp, _i, _vp, _sz, _vp]),
     "pc_dense_pool_fwd": (_i, [_sz, _i, _i, _i, _vp, _sz, _vp, _vp, _i, _vp, _sz, _vp, _sz, _vp]),
+    "pc_dense_bwd_weight_workspace_bytes": (_sz, [_sz, _i, _i]),
+    "pc_dense_bwd_weight": (_i, [_sz, _i, _i, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp]),
     "pc_unpack_features": (_i, [_sz, _vp, _vp, _vp, _vp]),
     "pc_narrow_indices_u16": (_i, [_sz, _vp, _vp, _vp]),
 }

@@ -3,8 +3,10 @@
 ``attention_contract(Q, K, V, num_heads, key_dim)`` is the hot part of ``AttentionLayer.call`` (:35-42): the raw
 reshape to heads, QK^T / sqrt(d), softmax over the neighbourhood and the weighted value sum, as one CUDA kernel with a
 matching backward kernel.  ``AttentionLayer`` keeps the reference class's constructor and ``[input, query]`` call
-convention; its three Dense projections (:24-26,31-34) are stock dense layers (torch.nn.Linear here, tf.layers.Dense
-there) and stay outside the accelerated path exactly like the reference's conv2d stack.
+convention.  Its three Dense projections (:24-26,31-34; tf.layers.Dense there) run on this library's tcgen05 Dense
+engine (csrc/gemm_tf32.cu, 3xTF32) in both directions -- forward, input gradient and weight gradient -- so a training
+step never touches a vendor GEMM; without gradients the whole layer is ONE tensor-core kernel (pc_attention_layer_fwd).
+``torch.nn.Linear`` is only the parameter container (weight (out, in), bias).
 """
 import torch
 
@@ -75,6 +77,37 @@ def attention_layer_fused(xq, x, wq, bq, wk, bk, wv, bv):
     return out
 
 
+class PreparedAttentionLayer:
+    """The fused layer with everything that depends on the weights alone kept across calls: the (in, out) copies of the
+    three Dense kernels and the tensor-core operand image inside the workspace (pc_attention_layer_prepare).  Rebuilt
+    only when a parameter changed (torch's version counters) or a larger G needs a larger workspace."""
+
+    def __init__(self):
+        self.key, self.ws, self.G, self.w = None, None, 0, None
+
+    @_lib.on_tensor_device
+    def __call__(self, xq, x, query_net, key_net, value_net):
+        x = _lib.cuda_f32(x.detach(), "x")
+        xq = _lib.cuda_f32(xq.detach(), "xq")
+        G, S, C = x.shape
+        L = _lib.lib()
+        params = [query_net.weight, query_net.bias, key_net.weight, key_net.bias, value_net.weight, value_net.bias]
+        key = tuple((None if p is None else (p.data_ptr(), p._version)) for p in params) + (S, C, str(x.device))
+        if key != self.key or G > self.G:
+            with torch.no_grad():
+                self.w = [None if p is None else (p.detach().t().contiguous() if p.dim() == 2 else p.detach().contiguous())
+                          for p in params]          # Dense kernels as (in, out), biases as they are
+            self.ws = _lib.workspace(max(L.pc_attention_layer_workspace_bytes(G, S, C), 16), x.device)
+            rc = L.pc_attention_layer_prepare(S, C, *[_lib.ptr(t) for t in self.w], _lib.ptr(self.ws), _lib.stream())
+            _lib.check(rc, "pc_attention_layer_prepare")
+            self.key, self.G = key, G
+        out = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        rc = L.pc_attention_layer_fwd_prepared(G, S, C, _lib.ptr(xq), _lib.ptr(x), *[_lib.ptr(t) for t in self.w],
+                                               _lib.ptr(out), _lib.ptr(self.ws), _lib.stream())
+        _lib.check(rc, "pc_attention_layer_fwd_prepared")
+        return out
+
+
 class AttentionLayer(torch.nn.Module):
     """AttentionLayer(output_dim, key_dim, num_heads) -- attention_layer.py:10-45.
 
@@ -89,6 +122,7 @@ class AttentionLayer(torch.nn.Module):
         self.output_dim, self.key_dim, self.num_heads = output_dim, key_dim, num_heads
         self.in_features = in_features
         self.query_net = self.key_net = self.value_net = None
+        self._prepared = PreparedAttentionLayer()
         if in_features is not None:
             self._build(in_features)
 
@@ -111,12 +145,12 @@ class AttentionLayer(torch.nn.Module):
             # inference at the four ScanNet attention widths: projections + contraction in one tensor-core kernel,
             # K and V never stored
             lead = inp.shape[:-2]
-            out = attention_layer_fused(query.reshape(-1, C), inp.reshape(-1, 32, C),
-                                        self.query_net.weight.t().contiguous(), self.query_net.bias,
-                                        self.key_net.weight.t().contiguous(), self.key_net.bias,
-                                        self.value_net.weight.t().contiguous(), self.value_net.bias)
+            out = self._prepared(query.reshape(-1, C), inp.reshape(-1, 32, C), self.query_net, self.key_net, self.value_net)
             return out.reshape(*lead, C)
-        Q = self.query_net(query)          # (B,np,1,HD)
-        K = self.key_net(inp)              # (B,np,S,HD)
-        V = self.value_net(inp)
-        return attention_contract(Q[:, :, 0, :], K, V, self.num_heads, self.key_dim)
+        # training (or a shape the fused kernel does not cover): projections on the tcgen05 Dense engine, forward and
+        # backward (sa_modules.dense_layer), contraction + its backward on pc_attention_fwd / pc_attention_bwd
+        from .sa_modules import dense_layer
+        Q = dense_layer(query, self.query_net.weight, self.query_net.bias, linear_layout=True)    # (B,np,1,HD)
+        K = dense_layer(inp, self.key_net.weight, self.key_net.bias, linear_layout=True)          # (B,np,S,HD)
+        V = dense_layer(inp, self.value_net.weight, self.value_net.bias, linear_layout=True)
+        return attention_contract(Q[..., 0, :], K, V, self.num_heads, self.key_dim)

@@ -325,7 +325,35 @@ size_t attention_layer_wide_image_bytes(int C);
 bool attention_layer_wide_supported(int S, int C);
 int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
                              const float *wk, const float *bk, const float *wv, const float *bv, float *out,
-                             void *workspace, cudaStream_t st);
+                             void *workspace, int mode, cudaStream_t st);
+
+// mode bit 0: build the operand image in the workspace; bit 1: run the layer on an image that is already there
+int attention_layer_run(int G, int S, int C, const float *xq, const float *x, const float *wq, const float *bq,
+                        const float *wk, const float *bk, const float *wv, const float *bv, float *out, void *workspace,
+                        int mode, cudaStream_t st) {
+  const bool run = mode & 2;
+  if (G < 0 || S <= 0 || C <= 0) return PC_ERR_INVALID_ARGUMENT;
+  const bool wide = attention_layer_wide_supported(S, C);
+  if (!wide && (S != kS || C != kC)) return PC_ERR_UNSUPPORTED;  // other shapes: Dense GEMM + pc_attention_fwd
+  if (run && G == 0 && !(mode & 1)) return PC_OK;
+  if (!wq || !wk || !wv || (run && G > 0 && (!xq || !x || !out))) return PC_ERR_INVALID_ARGUMENT;
+  if (!workspace) return PC_ERR_WORKSPACE;
+  if (!aligned16(workspace) || (run && G > 0 && (!aligned16(x) || !aligned16(out)))) return PC_ERR_UNSUPPORTED;
+  if (run && G == 0) mode &= ~2;
+  if (wide) return attention_layer_wide_fwd(G, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, mode, st);
+  unsigned char *image = (unsigned char *)workspace;
+  if (mode & 1) attention_layer_prep_kernel<<<(kN * kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
+  if (!(mode & 2)) PC_RETURN_LAUNCH_STATUS();
+  float *qbuf = reinterpret_cast<float *>(image + ((kImageBytes + 255) / 256) * 256);
+  const int qblocks = (G + 63) / 64 < num_sms() * 2 ? (G + 63) / 64 : num_sms() * 2;
+  attention_layer_q_kernel<<<qblocks, 256, 0, st>>>(G, xq, wq, bq, qbuf);
+  const size_t smem = 4 * kOperandBytes + kImageBytes + 64;
+  PC_CUDA_TRY(allow_smem(attention_layer_c64_kernel, smem));
+  const int ntiles = (int)(((size_t)G * kS + kRows - 1) / kRows);
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  attention_layer_c64_kernel<<<grid, kThreads, smem, st>>>(G, qbuf, x, image, out);
+  PC_RETURN_LAUNCH_STATUS();
+}
 }  // namespace pc
 
 extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
@@ -338,29 +366,18 @@ extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
 extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq,
                                       const float *bq, const float *wk, const float *bk, const float *wv,
                                       const float *bv, float *out, void *workspace, pc_stream_t stream) {
-  if (G < 0 || S <= 0 || C <= 0) return PC_ERR_INVALID_ARGUMENT;
-  if (pc::attention_layer_wide_supported(S, C)) {
-    if (G == 0) return PC_OK;
-    if (!xq || !x || !wq || !wk || !wv || !out) return PC_ERR_INVALID_ARGUMENT;
-    if (!workspace) return PC_ERR_WORKSPACE;
-    if (!pc::aligned16(x) || !pc::aligned16(out) || !pc::aligned16(workspace)) return PC_ERR_UNSUPPORTED;
-    return pc::attention_layer_wide_fwd(G, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, (cudaStream_t)stream);
-  }
-  if (S != pc::kS || C != pc::kC) return PC_ERR_UNSUPPORTED;  // other shapes: Dense + pc_attention_fwd
-  if (G == 0) return PC_OK;
-  if (!xq || !x || !wq || !wk || !wv || !out) return PC_ERR_INVALID_ARGUMENT;
-  if (!workspace) return PC_ERR_WORKSPACE;
-  if (!pc::aligned16(x) || !pc::aligned16(out) || !pc::aligned16(workspace)) return PC_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned char *image = (unsigned char *)workspace;
-  pc::attention_layer_prep_kernel<<<(pc::kN * pc::kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
-  float *qbuf = reinterpret_cast<float *>(image + ((pc::kImageBytes + 255) / 256) * 256);
-  const int qblocks = (G + 63) / 64 < pc::num_sms() * 2 ? (G + 63) / 64 : pc::num_sms() * 2;
-  pc::attention_layer_q_kernel<<<qblocks, 256, 0, st>>>(G, xq, wq, bq, qbuf);
-  const size_t smem = 4 * pc::kOperandBytes + pc::kImageBytes + 64;
-  PC_CUDA_TRY(pc::allow_smem(pc::attention_layer_c64_kernel, smem));
-  const int ntiles = (int)(((size_t)G * pc::kS + pc::kRows - 1) / pc::kRows);
-  const int grid = ntiles < pc::num_sms() ? ntiles : pc::num_sms();
-  pc::attention_layer_c64_kernel<<<grid, pc::kThreads, smem, st>>>(G, qbuf, x, image, out);
-  PC_RETURN_LAUNCH_STATUS();
+  return pc::attention_layer_run(G, S, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, 3, (cudaStream_t)stream);
+}
+
+extern "C" int pc_attention_layer_prepare(int S, int C, const float *wq, const float *bq, const float *wk,
+                                          const float *bk, const float *wv, const float *bv, void *workspace,
+                                          pc_stream_t stream) {
+  return pc::attention_layer_run(0, S, C, nullptr, nullptr, wq, bq, wk, bk, wv, bv, nullptr, workspace, 1,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, const float *x, const float *wq,
+                                               const float *bq, const float *wk, const float *bk, const float *wv,
+                                               const float *bv, float *out, void *workspace, pc_stream_t stream) {
+  return pc::attention_layer_run(G, S, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, 2, (cudaStream_t)stream);
 }

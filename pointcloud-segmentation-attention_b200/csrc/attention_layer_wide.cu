@@ -343,14 +343,18 @@ size_t attention_layer_wide_image_bytes(int C) { return (size_t)(C / 128) * (C /
 
 bool attention_layer_wide_supported(int S, int C) { return S == kS && (C == 128 || C == 256 || C == 512); }
 
+// mode bit 0: build the weight image (depends on wk / wv only: callers that keep the workspace across calls do it once
+// per set of weights); bit 1: run the layer.
 int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
                              const float *wk, const float *bk, const float *wv, const float *bv, float *out,
-                             void *workspace, cudaStream_t st) {
+                             void *workspace, int mode, cudaStream_t st) {
   unsigned char *image = (unsigned char *)workspace;
   const size_t img = attention_layer_wide_image_bytes(C);
   float *qbuf = reinterpret_cast<float *>(image + img);
   const size_t elems = img / 8;
-  wide_prep_kernel<<<(unsigned)((elems + 255) / 256 < 4096 ? (elems + 255) / 256 : 4096), 256, 0, st>>>(C, wk, wv, image);
+  if (mode & 1)
+    wide_prep_kernel<<<(unsigned)((elems + 255) / 256 < 4096 ? (elems + 255) / 256 : 4096), 256, 0, st>>>(C, wk, wv, image);
+  if (!(mode & 2)) PC_RETURN_LAUNCH_STATUS();
   const int qb = (G + 7) / 8 < num_sms() * 4 ? (G + 7) / 8 : num_sms() * 4;
   wide_q_kernel<<<qb, 256, 0, st>>>(G, C, xq, wq, bq, qbuf);
   const size_t smem = 2 * (size_t)kStage + 2 * kMaxC * sizeof(float) + 8 * sizeof(uint64_t) + 16;

@@ -121,7 +121,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
 __global__ void __launch_bounds__(kThreads, 1)
-dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, int vec_x,
+dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, int vec_x, int vec_o,
                   const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
                   float *__restrict__ out, float *__restrict__ pooled) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -199,7 +199,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
       if (tid == 0) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
         const unsigned char *src = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
         const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
-        const uint32_t bytes = (uint32_t)nc * 128u;
+        const uint32_t bytes = (uint32_t)((nc + 15) & ~15) * 128u;   // the MMA's N is a multiple of 16: zero rows beyond nc
         asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(2u * bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                      "l"(src), "r"(bytes), "r"(full[s])
@@ -240,8 +240,8 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
         const int a = w & 1, j = item % nchunk;
         const int nc = min(kMaxNc, N - j * kMaxNc);
-        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nc >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc rounded up to 16, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
         mbar_wait(t_empty[a], ((w >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t acc = 0;
@@ -322,7 +322,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
             const float4 val = *reinterpret_cast<const float4 *>(patch + r * 36 + cq);
             if (row0 + r < rows && c0 + cq < nc) {
               float *dst = out + (row0 + r) * ldo + (size_t)j * kMaxNc + c0 + cq;
-              if ((ldo & 3) == 0 && c0 + cq + 3 < nc) {
+              if (vec_o && c0 + cq + 3 < nc) {
                 *reinterpret_cast<float4 *>(dst) = val;
               } else {
                 dst[0] = val.x;
@@ -345,6 +345,262 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient: dW (K, N) = X^T (K, rows) . dY (rows, N), db (N) = column sums of dY.
+// The reduction dimension is the ROW index, so both operands are transposed on the way into shared memory: producers
+// read 32 rows x (128 | nc) columns of X / dY with 128-bit loads (lane = row, so that the scattered 4-byte stores of a
+// warp -- element (column, row) of the K-major operand -- fall into 32 different banks of the swizzled layout) and write
+// TF32 hi / lo parts.  Work item = (tile of 128 input channels, chunk of <= 256 output channels, split of the rows);
+// each item leaves its partial product in the workspace, a second kernel adds the partials in ascending split order
+// (deterministic; no float atomics).  db is accumulated by the same producers (items of channel tile 0 only).
+__global__ void __launch_bounds__(kThreads, 1)
+dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int splits, size_t rows_per_split, int vec_x,
+                        int vec_y, const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ part_w,
+                        float *__restrict__ part_b) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *stage_buf = smem;
+  float *s_patch = reinterpret_cast<float *>(smem + 2 * kStage);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_patch + 4 * kPatch);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+  const uint32_t full[2] = {bar0, bar0 + 8}, empty[2] = {bar0 + 16, bar0 + 24};
+  const uint32_t t_full[2] = {bar0 + 32, bar0 + 40}, t_empty[2] = {bar0 + 48, bar0 + 56};
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(128u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty[s]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full[s]), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty[s]), "r"(128u));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *s_tmem;
+
+  const int nmt = (K + kRows - 1) / kRows, nchunk = (N + kMaxNc - 1) / kMaxNc;
+  const int nitems = nmt * nchunk * splits;            // item = (mt * nchunk + j) * splits + s
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage_buf);
+  auto item_rows = [&](int item, size_t &r_lo, int &nblk) {
+    const int sp = item % splits;
+    r_lo = (size_t)sp * rows_per_split;
+    const size_t r_hi = r_lo + rows_per_split < rows ? r_lo + rows_per_split : rows;
+    nblk = r_lo < r_hi ? (int)((r_hi - r_lo + kKB - 1) / kKB) : 0;
+  };
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producers (lane = row of the 32-row block)
+    int it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int mj = item / splits, mt = mj / nchunk, j = mj - mt * nchunk, sp = item - mj * splits;
+      const int nc = min(kMaxNc, N - j * kMaxNc);
+      size_t r_lo;
+      int nblk;
+      item_rows(item, r_lo, nblk);
+      const size_t r_end = r_lo + rows_per_split < rows ? r_lo + rows_per_split : rows;
+      float bsum[16][4];                                 // column sums of dY over this item's rows (this lane's rows)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bsum[i][0] = bsum[i][1] = bsum[i][2] = bsum[i][3] = 0.f;
+      for (int blk = 0; blk < nblk; ++blk, ++it) {
+        const size_t row = r_lo + (size_t)blk * kKB + lane;
+        const bool rin = row < r_end;
+        float4 xa[8], yb[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                    // X: columns 128 mt + 4 (8 warp + i) ..
+          const int c0 = mt * kRows + 4 * (warp * 8 + i);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rin && c0 < K) {
+            const float *src = x + row * ldx + c0;
+            if (vec_x && c0 + 3 < K) v = __ldg(reinterpret_cast<const float4 *>(src));
+            else {
+              v.x = __ldg(src);
+              if (c0 + 1 < K) v.y = __ldg(src + 1);
+              if (c0 + 2 < K) v.z = __ldg(src + 2);
+              if (c0 + 3 < K) v.w = __ldg(src + 3);
+            }
+          }
+          xa[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                   // dY: columns 256 j + 4 (16 warp + i) ..
+          const int cl = 4 * (warp * 16 + i), c0 = j * kMaxNc + cl;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rin && cl < nc) {
+            const float *src = dy + row * ldy + c0;
+            if (vec_y && cl + 3 < nc) v = __ldg(reinterpret_cast<const float4 *>(src));
+            else {
+              v.x = __ldg(src);
+              if (cl + 1 < nc) v.y = __ldg(src + 1);
+              if (cl + 2 < nc) v.z = __ldg(src + 2);
+              if (cl + 3 < nc) v.w = __ldg(src + 3);
+            }
+          }
+          yb[i] = v;
+          bsum[i][0] += v.x; bsum[i][1] += v.y; bsum[i][2] += v.z; bsum[i][3] += v.w;
+        }
+        const int s = it & 1;
+        mbar_wait(empty[s], ((it >> 1) & 1) ^ 1);
+        unsigned char *st = stage_buf + s * kStage;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m0 = 4 * (warp * 8 + i);
+          const float v[4] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h = tf32_rna(v[e]), l = tf32_rna(v[e] - h);
+            const int off = block_offset(m0 + e, lane);
+            *reinterpret_cast<float *>(st + off) = h;
+            *reinterpret_cast<float *>(st + kABlock + off) = l;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n0 = 4 * (warp * 16 + i);
+          if (n0 < nc) {                                   // warp-uniform
+            const float v[4] = {yb[i].x, yb[i].y, yb[i].z, yb[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float h = tf32_rna(v[e]), l = tf32_rna(v[e] - h);
+              const int off = block_offset(n0 + e, lane);
+              *reinterpret_cast<float *>(st + 2 * kABlock + off) = h;
+              *reinterpret_cast<float *>(st + 2 * kABlock + kBBlock + off) = l;
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
+      }
+      if (mt == 0 && part_b) {                             // db partial of (chunk j, split sp): sum over the 32 lanes = rows
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = bsum[i][e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PC_FULL_MASK, v, o);
+            const int cl = 4 * (warp * 16 + i) + e;
+            if (lane == 0 && cl < nc) part_b[(size_t)sp * N + j * kMaxNc + cl] = v;
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int it = 0, w = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
+        const int a = w & 1, j = (item / splits) % nchunk;
+        const int nc = min(kMaxNc, N - j * kMaxNc);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        size_t r_lo;
+        int nblk;
+        item_rows(item, r_lo, nblk);
+        mbar_wait(t_empty[a], ((w >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc = 0;
+        for (int blk = 0; blk < nblk; ++blk, ++it) {
+          const int s = it & 1;
+          mbar_wait(full[s], (it >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = stage_s + s * kStage, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + kBBlock;
+#pragma unroll
+          for (int split = 0; split < 3; ++split) {
+            const uint32_t as = (split == 2) ? a_lo : a_hi, bs = (split == 1) ? b_lo : b_hi;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              mma_tf32(tmem + a * kMaxNc, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
+              acc = 1;
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty[s]) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_full[a]) : "memory");
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: partial (128 x nc) tile -> workspace
+    const int qtr = warp & 3;
+    float *patch = s_patch + qtr * kPatch;
+    int w = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
+      const int a = w & 1, mj = item / splits, mt = mj / nchunk, j = mj - mt * nchunk, sp = item - mj * splits;
+      const int nc = min(kMaxNc, N - j * kMaxNc);
+      size_t r_lo;
+      int nblk;
+      item_rows(item, r_lo, nblk);
+      mbar_wait(t_full[a], (w >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * kMaxNc;
+      float *dst_base = part_w + (size_t)sp * K * N;
+      const int k0 = mt * kRows + qtr * 32;                // this warp's 32 input channels
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        uint32_t v[32];
+        if (nblk > 0) {
+          PCG_TMEM_LD32(taddr + c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {                                           // an empty split never touched the accumulator
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = 0u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          *reinterpret_cast<float4 *>(patch + lane * 36 + 4 * t) =
+              make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]), __uint_as_float(v[4 * t + 2]),
+                          __uint_as_float(v[4 * t + 3]));
+        __syncwarp();
+        const int rr = lane >> 3, cq = (lane & 7) * 4;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int r = 4 * t + rr;
+          const float4 val = *reinterpret_cast<const float4 *>(patch + r * 36 + cq);
+          if (k0 + r < K && c0 + cq < nc) {
+            float *dst = dst_base + (size_t)(k0 + r) * N + (size_t)j * kMaxNc + c0 + cq;
+            dst[0] = val.x;
+            if (c0 + cq + 1 < nc) dst[1] = val.y;
+            if (c0 + cq + 2 < nc) dst[2] = val.z;
+            if (c0 + cq + 3 < nc) dst[3] = val.w;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty[a]) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+  }
+}
+
+// dst[i] = sum over splits (ascending) of part[s][i]
+__global__ void __launch_bounds__(256)
+split_sum_kernel(size_t count, int splits, const float *__restrict__ part, float *__restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(part + (size_t)s * count + i);
+    dst[i] = acc;
+  }
+}
+
+int bwd_weight_splits(size_t rows, int K, int N) {
+  const int nmt = (K + kRows - 1) / kRows, nchunk = (N + kMaxNc - 1) / kMaxNc;
+  long long sp = (2LL * 148) / ((long long)nmt * nchunk);
+  const long long max_sp = (long long)((rows + 4 * kKB - 1) / (4 * kKB));   // at least 4 row blocks per split
+  if (sp > max_sp) sp = max_sp;
+  if (sp > 512) sp = 512;
+  return sp < 1 ? 1 : (int)sp;
+}
+
 size_t image_bytes(int K, int N) {
   return (size_t)((N + kMaxNc - 1) / kMaxNc) * ((K + kKB - 1) / kKB) * (2 * kBBlock);
 }
@@ -363,21 +619,22 @@ int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, si
   const int nitems = ntiles * ((N + kMaxNc - 1) / kMaxNc);
   const int grid = nitems < num_sms() ? nitems : num_sms();
   const int vec_x = (ldx % 4 == 0) && aligned16(x);
+  const int vec_o = (ldo % 4 == 0) && aligned16(out);
   if (pool == 1) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
-    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, x, image, bias, out, pooled);
+    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else if (pool == 2) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
-    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, x, image, bias, out, pooled);
+    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
-    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, x, image, bias, out, pooled);
+    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   }
   PC_RETURN_LAUNCH_STATUS();
 }
 
 bool dense_shape_ok(size_t rows, int K, int N) {
-  return rows > 0 && rows < (1ull << 31) * 64 && K >= 1 && K <= 65536 && N >= 16 && N <= kMaxN && N % 16 == 0;
+  return rows > 0 && rows < (1ull << 31) * 64 && K >= 1 && K <= 65536 && N >= 1 && N <= kMaxN;
 }
 
 }  // namespace
@@ -391,7 +648,7 @@ extern "C" size_t pc_dense_image_bytes(int K, int N) {
 
 extern "C" int pc_dense_prepare(int K, int N, const float *w, int transpose, void *image, pc_stream_t stream) {
   if (K <= 0 || N <= 0 || !w || !image) return PC_ERR_INVALID_ARGUMENT;
-  if (N > pc::kMaxN || N % 16 != 0) return PC_ERR_UNSUPPORTED;
+  if (N > pc::kMaxN) return PC_ERR_UNSUPPORTED;
   // transpose = 0: w is (K, N) row-major, Y = X w.   transpose = 1: w is (N, K) row-major, Y = X w^T (input gradients)
   return pc::launch_prep(K, N, transpose ? 1 : (size_t)N, transpose ? (size_t)K : 1, w, (unsigned char *)image,
                          (cudaStream_t)stream);
@@ -415,4 +672,41 @@ extern "C" int pc_dense_pool_fwd(size_t groups, int group_size, int K, int N, co
   if (group_size != 32 || !pc::dense_shape_ok(groups * 32, K, N)) return PC_ERR_UNSUPPORTED;
   return pc::launch_dense(y_full ? 2 : 1, groups * 32, K, ldx, N, ldy, ldp, relu, x, (const unsigned char *)image, bias,
                           y_full, y_pooled, (cudaStream_t)stream);
+}
+
+extern "C" size_t pc_dense_bwd_weight_workspace_bytes(size_t rows, int K, int N) {
+  if (rows == 0 || K <= 0 || N <= 0) return 0;
+  const int sp = pc::bwd_weight_splits(rows, K, N);
+  return ((size_t)sp * K * N + (size_t)sp * N) * sizeof(float);
+}
+
+extern "C" int pc_dense_bwd_weight(size_t rows, int K, int N, const float *x, size_t ldx, const float *dy, size_t ldy,
+                                   float *dw, float *db, void *workspace, pc_stream_t stream) {
+  if (K <= 0 || N <= 0 || !dw) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {   // no rows: the gradients are zero
+    PC_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * N, st));
+    if (db) PC_CUDA_TRY(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+    return PC_OK;
+  }
+  if (!x || !dy || ldx < (size_t)K || ldy < (size_t)N) return PC_ERR_INVALID_ARGUMENT;
+  if (N > pc::kMaxN || K > 65536) return PC_ERR_UNSUPPORTED;
+  if (!workspace) return PC_ERR_WORKSPACE;
+  const int sp = pc::bwd_weight_splits(rows, K, N);
+  size_t rps = (rows + sp - 1) / sp;
+  rps = (rps + pc::kKB - 1) / pc::kKB * pc::kKB;
+  float *part_w = (float *)workspace, *part_b = part_w + (size_t)sp * K * N;
+  const size_t smem = 2 * (size_t)pc::kStage + 4 * pc::kPatch * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+  PC_CUDA_TRY(pc::allow_smem(pc::dense_bwd_weight_kernel, smem));
+  const int nitems = ((K + pc::kRows - 1) / pc::kRows) * ((N + pc::kMaxNc - 1) / pc::kMaxNc) * sp;
+  const int grid = nitems < pc::num_sms() ? nitems : pc::num_sms();
+  pc::dense_bwd_weight_kernel<<<grid, pc::kThreads, smem, st>>>(rows, K, ldx, N, ldy, sp, rps, (ldx % 4 == 0) && pc::aligned16(x),
+                                                              (ldy % 4 == 0) && pc::aligned16(dy), x, dy, part_w,
+                                                              db ? part_b : nullptr);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  const size_t cnt = (size_t)K * N;
+  pc::split_sum_kernel<<<(unsigned)((cnt + 255) / 256 < 2048 ? (cnt + 255) / 256 : 2048), 256, 0, st>>>(cnt, sp, part_w, dw);
+  if (db) pc::split_sum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>((size_t)N, sp, part_b, db);
+  PC_RETURN_LAUNCH_STATUS();
 }

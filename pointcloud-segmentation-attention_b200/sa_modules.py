@@ -19,7 +19,7 @@ layers and is out of scope here; training-time Dense gradients are in ``attentio
 import torch
 
 from . import _lib
-from .attention_layer import attention_layer_fused
+from .attention_layer import PreparedAttentionLayer
 from .pointnet_util import sample_and_group, sample_and_group_all
 
 BN_EPSILON = 1e-3   # tf.contrib.layers.batch_norm default, as used by tf_util.batch_norm_template (tf_util.py:512-530)
@@ -72,6 +72,63 @@ def dense_max_pool(x, image, relu=True, keep_full=False):
                                       image.N, _lib.stream())
     _lib.check(rc, "pc_dense_pool_fwd")
     return (pooled, full) if keep_full else pooled
+
+
+@_lib.on_tensor_device
+def dense_weight_grad(x, dy, want_bias=True):
+    """dW (K, N) = x^T . dy and db (N) = column sums of dy for x (..., K), dy (..., N) -- pc_dense_bwd_weight."""
+    x = _lib.cuda_f32(x.detach(), "x")
+    dy = _lib.cuda_f32(dy.detach(), "dy")
+    K, N = x.shape[-1], dy.shape[-1]
+    rows = x.numel() // K
+    if dy.numel() // N != rows:
+        raise ValueError("dense_weight_grad expects x (..., K) and dy (..., N) over the same rows")
+    L = _lib.lib()
+    dw = torch.empty((K, N), dtype=torch.float32, device=x.device)
+    db = torch.empty(N, dtype=torch.float32, device=x.device) if want_bias else None
+    ws = _lib.workspace(L.pc_dense_bwd_weight_workspace_bytes(rows, K, N), x.device)
+    rc = L.pc_dense_bwd_weight(rows, K, N, _lib.ptr(x), K, _lib.ptr(dy), N, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws),
+                               _lib.stream())
+    _lib.check(rc, "pc_dense_bwd_weight")
+    return dw, db
+
+
+class _DenseFn(torch.autograd.Function):
+    """y = act(x . W + b) with every product of the forward and the backward on the tcgen05 engine:
+    dx = (dy * act') . W^T (transposed weight image), dW = x^T . (dy * act'), db = column sums.
+    ``linear_layout``: W is stored (cout, cin) as torch.nn.Linear keeps it (the image is built with the matching strides,
+    nothing is copied); otherwise (cin, cout) as TensorFlow's Dense / conv kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, linear_layout):
+        image = DenseImage(weight, bias, transpose=linear_layout)
+        y = dense(x, image, relu)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.cfg = (relu, linear_layout, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        relu, linear_layout, has_bias = ctx.cfg
+        dy = _lib.cuda_f32(dy, "dy")
+        if relu:
+            dy = dy * (y > 0).to(dy.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # forward image reads W as (K=cin, N=cout); the input gradient needs (K=cout, N=cin) of the same memory
+            dx = dense(dy, DenseImage(weight, None, transpose=not linear_layout))
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw, db = dense_weight_grad(x, dy, want_bias=has_bias)       # (cin, cout)
+            if linear_layout:
+                dw = dw.t()
+        return dx, dw, (db if has_bias else None), None, None
+
+
+def dense_layer(x, weight, bias=None, relu=False, linear_layout=False):
+    """Differentiable Dense / 1x1-conv layer on the tensor cores (forward and backward)."""
+    return _DenseFn.apply(_lib.cuda_f32(x, "x"), _lib.cuda_f32(weight, "weight"),
+                          None if bias is None else _lib.cuda_f32(bias, "bias"), bool(relu), bool(linear_layout))
 
 
 def fold_batch_norm(weight, bias, gamma, beta, moving_mean, moving_var, eps=BN_EPSILON):
@@ -200,6 +257,7 @@ class PointnetSAModuleAttention(torch.nn.Module):
         self.register_buffer("moving_mean", torch.zeros(C))
         self.register_buffer("moving_variance", torch.ones(C))
         self.mlp2 = SharedMLP(C, mlp2, bn) if mlp2 else None
+        self._attention = PreparedAttentionLayer()
 
     def forward(self, xyz, points):
         with torch.no_grad():
@@ -211,9 +269,7 @@ class PointnetSAModuleAttention(torch.nn.Module):
                 pooled, feats = None, self.mlp(new_points)                 # (B, npoint, nsample, C)
             B, m, ns, C = feats.shape
             x = feats.reshape(B * m, ns, C)
-            att = attention_layer_fused(x[:, 0, :].contiguous(), x, self.query_net.weight.t().contiguous(), self.query_net.bias,
-                                        self.key_net.weight.t().contiguous(), self.key_net.bias,
-                                        self.value_net.weight.t().contiguous(), self.value_net.bias).reshape(B, m, C)
+            att = self._attention(x[:, 0, :].contiguous(), x, self.query_net, self.key_net, self.value_net).reshape(B, m, C)
             s = self.gamma / torch.sqrt(self.moving_variance + BN_EPSILON)
             out = (att - self.moving_mean) * s + self.beta
             if pooled is not None:

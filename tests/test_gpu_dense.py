@@ -162,3 +162,91 @@ def test_sa_module_attention_matches_the_reference_graph(level, and_pooling):
     want = cpu.sa_attention_tail(new_points, layers, Wd[0], bd[0], Wd[1], bd[1], Wd[2], bd[2], bn_out, and_pooling)
     check(out, want, "sa_module_attention%s level %d" % ("_and_pooling" if and_pooling else "", level + 1),
           scale_tol=2e-5, rel_tol=1e-4)
+
+
+@pytest.mark.parametrize("rows,K,N", [(4096, 64, 128), (1000, 9, 32), (70000, 64, 64), (5000, 259, 256), (2048, 512, 1024),
+                                      (96, 131, 48), (33, 300, 16)])
+def test_dense_weight_gradient(rows, K, N):
+    """dW = X^T dY and db = column sums of dY on the tensor cores (row-split partial products summed in a fixed order):
+    against float64, and bit-identical from run to run."""
+    rng = np.random.default_rng(rows + K)
+    x = rng.standard_normal((rows, K), dtype=np.float32)
+    dy = rng.standard_normal((rows, N), dtype=np.float32)
+    dw, db = sam.dense_weight_grad(cu(x), cu(dy))
+    check(dw, x.astype(np.float64).T @ dy.astype(np.float64), "dW %dx%dx%d" % (rows, K, N))
+    check(db, dy.astype(np.float64).sum(0), "db")
+    dw2, db2 = sam.dense_weight_grad(cu(x), cu(dy))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("linear_layout,relu", [(False, True), (True, False)])
+def test_dense_layer_autograd_matches_float64(linear_layout, relu):
+    rng = np.random.default_rng(3)
+    rows, cin, cout = 3000, 67, 96
+    x = rng.standard_normal((rows, cin), dtype=np.float32)
+    W = (rng.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    g = rng.standard_normal((rows, cout), dtype=np.float32)
+    xt = cu(x).requires_grad_(True)
+    wt = (cu(W).t().contiguous() if linear_layout else cu(W)).requires_grad_(True)
+    bt = cu(b).requires_grad_(True)
+    y = sam.dense_layer(xt, wt, bt, relu=relu, linear_layout=linear_layout)
+    y.backward(cu(g))
+    x64 = torch.from_numpy(x).double().requires_grad_(True)
+    w64 = torch.from_numpy(W).double().requires_grad_(True)
+    b64 = torch.from_numpy(b).double().requires_grad_(True)
+    y64 = x64 @ w64 + b64
+    if relu:
+        # the ReLU mask is taken where the fp32 forward is positive; entries within rounding of 0 may differ: use ours
+        y64 = y64 * (y.detach().cpu().double() > 0)
+    y64.backward(torch.from_numpy(g).double())
+    check(y, y64.detach().numpy(), "forward")
+    check(xt.grad, x64.grad.numpy(), "dx")
+    check(wt.grad.t() if linear_layout else wt.grad, w64.grad.numpy(), "dW")
+    check(bt.grad, b64.grad.numpy(), "db")
+
+
+@pytest.mark.parametrize("C", [64, 128])
+def test_attention_layer_training_step_runs_on_the_dense_engine(C):
+    """AttentionLayer under autograd (attention_points/train.py:337-339 minimises through it): Dense Q / K / V forward,
+    their input and weight gradients and the contraction's backward, none of it through a vendor GEMM; against a
+    float64 torch restatement of attention_layer.py:29-45 (raw reshape included)."""
+    from pcops_b200.attention_layer import AttentionLayer
+    rng = np.random.default_rng(C)
+    B, m, S = 2, 96, 32
+    x = rng.standard_normal((B, m, S, C), dtype=np.float32)
+    layer = AttentionLayer(4, 4, C // 4, in_features=C).to(DEV)
+    xt = cu(x).requires_grad_(True)
+    g = rng.standard_normal((B, m, C), dtype=np.float32)
+    out = layer([xt, xt[:, :, :1, :]])
+    out.backward(cu(g))
+
+    def f64(t):
+        return t.detach().cpu().double().requires_grad_(True)
+    x64 = f64(xt)
+    P = [f64(p) for p in (layer.query_net.weight, layer.query_net.bias, layer.key_net.weight, layer.key_net.bias,
+                          layer.value_net.weight, layer.value_net.bias)]
+    Q = x64[:, :, :1, :] @ P[0].t() + P[1]
+    K = x64 @ P[2].t() + P[3]
+    V = x64 @ P[4].t() + P[5]
+    H = C // 4
+    Qh, Kh, Vh = (t.reshape(B, m, H, t.shape[2], 4) for t in (Q, K, V))      # attention_layer.py:35
+    w = torch.softmax(Qh @ Kh.transpose(-1, -2) / 2.0, dim=-1)
+    ref = (w @ Vh).reshape(B, m, C)
+    ref.backward(torch.from_numpy(g).double())
+    check(out, ref.detach().numpy(), "layer forward C=%d" % C, scale_tol=1e-5, rel_tol=1e-4)
+    check(xt.grad, x64.grad.numpy(), "dX", scale_tol=2e-5, rel_tol=2e-4)
+    for name, p, p64 in zip(("dWq", "dbq", "dWk", "dbk", "dWv", "dbv"),
+                            (layer.query_net.weight, layer.query_net.bias, layer.key_net.weight, layer.key_net.bias,
+                             layer.value_net.weight, layer.value_net.bias), P):
+        check(p.grad, p64.grad.numpy(), name, scale_tol=2e-5, rel_tol=2e-4)
+    # inference through the same module: ONE fused kernel on a cached operand image, same values as the composition
+    with torch.no_grad():
+        fused = layer([xt, xt[:, :, :1, :]])
+        prepared = layer._prepared.ws
+        fused2 = layer([xt, xt[:, :, :1, :]])
+        assert layer._prepared.ws is prepared and torch.equal(fused, fused2)          # nothing rebuilt
+        check(fused, ref.detach().numpy(), "fused inference", scale_tol=1e-5, rel_tol=1e-4)
+        layer.key_net.bias.add_(0.5)                                                   # in-place update -> rebuilt
+        fused3 = layer([xt, xt[:, :, :1, :]])
+        assert layer._prepared.ws is not prepared and not torch.equal(fused, fused3)
