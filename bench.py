@@ -68,6 +68,9 @@ def parse():
                     help="1: also time the forward with the whole AttentionLayer (Dense Q/K/V + contraction on tcgen05) per level")
     ap.add_argument("--scenes", type=int, default=39,
                     help="whole scans per GPU in the config-4 region (0: skip); 39 x 8 GPUs = the 312 scans of the validation split")
+    ap.add_argument("--full-model", type=int, default=1,
+                    help="1: also time the WHOLE attention-model inference forward (4 SA-attention + 4 FP levels + fc, every "
+                         "dense layer on the tcgen05 engine, no stand-in tensors)")
     ap.add_argument("--config5", type=int, default=1, help="1: the config-5 sweep (FPS / ball / kNN, N = 16k..1M, npoint 1k..16k, B = 64 sharded)")
     ap.add_argument("--sweep-batch", type=int, default=64, help="scenes of the config-5 sweep, sharded over the ranks")
     ap.add_argument("--sweep-max-n", type=int, default=1 << 20)
@@ -932,6 +935,47 @@ def main():
         del lp
         torch.cuda.empty_cache()
 
+    # ---- timed region 3c: the WHOLE inference forward of the attention model (pointnet2_sem_seg_attention.py:28-62):
+    # geometry + shared MLPs + attention layers + FP MLPs + fc, every tensor produced by the layer before it ----------
+    full_model = None
+    if args.full_model:
+        try:
+            from pcops_b200.model_pipeline import ScanNetAttentionModel
+            MD = max(1, min(D, 4))
+            models = [ScanNetAttentionModel(B, NPOINTS, 6, dev, seed=rank * 16 + d) for d in range(MD)]
+            for md in models:
+                md.set_inputs(dev_xyz[0], dev_feat[0])
+                if use_graph:
+                    md.capture()
+                else:
+                    md.forward()
+            torch.cuda.synchronize(dev)
+
+            def step_model(i):
+                md = models[i % MD]
+                md.set_inputs(dev_xyz[i % R], dev_feat[i % R])
+                if use_graph:
+                    md.replay()
+                else:
+                    md.forward()
+            fm_ok, fm_flops, fm_launches = 1.0, models[0].dense_flops(), models[0].launches_per_step
+        except Exception as exc:
+            fm_ok, full_model = -1.0, {"error": repr(exc)[:300]}
+        # the timed region itself contains collectives (agreeing on the repeats): only enter it if every rank is ready
+        if sharding.max_vector_over_ranks([fm_ok])[0] > 0:
+            fm_block, fm_reps, _, _, _ = timed_region(step_model, models)
+            full_model = {"workload": "whole attention-model inference forward, B=%d x %d, xyz + 6 features -> %d-class logits: "
+                                      "4 x (sample_and_group, shared MLP, AttentionLayer), 4 x (three_nn, interpolate, MLP), fc1, "
+                                      "fc2; no stand-in tensors; dense layers = 3xTF32 tcgen05" % (B, NPOINTS, 21),
+                          "value": world * B * K / (fm_block * 1e-3), "unit": UNIT, "ms_per_step": fm_block / K,
+                          "repeats": fm_reps, "batches_in_flight": MD, "dense_gflop_per_step": fm_flops / 1e9,
+                          "dense_tflops_fp32_equivalent": fm_flops / (fm_block / K * 1e-3) / 1e12,
+                          "gpu_launches": fm_launches * K * fm_reps * world}
+            del models
+            torch.cuda.empty_cache()
+        elif full_model is None:
+            full_model = {"error": "the whole-model region failed on another rank"}
+
     # ---- timed region 4: config 4, whole scans through the GPU chunker + forward + map_back -------------------
     config4 = None
     if args.scenes > 0 and args.attention and not args.fuse_layers:
@@ -1145,6 +1189,7 @@ def main():
         "reference_gpu_kernels": ref_gpu,
         "config1_single_scene_sa1": config1,
         "with_attention_layers": with_layers,
+        "full_model_inference": full_model,
         "config3_training_step": train,
         "config4_whole_scene": config4,
         "config5_sweep": config5,
@@ -1156,6 +1201,7 @@ def main():
         "config4": brief(config4, ("value", "ms_per_scan", "scans_total", "chunker_ms_per_scan", "error")),
         "config5": brief(config5, ("total_ms", "failed", "error")),
         "with_attention_layers": brief(with_layers, ("value",)),
+        "full_model_inference": brief(full_model, ("value", "ms_per_step", "dense_tflops_fp32_equivalent", "error")),
         "roofline_frac": roofline["frac"], "step_hbm_frac": step_shape["step_hbm_frac"]}
     print(json.dumps(line))
     if world > 1:

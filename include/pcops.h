@@ -228,13 +228,14 @@ PC_API int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const fl
                            void *workspace, pc_stream_t stream);
 /* The same layer in two steps for callers that keep the workspace across calls: _prepare builds the tensor-core operand
  * image of the weights at the start of the workspace (once per set of weights), _fwd_prepared runs the layer on it
- * without rebuilding (the weight / bias pointers are still read by the Q projection and the epilogue).  The
+ * without rebuilding (the weight / bias pointers are still read by the Q projection and the epilogue); xq_stride is the
+ * row stride of xq in floats (0 = C; S * C with xq = x reads sample 0 of every group, attention_layer.py:259).  The
  * workspace must have been sized for the largest G used: pc_attention_layer_workspace_bytes(G_max, S, C). */
 PC_API int pc_attention_layer_prepare(int S, int C, const float *wq, const float *bq, const float *wk, const float *bk,
                                const float *wv, const float *bv, void *workspace, pc_stream_t stream);
-PC_API int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, const float *x, const float *wq,
-                                    const float *bq, const float *wk, const float *bk, const float *wv, const float *bv,
-                                    float *out, void *workspace, pc_stream_t stream);
+PC_API int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, size_t xq_stride, const float *x,
+                                    const float *wq, const float *bq, const float *wk, const float *bk, const float *wv,
+                                    const float *bv, float *out, void *workspace, pc_stream_t stream);
 
 /* Gradient of pc_attention_fwd w.r.t. Q, K, V given dout (G,HD); dQ (G,HD), dK and dV (G,S,HD) fully overwritten. */
 PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, const float *dout,

@@ -53,7 +53,7 @@ SIGNATURES = {
     "pc_attention_layer_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_attention_layer_fwd": (_i, [_i, _i, _i] + [_vp] * 11),
     "pc_attention_layer_prepare": (_i, [_i, _i] + [_vp] * 8),
-    "pc_attention_layer_fwd_prepared": (_i, [_i, _i, _i] + [_vp] * 11),
+    "pc_attention_layer_fwd_prepared": (_i, [_i, _i, _i, _vp, _sz] + [_vp] * 10),
     "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_scene_cells_workspace_bytes": (_sz, [_i, _i]),

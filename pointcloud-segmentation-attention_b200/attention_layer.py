@@ -102,7 +102,7 @@ class PreparedAttentionLayer:
             _lib.check(rc, "pc_attention_layer_prepare")
             self.key, self.G = key, G
         out = torch.empty((G, C), dtype=torch.float32, device=x.device)
-        rc = L.pc_attention_layer_fwd_prepared(G, S, C, _lib.ptr(xq), _lib.ptr(x), *[_lib.ptr(t) for t in self.w],
+        rc = L.pc_attention_layer_fwd_prepared(G, S, C, _lib.ptr(xq), 0, _lib.ptr(x), *[_lib.ptr(t) for t in self.w],
                                                _lib.ptr(out), _lib.ptr(self.ws), _lib.stream())
         _lib.check(rc, "pc_attention_layer_fwd_prepared")
         return out

@@ -73,8 +73,8 @@ __global__ void attention_layer_prep_kernel(const float *__restrict__ wq, const 
 // Q = xq Wq + bq for every neighbourhood (G x 64 outputs, 64 MACs each: 0.5 % of the layer's work) into a scratch the
 // main kernel's epilogue reads back through L2; keeps the serial 64-step GEMV off the tile pipeline's critical path.
 __global__ void __launch_bounds__(256)
-attention_layer_q_kernel(int G, const float *__restrict__ xq, const float *__restrict__ wq, const float *__restrict__ bq,
-                         float *__restrict__ q) {
+attention_layer_q_kernel(int G, size_t ldq, const float *__restrict__ xq, const float *__restrict__ wq,
+                         const float *__restrict__ bq, float *__restrict__ q) {
   __shared__ __align__(16) float s_w[kC * kC];
   __shared__ __align__(16) float s_x[64][kC + 4];  // 64 query rows per step; +4 keeps float4 rows aligned, spreads banks
   for (int i = threadIdx.x; i < kC * kC; i += 256) s_w[i] = __ldg(wq + i);
@@ -86,7 +86,7 @@ attention_layer_q_kernel(int G, const float *__restrict__ xq, const float *__res
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * (kC / 4); i += 256) {
       const int r = i >> 4, c4 = i & 15;
-      const float4 v = (g0 + r < G) ? __ldg(reinterpret_cast<const float4 *>(xq + (size_t)(g0 + r) * kC) + c4)
+      const float4 v = (g0 + r < G) ? __ldg(reinterpret_cast<const float4 *>(xq + (size_t)(g0 + r) * ldq) + c4)
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4 *>(&s_x[r][4 * c4]) = v;
     }
@@ -325,13 +325,15 @@ size_t attention_layer_wide_image_bytes(int C);
 bool attention_layer_wide_supported(int S, int C);
 int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
                              const float *wk, const float *bk, const float *wv, const float *bv, float *out,
-                             void *workspace, int mode, cudaStream_t st);
+                             void *workspace, int mode, size_t ldq, cudaStream_t st);
 
 // mode bit 0: build the operand image in the workspace; bit 1: run the layer on an image that is already there
 int attention_layer_run(int G, int S, int C, const float *xq, const float *x, const float *wq, const float *bq,
                         const float *wk, const float *bk, const float *wv, const float *bv, float *out, void *workspace,
-                        int mode, cudaStream_t st) {
+                        int mode, size_t ldq, cudaStream_t st) {
   const bool run = mode & 2;
+  if (ldq == 0) ldq = (size_t)C;   // query rows packed; otherwise row stride in floats (e.g. S*C: sample 0 of every group)
+  if (ldq < (size_t)C || (ldq & 3)) return PC_ERR_INVALID_ARGUMENT;
   if (G < 0 || S <= 0 || C <= 0) return PC_ERR_INVALID_ARGUMENT;
   const bool wide = attention_layer_wide_supported(S, C);
   if (!wide && (S != kS || C != kC)) return PC_ERR_UNSUPPORTED;  // other shapes: Dense GEMM + pc_attention_fwd
@@ -340,13 +342,13 @@ int attention_layer_run(int G, int S, int C, const float *xq, const float *x, co
   if (!workspace) return PC_ERR_WORKSPACE;
   if (!aligned16(workspace) || (run && G > 0 && (!aligned16(x) || !aligned16(out)))) return PC_ERR_UNSUPPORTED;
   if (run && G == 0) mode &= ~2;
-  if (wide) return attention_layer_wide_fwd(G, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, mode, st);
+  if (wide) return attention_layer_wide_fwd(G, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, mode, ldq, st);
   unsigned char *image = (unsigned char *)workspace;
   if (mode & 1) attention_layer_prep_kernel<<<(kN * kC + 255) / 256, 256, 0, st>>>(wq, bq, wk, bk, wv, bv, image);
   if (!(mode & 2)) PC_RETURN_LAUNCH_STATUS();
   float *qbuf = reinterpret_cast<float *>(image + ((kImageBytes + 255) / 256) * 256);
   const int qblocks = (G + 63) / 64 < num_sms() * 2 ? (G + 63) / 64 : num_sms() * 2;
-  attention_layer_q_kernel<<<qblocks, 256, 0, st>>>(G, xq, wq, bq, qbuf);
+  attention_layer_q_kernel<<<qblocks, 256, 0, st>>>(G, ldq, xq, wq, bq, qbuf);
   const size_t smem = 4 * kOperandBytes + kImageBytes + 64;
   PC_CUDA_TRY(allow_smem(attention_layer_c64_kernel, smem));
   const int ntiles = (int)(((size_t)G * kS + kRows - 1) / kRows);
@@ -366,18 +368,20 @@ extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
 extern "C" int pc_attention_layer_fwd(int G, int S, int C, const float *xq, const float *x, const float *wq,
                                       const float *bq, const float *wk, const float *bk, const float *wv,
                                       const float *bv, float *out, void *workspace, pc_stream_t stream) {
-  return pc::attention_layer_run(G, S, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, 3, (cudaStream_t)stream);
+  return pc::attention_layer_run(G, S, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, 3, 0, (cudaStream_t)stream);
 }
 
 extern "C" int pc_attention_layer_prepare(int S, int C, const float *wq, const float *bq, const float *wk,
                                           const float *bk, const float *wv, const float *bv, void *workspace,
                                           pc_stream_t stream) {
-  return pc::attention_layer_run(0, S, C, nullptr, nullptr, wq, bq, wk, bk, wv, bv, nullptr, workspace, 1,
+  return pc::attention_layer_run(0, S, C, nullptr, nullptr, wq, bq, wk, bk, wv, bv, nullptr, workspace, 1, 0,
                                  (cudaStream_t)stream);
 }
 
-extern "C" int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, const float *x, const float *wq,
-                                               const float *bq, const float *wk, const float *bk, const float *wv,
-                                               const float *bv, float *out, void *workspace, pc_stream_t stream) {
-  return pc::attention_layer_run(G, S, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, 2, (cudaStream_t)stream);
+extern "C" int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, size_t xq_stride, const float *x,
+                                               const float *wq, const float *bq, const float *wk, const float *bk,
+                                               const float *wv, const float *bv, float *out, void *workspace,
+                                               pc_stream_t stream) {
+  return pc::attention_layer_run(G, S, C, xq, x, wq, bq, wk, bk, wv, bv, out, workspace, 2, xq_stride,
+                                 (cudaStream_t)stream);
 }

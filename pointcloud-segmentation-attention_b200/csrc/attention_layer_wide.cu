@@ -67,14 +67,14 @@ __global__ void wide_prep_kernel(int C, const float *__restrict__ wk, const floa
 
 // Q = xq Wq + bq: G x C outputs, C MACs each (1/64 of the layer's work), k ascending with fmaf from the bias.
 __global__ void __launch_bounds__(256)
-wide_q_kernel(int G, int C, const float *__restrict__ xq, const float *__restrict__ wq, const float *__restrict__ bq,
-              float *__restrict__ q) {
+wide_q_kernel(int G, int C, size_t ldq, const float *__restrict__ xq, const float *__restrict__ wq,
+              const float *__restrict__ bq, float *__restrict__ q) {
   __shared__ float s_x[8][kMaxC];
   for (int g0 = blockIdx.x * 8; g0 < G; g0 += gridDim.x * 8) {
     __syncthreads();
     for (int i = threadIdx.x; i < 8 * C; i += 256) {
       const int r = i / C, k = i - r * C;
-      s_x[r][k] = (g0 + r < G) ? __ldg(xq + (size_t)(g0 + r) * C + k) : 0.f;
+      s_x[r][k] = (g0 + r < G) ? __ldg(xq + (size_t)(g0 + r) * ldq + k) : 0.f;
     }
     __syncthreads();
     for (int n = threadIdx.x; n < C; n += 256) {
@@ -347,7 +347,7 @@ bool attention_layer_wide_supported(int S, int C) { return S == kS && (C == 128 
 // per set of weights); bit 1: run the layer.
 int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
                              const float *wk, const float *bk, const float *wv, const float *bv, float *out,
-                             void *workspace, int mode, cudaStream_t st) {
+                             void *workspace, int mode, size_t ldq, cudaStream_t st) {
   unsigned char *image = (unsigned char *)workspace;
   const size_t img = attention_layer_wide_image_bytes(C);
   float *qbuf = reinterpret_cast<float *>(image + img);
@@ -356,7 +356,7 @@ int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, cons
     wide_prep_kernel<<<(unsigned)((elems + 255) / 256 < 4096 ? (elems + 255) / 256 : 4096), 256, 0, st>>>(C, wk, wv, image);
   if (!(mode & 2)) PC_RETURN_LAUNCH_STATUS();
   const int qb = (G + 7) / 8 < num_sms() * 4 ? (G + 7) / 8 : num_sms() * 4;
-  wide_q_kernel<<<qb, 256, 0, st>>>(G, C, xq, wq, bq, qbuf);
+  wide_q_kernel<<<qb, 256, 0, st>>>(G, C, ldq, xq, wq, bq, qbuf);
   const size_t smem = 2 * (size_t)kStage + 2 * kMaxC * sizeof(float) + 8 * sizeof(uint64_t) + 16;
   PC_CUDA_TRY(allow_smem(attention_layer_wide_kernel, smem));
   const int ntiles = (int)(((size_t)G * kS + kRows - 1) / kRows);

@@ -16,7 +16,7 @@ for k, v in (d.get("rooflines") or {}).items():
     print("  %-30s %8.1f us %-5s frac %.3f" % (k, v["ms"] * 1e3, v["bound"], v["frac"]))
 print("grid variants", {k: round(v * 1e3, 1) for k, v in (d.get("grid_variants_ms") or {}).items()})
 for k in ("gathers_steady_state", "attention_layer_tcgen05", "reference_gpu_kernels", "config1_single_scene_sa1",
-          "with_attention_layers", "config3_training_step", "config4_whole_scene"):
+          "with_attention_layers", "full_model_inference", "config3_training_step", "config4_whole_scene"):
     print(k, json.dumps(d.get(k))[:900])
 c5 = d.get("config5_sweep") or {}
 print("config5 total_ms", c5.get("total_ms"), "failed", c5.get("failed"), c5.get("error"))
