@@ -322,6 +322,7 @@ attention_layer_c64_kernel(int G, const float *__restrict__ qg, const float *__r
 
 // attention_layer_wide.cu: C = 128 / 256 / 512
 size_t attention_layer_wide_image_bytes(int C);
+size_t attention_layer_wide_workspace_bytes(int G, int C);
 bool attention_layer_wide_supported(int S, int C);
 int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
                              const float *wk, const float *bk, const float *wv, const float *bv, float *out,
@@ -360,7 +361,7 @@ int attention_layer_run(int G, int S, int C, const float *xq, const float *x, co
 
 extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
   if (G > 0 && pc::attention_layer_wide_supported(S, C))
-    return pc::attention_layer_wide_image_bytes(C) + (size_t)G * C * sizeof(float);  // operand image | Q scratch
+    return pc::attention_layer_wide_workspace_bytes(G, C);  // K | V operand image | W_q Dense image | Q scratch
   if (S != pc::kS || C != pc::kC || G <= 0) return 0;
   return (size_t)((pc::kImageBytes + 255) / 256) * 256 + (size_t)G * pc::kC * sizeof(float);  // operand image | Q scratch
 }

@@ -122,4 +122,13 @@ int csr_build(int b, int nkeys, int npos, const int *idx, int *workspace, cudaSt
 int csr_reduce(int b, int nkeys, int npos, int c, int div, const float *src, const float *w, const int *workspace,
                float *out, cudaStream_t stream);
 
+
+// ---- tcgen05 Dense engine (gemm_tf32.cu), for kernels that need a projection of their own ----
+size_t dense_image_bytes(int K, int N);
+// image of W: element (k, n) = w[k * sk + n * sn]
+int dense_prepare(int K, int N, size_t sk, size_t sn, const float *w, void *image, cudaStream_t st);
+// out (rows, N; stride ldo) = act(x (rows, K; stride ldx) . W + bias)
+int dense_forward(size_t rows, int K, size_t ldx, int N, size_t ldo, int relu, const float *x, const void *image,
+                  const float *bias, float *out, cudaStream_t st);
+
 }  // namespace pc

@@ -14,15 +14,34 @@
 namespace pc {
 namespace {
 
+// I = uint32_t with multiply-shift index decoding (FastDiv) when the output has < 2^31 floats, size_t with real divisions
+// beyond: the three 64-bit divisions per 16 output bytes made this gather ALU-bound (ncu: issue slots 72 %, ALU 49 %).
+template <class I> struct SaDecode;
+template <> struct SaDecode<uint32_t> {
+  FastDiv w, ns, m;
+  SaDecode(int W, int NS, int M) : w((uint32_t)W), ns((uint32_t)NS), m((uint32_t)M) {}
+  __device__ __forceinline__ uint32_t by_w(uint32_t x) const { return w.div(x); }
+  __device__ __forceinline__ uint32_t by_ns(uint32_t x) const { return ns.div(x); }
+  __device__ __forceinline__ uint32_t by_m(uint32_t x) const { return m.div(x); }
+};
+template <> struct SaDecode<size_t> {
+  size_t w, ns, m;
+  SaDecode(int W, int NS, int M) : w(W), ns(NS), m(M) {}
+  __device__ __forceinline__ size_t by_w(size_t x) const { return x / w; }
+  __device__ __forceinline__ size_t by_ns(size_t x) const { return x / ns; }
+  __device__ __forceinline__ size_t by_m(size_t x) const { return x / m; }
+};
+
+template <class I>
 __global__ void __launch_bounds__(256)
-sa_group_kernel(size_t total, int n, int c, int m, int ns, bool vec_store, const float *__restrict__ xyz,
+sa_group_kernel(I total, SaDecode<I> dec, int n, int c, bool vec_store, const float *__restrict__ xyz,
                 const float *__restrict__ points, const int *__restrict__ idx, const float *__restrict__ new_xyz,
                 float *__restrict__ out, float *__restrict__ gxyz) {
   const int W = 3 + c;
-  const size_t nchunks = (total + 3) / 4;
-  for (size_t ch = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
-    const size_t e0 = ch * 4;
-    size_t row = e0 / W;  // (scene*m + j)*ns + k
+  const I nchunks = (total + 3) / 4;
+  for (I ch = (I)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += (I)gridDim.x * blockDim.x) {
+    const I e0 = ch * 4;
+    I row = dec.by_w(e0);  // (scene*m + j)*ns + k
     int col = (int)(e0 - row * W);
     float v[4];
     int src = -1;
@@ -33,13 +52,14 @@ sa_group_kernel(size_t total, int n, int c, int m, int ns, bool vec_store, const
       if (e0 + t < total) {
         if (src < 0) {
           src = __ldg(idx + row);
-          q = row / ns;        // scene*m + j
-          scene = q / m;
+          const I qq = dec.by_ns(row);        // scene*m + j
+          q = qq;
+          scene = dec.by_m(qq);
         }
         if (col < 3) {
           const float g = __fsub_rn(__ldg(xyz + (scene * n + src) * 3 + col), __ldg(new_xyz + q * 3 + col));
           v[t] = g;
-          if (gxyz) gxyz[row * 3 + col] = g;
+          if (gxyz) gxyz[(size_t)row * 3 + col] = g;
         } else {
           v[t] = __ldg(points + (scene * n + src) * (size_t)c + (col - 3));
         }
@@ -65,27 +85,28 @@ __device__ __forceinline__ void fp_weights(const float *__restrict__ dist, size_
   w1 = __fdiv_rn(r0, norm); w2 = __fdiv_rn(r1, norm); w3 = __fdiv_rn(r2, norm);
 }
 
-// A warp owns 32 consecutive dense points: lane r computes the weights and fetches the indices of point r ONCE (they
-// are shared by all c2 channels), then the warp walks the 32 rows, broadcasting (i1,i2,i3,w1,w2,w3) by shuffle while
-// its lanes cover the row's channels -- 128-bit loads / stores when the channel counts and bases allow.
+// A warp owns RPW (<= 32) consecutive dense points: lane r computes the weights and fetches the indices of point r ONCE
+// (they are shared by all c2 channels), then the warp walks its rows, broadcasting (i1,i2,i3,w1,w2,w3) by shuffle while
+// its lanes cover the row's channels -- 128-bit loads / stores when the channel counts and bases allow.  RPW = 32 for
+// the big levels; the host lowers it when there are few rows (FP1: 1024 rows x 768 channels ran on 4 CTAs, 69 us).
 __global__ void __launch_bounds__(256)
-fp_interp_kernel(size_t rows, int n, int m, int c2, int c1, bool vec, const float *__restrict__ dist,
+fp_interp_kernel(size_t rows, int RPW, int n, int m, int c2, int c1, bool vec, const float *__restrict__ dist,
                  const int *__restrict__ idx, const float *__restrict__ points2, const float *__restrict__ points1,
                  float *__restrict__ out, float *__restrict__ weight) {
   const int lane = threadIdx.x & 31;
   const int W = c2 + c1;
   const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t r0 = warp_global * 32; r0 < rows; r0 += nwarps * 32) {
+  for (size_t r0 = warp_global * RPW; r0 < rows; r0 += nwarps * RPW) {
     const size_t my = r0 + lane;
     float w1 = 0.f, w2 = 0.f, w3 = 0.f;
     int i1 = 0, i2 = 0, i3 = 0;
-    if (my < rows && c2 > 0) {
+    if (lane < RPW && my < rows && c2 > 0) {
       fp_weights(dist, my, w1, w2, w3);
       i1 = __ldg(idx + my * 3 + 0); i2 = __ldg(idx + my * 3 + 1); i3 = __ldg(idx + my * 3 + 2);
       if (weight) { weight[my * 3 + 0] = w1; weight[my * 3 + 1] = w2; weight[my * 3 + 2] = w3; }
     }
-    const int nr = (int)min((size_t)32, rows - r0);
+    const int nr = (int)min((size_t)RPW, rows - r0);
     for (int rr = 0; rr < nr; ++rr) {
       const size_t row = r0 + rr;
       const float a1 = __shfl_sync(PC_FULL_MASK, w1, rr), a2 = __shfl_sync(PC_FULL_MASK, w2, rr),
@@ -134,9 +155,14 @@ extern "C" int pc_sa_group(int b, int n, int c, int m, int nsample, const float 
   size_t blocks = ((total + 3) / 4 + 255) / 256;
   const size_t cap = (size_t)pc::num_sms() * 32;
   if (blocks > cap) blocks = cap;
-  pc::sa_group_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(total, n, c, m, nsample, pc::aligned16(new_points),
-                                                                        xyz, points, idx, new_xyz, new_points,
-                                                                        grouped_xyz);
+  if (total < (1ull << 31))
+    pc::sa_group_kernel<uint32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (uint32_t)total, pc::SaDecode<uint32_t>(3 + c, nsample, m), n, c, pc::aligned16(new_points), xyz, points, idx, new_xyz,
+        new_points, grouped_xyz);
+  else
+    pc::sa_group_kernel<size_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        total, pc::SaDecode<size_t>(3 + c, nsample, m), n, c, pc::aligned16(new_points), xyz, points, idx, new_xyz, new_points,
+        grouped_xyz);
   PC_RETURN_LAUNCH_STATUS();
 }
 
@@ -147,12 +173,14 @@ extern "C" int pc_fp_interpolate(int b, int n, int m, int c2, int c1, const floa
   if (b == 0 || n == 0 || c2 + c1 == 0) return PC_OK;
   if (!out || (c2 > 0 && (m == 0 || !dist || !idx || !points2)) || (c1 > 0 && !points1)) return PC_ERR_INVALID_ARGUMENT;
   const size_t rows = (size_t)b * n;
-  size_t blocks = ((rows + 31) / 32 + 7) / 8;  // 8 warps per CTA, one 32-row group per warp
+  int rpw = 32;  // rows per warp: fewer when the launch would not fill the chip
+  while (rpw > 1 && (rows + rpw - 1) / rpw < (size_t)pc::num_sms() * 16) rpw >>= 1;
+  size_t blocks = ((rows + rpw - 1) / rpw + 7) / 8;  // 8 warps per CTA, one group of rows per warp
   const size_t cap = (size_t)pc::num_sms() * 32;
   if (blocks > cap) blocks = cap;
   const bool vec = c2 % 4 == 0 && c1 % 4 == 0 && pc::aligned16(out) && pc::aligned16(points2) &&
                    (c1 == 0 || pc::aligned16(points1));
-  pc::fp_interp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, n, m, c2, c1, vec, dist, idx, points2,
+  pc::fp_interp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, rpw, n, m, c2, c1, vec, dist, idx, points2,
                                                                          points1, out, weight);
   PC_RETURN_LAUNCH_STATUS();
 }

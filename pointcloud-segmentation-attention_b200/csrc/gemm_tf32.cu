@@ -121,7 +121,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
 __global__ void __launch_bounds__(kThreads, 1)
-dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, int vec_x, int vec_o,
+dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, size_t ldo, size_t ldp, int relu, int vec_x, int vec_o,
                   const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
                   float *__restrict__ out, float *__restrict__ pooled) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -157,9 +157,11 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *s_tmem;
 
-  const int nkb = (K + kKB - 1) / kKB, nchunk = (N + kMaxNc - 1) / kMaxNc;
+  // item = (tile of 128 rows, unit of sw output columns); sw = 256 unless the launch would leave SMs without an item
+  // (few rows): then 128 / 64 / 32, a contiguous slice of the 256-column image slot (8-row groups are 1 KB apart)
+  const int nkb = (K + kKB - 1) / kKB, nchunk = (N + sw - 1) / sw;
   const int ntiles = (int)((rows + kRows - 1) / kRows);
-  const int nitems = ntiles * nchunk;                 // item = tile * nchunk + j: a tile's chunks run on neighbouring CTAs
+  const int nitems = ntiles * nchunk;                 // item = tile * nchunk + u: a tile's units run on neighbouring CTAs
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage_buf);
 
   if (warp < 4) {
@@ -191,13 +193,13 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
     };
     auto produce = [&](const float4 (&buf)[8], int it_) {
       const int w = it_ / nkb, kb = it_ - w * nkb;
-      const int j = (blockIdx.x + w * (int)gridDim.x) % nchunk;
-      const int nc = min(kMaxNc, N - j * kMaxNc);
+      const int col0 = ((blockIdx.x + w * (int)gridDim.x) % nchunk) * sw;
+      const int nc = min(sw, N - col0);
       const int s = it_ & 1;
       mbar_wait(empty[s], ((it_ >> 1) & 1) ^ 1);       // the MMAs that read this stage two blocks ago have completed
       unsigned char *st = stage_buf + s * kStage;
       if (tid == 0) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
-        const unsigned char *src = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
+        const unsigned char *src = image + ((size_t)(col0 / kMaxNc) * nkb + kb) * (2 * kBBlock) + (size_t)(col0 % kMaxNc) * 128;
         const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
         const uint32_t bytes = (uint32_t)((nc + 15) & ~15) * 128u;   // the MMA's N is a multiple of 16: zero rows beyond nc
         asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(2u * bytes) : "memory");
@@ -238,8 +240,8 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
     if (lane == 0) {
       int it = 0, w = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
-        const int a = w & 1, j = item % nchunk;
-        const int nc = min(kMaxNc, N - j * kMaxNc);
+        const int a = w & 1;
+        const int nc = min(sw, N - (item % nchunk) * sw);
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc rounded up to 16, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
         mbar_wait(t_empty[a], ((w >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
@@ -270,8 +272,8 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
     float *patch = s_patch + qtr * kPatch;
     int w = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
-      const int a = w & 1, tile = item / nchunk, j = item - tile * nchunk;
-      const int nc = min(kMaxNc, N - j * kMaxNc);
+      const int a = w & 1, tile = item / nchunk, col0 = (item - tile * nchunk) * sw;
+      const int nc = min(sw, N - col0);
       const size_t row0 = (size_t)tile * kRows + qtr * 32;    // this warp's 32 rows
       mbar_wait(t_full[a], (w >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -280,7 +282,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
         uint32_t v[32];
         PCG_TMEM_LD32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float *cb = s_bias + j * kMaxNc + c0;
+        const float *cb = s_bias + col0 + c0;
         float y[32];
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
@@ -306,7 +308,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
               if (lane == t) mine = m;
             }
           }
-          if (row0 < rows && c0 + lane < nc) pooled[(row0 >> 5) * ldp + (size_t)j * kMaxNc + c0 + lane] = mine;
+          if (row0 < rows && c0 + lane < nc) pooled[(row0 >> 5) * ldp + (size_t)col0 + c0 + lane] = mine;
         }
         if (kPool != 1) {
           // transpose through the patch: thread = row writes its 32 columns, then 8 lanes cover one row's 128 bytes
@@ -321,7 +323,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp,
             const int r = 4 * t + rr;
             const float4 val = *reinterpret_cast<const float4 *>(patch + r * 36 + cq);
             if (row0 + r < rows && c0 + cq < nc) {
-              float *dst = out + (row0 + r) * ldo + (size_t)j * kMaxNc + c0 + cq;
+              float *dst = out + (row0 + r) * ldo + (size_t)col0 + c0 + cq;
               if (vec_o && c0 + cq + 3 < nc) {
                 *reinterpret_cast<float4 *>(dst) = val;
               } else {
@@ -616,19 +618,21 @@ int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, si
                  const unsigned char *image, const float *bias, float *out, float *pooled, cudaStream_t st) {
   const size_t smem = 2 * (size_t)kStage + (kMaxN + 4 * kPatch) * sizeof(float) + 8 * sizeof(uint64_t) + 16;
   const int ntiles = (int)((rows + kRows - 1) / kRows);
-  const int nitems = ntiles * ((N + kMaxNc - 1) / kMaxNc);
+  int sw = kMaxNc;   // output columns per item: narrower units when there are fewer (tile, unit) items than SMs
+  while (sw > 32 && (long long)ntiles * ((N + sw - 1) / sw) < num_sms()) sw >>= 1;
+  const int nitems = ntiles * ((N + sw - 1) / sw);
   const int grid = nitems < num_sms() ? nitems : num_sms();
   const int vec_x = (ldx % 4 == 0) && aligned16(x);
   const int vec_o = (ldo % 4 == 0) && aligned16(out);
   if (pool == 1) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
-    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else if (pool == 2) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
-    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
-    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   }
   PC_RETURN_LAUNCH_STATUS();
 }
@@ -638,6 +642,16 @@ bool dense_shape_ok(size_t rows, int K, int N) {
 }
 
 }  // namespace
+
+// used by the attention layers for their Q projection (attention_layer.cu)
+size_t dense_image_bytes(int K, int N) { return image_bytes(K, N); }
+int dense_prepare(int K, int N, size_t sk, size_t sn, const float *w, void *image, cudaStream_t st) {
+  return launch_prep(K, N, sk, sn, w, (unsigned char *)image, st);
+}
+int dense_forward(size_t rows, int K, size_t ldx, int N, size_t ldo, int relu, const float *x, const void *image,
+                  const float *bias, float *out, cudaStream_t st) {
+  return launch_dense(0, rows, K, ldx, N, ldo, 0, relu, x, (const unsigned char *)image, bias, out, nullptr, st);
+}
 }  // namespace pc
 
 // ---------------------------------------------------------------------------------------------------------------

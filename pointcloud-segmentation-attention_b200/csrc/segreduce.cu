@@ -8,7 +8,10 @@
 //   2. csr_reduce: one thread per (point, 4 channels) adds its contributors in that fixed order with 128-bit loads.
 // The sum order equals the reference's serial CPU loops (ascending (j,k) / (j,t)), so results are bit-identical to
 // them, and identical from run to run.  No atomics on floats anywhere; outputs are fully overwritten (no memset).
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pc {
 namespace {
@@ -29,35 +32,62 @@ __device__ __forceinline__ unsigned same_key_lanes(unsigned act, int key, int nb
 constexpr int kCsrThreads = 1024;
 constexpr size_t kCsrSmemBudget = 200 * 1024;
 
-// One CTA per scene.  Positions are split into W contiguous parts; counters cnt[w][key] live in shared memory.
+// A cluster of CL CTAs per scene (CL = 1: a plain CTA).  CTA r of the cluster owns the contiguous position slice
+// [r * slice, (r + 1) * slice); inside it the slice is split into W contiguous parts, one per warp, with counters
+// cnt[w][key] in shared memory.  The per-key totals of the CTAs meet through distributed shared memory (one
+// cluster.sync), so every CTA knows how many positions with its key lie in earlier slices, and the fill -- warp w walks
+// part w in order, 32 positions per step, ranking equal keys inside a step by ballot -- writes each position to its
+// final, ascending place: a stable counting sort with CL * W independent walkers and no sort pass.
+// (One CTA per scene left 132 of 148 SMs idle and took 38 us at the FP4 shape; measured after: see DESIGN.md.)
+template <int CL>
 __global__ void __launch_bounds__(kCsrThreads, 1)
-csr_build_kernel(int nkeys, int npos, int W, int part, int nbits, const int *__restrict__ idx, int *__restrict__ ws) {
-  extern __shared__ int cnt[];  // W * nkeys
+csr_build_kernel(int nkeys, int npos, int slice, int W, int part, int nbits, const int *__restrict__ idx,
+                 int *__restrict__ ws) {
+  extern __shared__ int cnt[];  // W * nkeys counters | nkeys totals of this CTA
   __shared__ int s_carry;
   __shared__ int s_warp[32];
-  const int scene = blockIdx.x;
+  int *s_tot = cnt + (size_t)W * nkeys;
+  const int scene = blockIdx.x / CL;
+  const int rank = (CL > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int *keys = idx + (size_t)scene * npos;
   int *row_ptr = ws + (size_t)scene * (nkeys + 1 + npos);
   int *list = row_ptr + nkeys + 1;
+  const int p_lo = min(npos, rank * slice), p_hi = min(npos, p_lo + slice);   // this CTA's positions
 
   for (int i = tid; i < W * nkeys; i += kCsrThreads) cnt[i] = 0;
   if (tid == 0) s_carry = 0;
   __syncthreads();
   // histogram per part (integer atomics: the final counts do not depend on order)
-  for (int p = tid; p < npos; p += kCsrThreads) atomicAdd(&cnt[(p / part) * nkeys + keys[p]], 1);
+  for (int p = p_lo + tid; p < p_hi; p += kCsrThreads) atomicAdd(&cnt[((p - p_lo) / part) * nkeys + keys[p]], 1);
   __syncthreads();
-  // cnt[w][key] <- row_ptr[key] + number of positions with this key in parts < w
+  // cnt[w][key] <- number of positions with this key in parts < w of this slice; s_tot[key] <- the slice's total
+  for (int key = tid; key < nkeys; key += kCsrThreads) {
+    int total = 0;
+    for (int w = 0; w < W; ++w) {
+      const int t = cnt[w * nkeys + key];
+      cnt[w * nkeys + key] = total;
+      total += t;
+    }
+    s_tot[key] = total;
+  }
+  if (CL > 1) cg::this_cluster().sync(); else __syncthreads();
+  // row_ptr: exclusive scan over the keys of the cluster-wide totals; `before` = this key's positions in earlier slices
   for (int base = 0; base < nkeys; base += kCsrThreads) {
     const int key = base + tid;
-    int total = 0;
-    if (key < nkeys)
-      for (int w = 0; w < W; ++w) {
-        int t = cnt[w * nkeys + key];
-        cnt[w * nkeys + key] = total;
-        total += t;
+    int total = 0, before = 0;
+    if (key < nkeys) {
+      if (CL > 1) {
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+          const int t = *cg::this_cluster().map_shared_rank(&s_tot[key], c);
+          if (c < rank) before += t;
+          total += t;
+        }
+      } else {
+        total = s_tot[key];
       }
-    // block-wide exclusive scan of `total`
+    }
     int incl = total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -76,21 +106,20 @@ csr_build_kernel(int nkeys, int npos, int W, int part, int nbits, const int *__r
       s_warp[lane] = iv - v;  // exclusive prefix of warp sums
     }
     __syncthreads();
-    const int carry = s_carry;
-    const int excl = carry + s_warp[warp] + incl - total;
+    const int excl = s_carry + s_warp[warp] + incl - total;
     if (key < nkeys) {
-      row_ptr[key] = excl;
-      for (int w = 0; w < W; ++w) cnt[w * nkeys + key] += excl;
+      if (rank == 0) row_ptr[key] = excl;
+      for (int w = 0; w < W; ++w) cnt[w * nkeys + key] += excl + before;
     }
     __syncthreads();
     if (tid == kCsrThreads - 1) s_carry = excl + total;
     __syncthreads();
   }
-  if (tid == 0) row_ptr[nkeys] = npos;
-  // stable fill: warp w walks part w in order, 32 positions per step
+  if (rank == 0 && tid == 0) row_ptr[nkeys] = npos;
+  // stable fill: warp w walks part w of the slice in order, 32 positions per step
   if (warp < W) {
     int *c = cnt + warp * nkeys;
-    const int lo = warp * part, hi = min(npos, lo + part);
+    const int lo = min(p_hi, p_lo + warp * part), hi = min(p_hi, lo + part);
     const unsigned lt = lanemask_lt();
     // keys of kPre steps are fetched ahead of the serial counter walk (the walk itself is a dependent
     // shared-memory chain; a global load per step in front of it made every step an L2 / DRAM round trip)
@@ -131,6 +160,30 @@ csr_build_kernel(int nkeys, int npos, int W, int part, int nbits, const int *__r
         if (dst[u] >= 0) list[dst[u]] = p0 + 32 * u + lane;
     }
   }
+  if (CL > 1) cg::this_cluster().sync();  // no CTA may exit while a peer can still read its totals
+}
+
+template <int CL>
+int launch_csr_build(int b, int nkeys, int npos, int slice, int W, int part, int nbits, size_t smem, const int *idx,
+                     int *workspace, cudaStream_t st) {
+  auto kernel = csr_build_kernel<CL>;
+  if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(kernel, smem));
+  if (CL == 1) {
+    kernel<<<b, kCsrThreads, smem, st>>>(nkeys, npos, slice, W, part, nbits, idx, workspace);
+    PC_RETURN_LAUNCH_STATUS();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)b * CL);
+  cfg.blockDim = dim3(kCsrThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PC_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, nkeys, npos, slice, W, part, nbits, idx, workspace));
+  return PC_OK;
 }
 
 // Fallback for key ranges too large for shared memory: counters in the row_ptr area itself, one warp walks all
@@ -404,24 +457,28 @@ size_t csr_workspace_bytes(int b, int nkeys, int npos) {
 int csr_build(int b, int nkeys, int npos, const int *idx, int *workspace, cudaStream_t st) {
   if (b > 65535) return PC_ERR_UNSUPPORTED;
   const size_t per_part = (size_t)nkeys * sizeof(int);
-  if (per_part <= kCsrSmemBudget) {
-    int W = (int)(kCsrSmemBudget / per_part);
+  if (2 * per_part <= kCsrSmemBudget) {   // at least one part's counters + the totals fit shared memory
+    // CTAs per scene: enough positions per CTA to keep its warps busy, at most a portable cluster of 8
+    int CL = 1;
+    while (CL < 8 && npos / (2 * CL) >= 1024) CL *= 2;
+    int slice = ((npos + CL - 1) / CL + 31) / 32 * 32;
+    if (slice < 32) slice = 32;
+    int W = (int)((kCsrSmemBudget - per_part) / per_part);
     if (W > 32) W = 32;
-    // no more parts than 32-position steps
-    const int steps = (npos + 31) / 32;
-    if (W > steps) W = steps > 0 ? steps : 1;
-    int part = ((npos + W - 1) / W + 31) / 32 * 32;
-    if (part < 32) part = 32;
-    W = (npos + part - 1) / part;
+    const int steps = (slice + 31) / 32;  // no more parts than 32-position steps
+    if (W > steps) W = steps;
+    int part = ((slice + W - 1) / W + 31) / 32 * 32;
+    W = (slice + part - 1) / part;
     if (W < 1) W = 1;
-    const size_t smem = (size_t)W * per_part;
-    if (smem > 48 * 1024) PC_CUDA_TRY(allow_smem(csr_build_kernel, smem));
+    const size_t smem = (size_t)(W + 1) * per_part;
     int nbits = 0;
     while ((1 << nbits) < nkeys) ++nbits;
-    csr_build_kernel<<<b, kCsrThreads, smem, st>>>(nkeys, npos, W, part, nbits, idx, workspace);
-  } else {
-    csr_build_big_kernel<<<b, 1024, 0, st>>>(nkeys, npos, idx, workspace);
+    if (CL == 8) return launch_csr_build<8>(b, nkeys, npos, slice, W, part, nbits, smem, idx, workspace, st);
+    if (CL == 4) return launch_csr_build<4>(b, nkeys, npos, slice, W, part, nbits, smem, idx, workspace, st);
+    if (CL == 2) return launch_csr_build<2>(b, nkeys, npos, slice, W, part, nbits, smem, idx, workspace, st);
+    return launch_csr_build<1>(b, nkeys, npos, slice, W, part, nbits, smem, idx, workspace, st);
   }
+  csr_build_big_kernel<<<b, 1024, 0, st>>>(nkeys, npos, idx, workspace);
   PC_RETURN_LAUNCH_STATUS();
 }
 
