@@ -361,7 +361,7 @@ int attention_layer_run(int G, int S, int C, const float *xq, const float *x, co
 
 extern "C" size_t pc_attention_layer_workspace_bytes(int G, int S, int C) {
   if (G > 0 && pc::attention_layer_wide_supported(S, C))
-    return pc::attention_layer_wide_workspace_bytes(G, C);  // K | V operand image | W_q Dense image | Q scratch
+    return pc::attention_layer_wide_workspace_bytes(G, C);  // K | V operand image | Q scratch
   if (S != pc::kS || C != pc::kC || G <= 0) return 0;
   return (size_t)((pc::kImageBytes + 255) / 256) * 256 + (size_t)G * pc::kC * sizeof(float);  // operand image | Q scratch
 }

@@ -15,7 +15,7 @@
 //              B block (64 KB) of the weight image
 //   warp  8    one thread issues 12 tcgen05.mma (M128 N256 K8, kind::tf32) per K block: X_hi W_hi + X_hi W_lo + X_lo W_hi;
 //              tcgen05.commit frees the stage / publishes the accumulator
-//   warps 4-7  epilogue: tcgen05.ld of the row's K chunk, logits against Q (Dense engine launch in front), softmax, V chunk,
+//   warps 4-7  epilogue: tcgen05.ld of the row's K chunk, logits against Q (from the front kernel), softmax, V chunk,
 //              weighted sum, 16-byte store of the head's 4 outputs
 // Two TMEM accumulators (2 x 256 columns) let the tensor cores start the next item while the epilogue reads this one.
 #include <math.h>
@@ -62,6 +62,39 @@ __global__ void wide_prep_kernel(int C, const float *__restrict__ wk, const floa
     unsigned char *blk = image + ((size_t)j * nkb + kb) * (2 * kBBlock);
     *reinterpret_cast<float *>(blk + block_offset(n, kl)) = hi;
     *reinterpret_cast<float *>(blk + kBBlock + block_offset(n, kl)) = lo;
+  }
+}
+
+// Q = xq Wq + bq in fp32 on the CUDA cores: G x C outputs, C MACs each (1/64 of the layer's work), k ascending with fmaf
+// from the bias.  (The tensor-core engine's 3xTF32 / 4xTF32 products were tried for it: the logits feed an exponent and
+// the layer's error at C = 512 went from 7e-6 to 1.2e-5 of the output scale -- past the 1e-5 bound -- so Q stays fp32.)
+// CTA = 8 query rows x 128 output columns, thread = one column with 8 accumulators; the first version gave a CTA all C
+// columns of its 8 rows (G / 8 CTAs in all): 32 CTAs x 512 serial steps = 142 us at SA4; now G / 8 x C / 128 CTAs.
+__global__ void __launch_bounds__(128)
+wide_q_kernel(int G, int C, size_t ldq, const float *__restrict__ xq, const float *__restrict__ wq,
+              const float *__restrict__ bq, float *__restrict__ q) {
+  __shared__ float s_x[8][kMaxC];
+  const int n = blockIdx.y * 128 + threadIdx.x;
+  const float b = bq ? __ldg(bq + n) : 0.f;
+  for (int g0 = blockIdx.x * 8; g0 < G; g0 += gridDim.x * 8) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * C; i += 128) {
+      const int r = i / C, k = i - r * C;
+      s_x[r][k] = (g0 + r < G) ? __ldg(xq + (size_t)(g0 + r) * ldq + k) : 0.f;
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = b;
+#pragma unroll 8
+    for (int k = 0; k < C; ++k) {
+      const float w = __ldg(wq + (size_t)k * C + n);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = fmaf(s_x[r][k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (g0 + r < G) q[(size_t)(g0 + r) * C + n] = acc[r];
   }
 }
 
@@ -312,7 +345,7 @@ attention_layer_wide_kernel(int G, int C, const float *__restrict__ qg, const fl
 
 size_t attention_layer_wide_image_bytes(int C) { return (size_t)(C / 128) * (C / kKB) * (2 * kBBlock); }
 size_t attention_layer_wide_workspace_bytes(int G, int C) {
-  return attention_layer_wide_image_bytes(C) + dense_image_bytes(C, C) + (size_t)G * C * sizeof(float);
+  return attention_layer_wide_image_bytes(C) + (size_t)G * C * sizeof(float);
 }
 
 bool attention_layer_wide_supported(int S, int C) { return S == kS && (C == 128 || C == 256 || C == 512); }
@@ -322,21 +355,16 @@ bool attention_layer_wide_supported(int S, int C) { return S == kS && (C == 128 
 int attention_layer_wide_fwd(int G, int C, const float *xq, const float *x, const float *wq, const float *bq,
                              const float *wk, const float *bk, const float *wv, const float *bv, float *out,
                              void *workspace, int mode, size_t ldq, cudaStream_t st) {
-  // workspace: K | V operand image | Dense image of W_q | Q scratch (G x C)
+  // workspace: K | V operand image | Q scratch (G x C)
   unsigned char *image = (unsigned char *)workspace;
   const size_t img = attention_layer_wide_image_bytes(C);
-  unsigned char *qimage = image + img;
-  float *qbuf = reinterpret_cast<float *>(qimage + dense_image_bytes(C, C));
+  float *qbuf = reinterpret_cast<float *>(image + img);
   const size_t elems = img / 8;
-  if (mode & 1) {
+  if (mode & 1)
     wide_prep_kernel<<<(unsigned)((elems + 255) / 256 < 4096 ? (elems + 255) / 256 : 4096), 256, 0, st>>>(C, wk, wv, image);
-    const int rc = dense_prepare(C, C, (size_t)C, 1, wq, qimage, st);
-    if (rc) return rc;
-  }
   if (!(mode & 2)) PC_RETURN_LAUNCH_STATUS();
-  // Q = xq W_q + b_q on the Dense engine (the CUDA-core GEMV this replaces ran 142 us at SA4: 32 CTAs, 512 serial steps)
-  const int qrc = dense_forward((size_t)G, C, ldq, C, (size_t)C, 0, xq, qimage, bq, qbuf, st);
-  if (qrc) return qrc;
+  const int qb = (G + 7) / 8 < num_sms() * 4 ? (G + 7) / 8 : num_sms() * 4;
+  wide_q_kernel<<<dim3(qb, C / 128), 128, 0, st>>>(G, C, ldq, xq, wq, bq, qbuf);
   const size_t smem = 2 * (size_t)kStage + 2 * kMaxC * sizeof(float) + 8 * sizeof(uint64_t) + 16;
   PC_CUDA_TRY(allow_smem(attention_layer_wide_kernel, smem));
   const int ntiles = (int)(((size_t)G * kS + kRows - 1) / kRows);

@@ -127,8 +127,9 @@ int csr_reduce(int b, int nkeys, int npos, int c, int div, const float *src, con
 size_t dense_image_bytes(int K, int N);
 // image of W: element (k, n) = w[k * sk + n * sn]
 int dense_prepare(int K, int N, size_t sk, size_t sn, const float *w, void *image, cudaStream_t st);
-// out (rows, N; stride ldo) = act(x (rows, K; stride ldx) . W + bias)
+// out (rows, N; stride ldo) = act(x (rows, K; stride ldx) . W + bias); four_products adds the lo x lo term of the TF32 split
+// (fp32-grade products: for small projections whose result feeds an exponent, e.g. the attention query)
 int dense_forward(size_t rows, int K, size_t ldx, int N, size_t ldo, int relu, const float *x, const void *image,
-                  const float *bias, float *out, cudaStream_t st);
+                  const float *bias, float *out, cudaStream_t st, bool four_products = false);
 
 }  // namespace pc

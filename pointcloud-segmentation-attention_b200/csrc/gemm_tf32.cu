@@ -121,8 +121,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
 __global__ void __launch_bounds__(kThreads, 1)
-dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, size_t ldo, size_t ldp, int relu, int vec_x, int vec_o,
-                  const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
+dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, size_t ldo, size_t ldp, int relu, int vec_x,
+                  int vec_o, const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
                   float *__restrict__ out, float *__restrict__ pooled) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *stage_buf = smem;                                          // [2][A_hi | A_lo | B_hi | B_lo]
@@ -252,9 +252,8 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, size_t ldo, siz
           mbar_wait(full[s], (it >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = stage_s + s * kStage, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + kBBlock;
-#pragma unroll
-          for (int split = 0; split < 3; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi
-            const uint32_t as = (split == 2) ? a_lo : a_hi, bs = (split == 1) ? b_lo : b_hi;
+          for (int split = 0; split < nsplit; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi [, X_lo W_lo: fp32-grade]
+            const uint32_t as = (split >= 2) ? a_lo : a_hi, bs = (split & 1) ? b_lo : b_hi;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               mma_tf32(tmem + a * kMaxNc, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
@@ -615,24 +614,28 @@ int launch_prep(int K, int N, size_t sk, size_t sn, const float *w, unsigned cha
 }
 
 int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, const float *x,
-                 const unsigned char *image, const float *bias, float *out, float *pooled, cudaStream_t st) {
+                 const unsigned char *image, const float *bias, float *out, float *pooled, cudaStream_t st,
+                 int nsplit = 3) {
   const size_t smem = 2 * (size_t)kStage + (kMaxN + 4 * kPatch) * sizeof(float) + 8 * sizeof(uint64_t) + 16;
   const int ntiles = (int)((rows + kRows - 1) / kRows);
-  int sw = kMaxNc;   // output columns per item: narrower units when there are fewer (tile, unit) items than SMs
-  while (sw > 32 && (long long)ntiles * ((N + sw - 1) / sw) < num_sms()) sw >>= 1;
+  // output columns per item: narrower units only when the launch has very few (tile, unit) items -- every unit of a
+  // tile stages the tile's A operand again, so splitting 64 items into 128 made SA4's layers slower (23 -> 33 us) while
+  // splitting FP1's 8 items into 64 made them faster
+  int sw = kMaxNc;
+  while (sw > 32 && (long long)ntiles * ((N + sw - 1) / sw) <= num_sms() / 4) sw >>= 1;
   const int nitems = ntiles * ((N + sw - 1) / sw);
   const int grid = nitems < num_sms() ? nitems : num_sms();
   const int vec_x = (ldx % 4 == 0) && aligned16(x);
   const int vec_o = (ldo % 4 == 0) && aligned16(out);
   if (pool == 1) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
-    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else if (pool == 2) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
-    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
-    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   }
   PC_RETURN_LAUNCH_STATUS();
 }
@@ -649,8 +652,9 @@ int dense_prepare(int K, int N, size_t sk, size_t sn, const float *w, void *imag
   return launch_prep(K, N, sk, sn, w, (unsigned char *)image, st);
 }
 int dense_forward(size_t rows, int K, size_t ldx, int N, size_t ldo, int relu, const float *x, const void *image,
-                  const float *bias, float *out, cudaStream_t st) {
-  return launch_dense(0, rows, K, ldx, N, ldo, 0, relu, x, (const unsigned char *)image, bias, out, nullptr, st);
+                  const float *bias, float *out, cudaStream_t st, bool four_products) {
+  return launch_dense(0, rows, K, ldx, N, ldo, 0, relu, x, (const unsigned char *)image, bias, out, nullptr, st,
+                      four_products ? 4 : 3);
 }
 }  // namespace pc
 
