@@ -23,8 +23,14 @@
  *
  * Arithmetic contract: fp32, never fused (no FMA contraction), evaluated in the reference's written order, so that
  * FPS / ball-query / kNN / three_nn / gather indices and grouped or gathered values are bit-exact against the
- * reference algorithm; three_interpolate, all gradients and the attention contraction are deterministic (fixed
- * summation order, no float atomics).
+ * reference ALGORITHM in un-fused arithmetic -- i.e. against the reference's CPU code, or its .cu files compiled with
+ * --fmad=false.  The reference's own compile scripts use plain `nvcc -O2` (fmad on), which contracts the distance
+ * into FMAs: against such a build FPS tie / arg-max choices and ball-boundary hits can differ.
+ * three_interpolate, all gradients and the attention contraction are deterministic (fixed summation order, no float
+ * atomics).  Non-finite coordinates follow the registered ops: a NaN distance is a ball-query hit (max = fmaxf,
+ * tf_grouping_g.cu:24), three_nn never selects an infinite or NaN distance (tf_interpolate.cpp:66,74).
+ * The tensor-core entry points (pc_dense_*, pc_attention_layer_*) compute 3xTF32 split products with fp32
+ * accumulation: ~2e-6 of the output scale against a float64 product (documented per call).
  */
 #ifndef PCOPS_H_
 #define PCOPS_H_
