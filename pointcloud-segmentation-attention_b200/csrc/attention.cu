@@ -193,6 +193,119 @@ attention_fwd_kernel(size_t heads_total, int S, int H, const float *__restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// S = 32, D = 4 (every attention level of the ScanNet models): LANE = HEAD, operands staged by bulk copies.
+// The warp-per-head kernel above spends ~90 warp instructions per KB of K / V (two shuffle reductions for the softmax,
+// a third for the weighted sum, expf, prefetch bookkeeping): ncu showed it at 74 % of the issue slots for 0.73 of the
+// HBM peak -- an HBM stream that is nearly issue-bound, and that competes for issue slots with the FPS CTAs it shares
+// SMs with in the pipeline.  Here a warp owns 32 CONSECUTIVE heads = one contiguous 16 KB run of K and one of V (the
+// raw reshape, attention_layer.py:35, makes head gh the 128 floats at offset 128 gh).  Lane 0 issues one cp.async.bulk
+// per run into the warp's shared-memory ring (mbarrier complete_tx; three blocks ahead), and lane l then walks the
+// 32 pseudo-keys of head l out of shared memory with 128-bit loads: logits and maximum in a first pass over K, exp and
+// the weighted sum in a second pass over V -- no shuffles, no reductions, ~16 warp instructions per KB.  Lane l visits
+// its samples in the rotated order (s + l) mod 32, which keeps every quarter-warp's eight 16-byte accesses in eight
+// different bank groups (the heads are 512 bytes apart).
+constexpr int kLhWarps = 2;                 // warps per CTA, each with its own ring: 2 x 48 KB = 96 KB, which still fits
+constexpr int kLhSlots = 3;                 // next to an FPS CTA (128 KB) on the same SM
+constexpr int kLhSlotBytes = 32 * 128 * 4;  // one slot = the K (or V) run of 32 heads = 16 KB
+
+__device__ __forceinline__ void lh_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(kLhWarps * 32)
+attention_fwd_lanehead_kernel(size_t heads_total, const float *__restrict__ Q, const float *__restrict__ K,
+                              const float *__restrict__ V, float *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char lh_smem[];
+  __shared__ __align__(8) uint64_t s_bar[kLhWarps][kLhSlots];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *ring = lh_smem + (size_t)warp * kLhSlots * kLhSlotBytes;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_bar[warp][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kLhSlots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8 * i), "r"(1u));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  __syncwarp();
+  const size_t nblocks = (heads_total + 31) / 32;
+  const size_t wstride = (size_t)gridDim.x * kLhWarps;
+  const size_t first = (size_t)blockIdx.x * kLhWarps + warp;
+  const int my_blocks = first < nblocks ? (int)((nblocks - 1 - first) / wstride) + 1 : 0;
+  const int nseq = 2 * my_blocks;   // the warp's copy sequence: K of block 0, V of block 0, K of block 1, ... ; slot = seq % 3
+
+  auto issue = [&](int seq) {
+    const size_t h0 = (first + (size_t)(seq >> 1) * wstride) * 32;
+    const uint32_t nh = (uint32_t)((heads_total - h0 < 32) ? heads_total - h0 : 32);
+    const uint32_t bytes = nh * 512u;
+    const int slot = seq % kLhSlots;
+    const float *src = ((seq & 1) ? V : K) + h0 * 128;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + 8 * slot), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ring_s + slot * kLhSlotBytes),
+                 "l"(src), "r"(bytes), "r"(bar_s + 8 * slot)
+                 : "memory");
+  };
+  if (lane == 0)
+    for (int seq = 0; seq < kLhSlots && seq < nseq; ++seq) issue(seq);
+  for (int b = 0; b < my_blocks; ++b) {
+    const size_t gh = (first + (size_t)b * wstride) * 32 + lane;
+    const bool live = gh < heads_total;
+    const float4 q = live ? __ldg(reinterpret_cast<const float4 *>(Q) + gh) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int seq_k = 2 * b, seq_v = 2 * b + 1;
+    const float4 *ks = reinterpret_cast<const float4 *>(ring + (size_t)(seq_k % kLhSlots) * kLhSlotBytes) + lane * 32;
+    const float4 *vs = reinterpret_cast<const float4 *>(ring + (size_t)(seq_v % kLhSlots) * kLhSlotBytes) + lane * 32;
+    float p[32];
+    float mx = -INFINITY;
+    lh_wait(bar_s + 8 * (seq_k % kLhSlots), (uint32_t)((seq_k / kLhSlots) & 1));
+    if (live) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float4 k = ks[(t + lane) & 31];
+        // (q . k) / sqrt(4), accumulated like the warp-per-head kernel: fmaf chain from 0, then the scale
+        const float lg = 0.5f * fmaf(q.w, k.w, fmaf(q.z, k.z, fmaf(q.y, k.y, fmaf(q.x, k.x, 0.f))));
+        p[t] = lg;
+        mx = fmaxf(mx, lg);
+      }
+    }
+    __syncwarp();   // every lane is done with the K slot: refill it with the copy three steps ahead
+    if (lane == 0 && seq_k + kLhSlots < nseq) issue(seq_k + kLhSlots);
+    float sum = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    lh_wait(bar_s + 8 * (seq_v % kLhSlots), (uint32_t)((seq_v / kLhSlots) & 1));
+    if (live) {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float e = exp2f((p[t] - mx) * 1.4426950408889634f);
+        const float4 v = vs[(t + lane) & 31];
+        sum += e;
+        o0 = fmaf(e, v.x, o0); o1 = fmaf(e, v.y, o1); o2 = fmaf(e, v.z, o2); o3 = fmaf(e, v.w, o3);
+      }
+      const float inv = 1.0f / sum;
+      reinterpret_cast<float4 *>(out)[gh] = make_float4(o0 * inv, o1 * inv, o2 * inv, o3 * inv);
+    }
+    __syncwarp();
+    if (lane == 0 && seq_v + kLhSlots < nseq) issue(seq_v + kLhSlots);
+  }
+}
+
+int launch_fwd_lanehead(size_t heads, const float *Q, const float *K, const float *V, float *out, cudaStream_t st) {
+  const size_t smem = (size_t)kLhWarps * kLhSlots * kLhSlotBytes;
+  PC_CUDA_TRY(allow_smem(attention_fwd_lanehead_kernel, smem));
+  const size_t nblocks = (heads + 31) / 32;
+  size_t grid = (nblocks + kLhWarps - 1) / kLhWarps;
+  const size_t cap = (size_t)num_sms() * 2;   // two 96 KB CTAs fit an SM that holds no FPS CTA, one fits next to it
+  if (grid > cap) grid = cap;
+  attention_fwd_lanehead_kernel<<<(unsigned)grid, kLhWarps * 32, smem, st>>>(heads, Q, K, V, out);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
 template <int D, int NS, bool VEC>
 __global__ void __launch_bounds__(kAttWarps * 32)
 attention_bwd_kernel(size_t heads_total, int S, int H, const float *__restrict__ Q, const float *__restrict__ K,
@@ -290,6 +403,7 @@ extern "C" int pc_attention_fwd(int G, int S, int H, int D, const float *Q, cons
   cudaStream_t st = (cudaStream_t)stream;
   const size_t heads = (size_t)G * H;
   const bool vec = (D % 4 == 0) && pc::aligned16(Q) && pc::aligned16(K) && pc::aligned16(V) && pc::aligned16(out);
+  if (D == 4 && S == 32 && vec) return pc::launch_fwd_lanehead(heads, Q, K, V, out, st);   // lane = head, bulk-copy staging
 #define PC_FWD(DD, VV)                                                                        \
   do {                                                                                        \
     if (S <= 32) return pc::launch_fwd<DD, 1, VV>(heads, S, H, Q, K, V, out, st);             \
