@@ -215,7 +215,8 @@ PC_API int pc_fp_interpolate(int b, int n, int m, int c2, int c1, const float *d
  * with the reference's RAW reshape of each neighbourhood's (S,HD) buffer to (H,S,D) (attention_layer.py:35):
  *   logit[h,s] = sum_d Q[h*D+d] * Kflat[h*S*D + s*D + d] / sqrt(D);  a = softmax_s(logit)
  *   out[h*D+d] = sum_s a[h,s] * Vflat[h*S*D + s*D + d]
- * Supported: D in {1,2,4,8,16}, 1 <= S <= 128 (else PC_ERR_UNSUPPORTED).  fp32 throughout. */
+ * Supported: D in {1,2,4,8,16,32,64}, 1 <= S <= 128 (else PC_ERR_UNSUPPORTED).  fp32 throughout.  S = 32, D = 4 (the
+ * ScanNet models) runs a lane-per-head kernel with cp.async.bulk staging. */
 PC_API int pc_attention_fwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, float *out,
                      pc_stream_t stream);
 
@@ -242,6 +243,12 @@ PC_API int pc_attention_layer_prepare(int S, int C, const float *wq, const float
 PC_API int pc_attention_layer_fwd_prepared(int G, int S, int C, const float *xq, size_t xq_stride, const float *x,
                                     const float *wq, const float *bq, const float *wk, const float *bk, const float *wv,
                                     const float *bv, float *out, void *workspace, pc_stream_t stream);
+
+/* InnerAttentionLayer's contraction (attention_layer.py:61-75; experimental layers): attention ACROSS the 5
+ * heads of one point.  Q, K, V (rows, 5 * key_dim) -> out (rows, 5 * key_dim): per row weights = softmax_j(Q_i . K_j /
+ * sqrt(key_dim)) (5 x 5), out_i = sum_j w_ij V_j.  key_dim in {4, 8, 16, 32, 64}. */
+PC_API int pc_inner_attention_fwd(size_t rows, int key_dim, const float *Q, const float *K, const float *V, float *out,
+                                  pc_stream_t stream);
 
 /* Gradient of pc_attention_fwd w.r.t. Q, K, V given dout (G,HD); dQ (G,HD), dK and dV (G,S,HD) fully overwritten. */
 PC_API int pc_attention_bwd(int G, int S, int H, int D, const float *Q, const float *K, const float *V, const float *dout,

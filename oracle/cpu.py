@@ -302,3 +302,33 @@ def attention_layer_f64(x, xq, Wq, bq, Wk, bk, Wv, bv, heads, key_dim):
     w = np.exp(w - w.max(-1, keepdims=True))
     w = w / w.sum(-1, keepdims=True)
     return (w @ Vh).reshape(G, heads * key_dim)
+
+
+# ---- the experimental layers (attention_layer.py:48-210), float64 numpy restatements ---------------------------------
+def dense_f64(x, W, b, relu=False):
+    y = np.asarray(x, np.float64) @ np.asarray(W, np.float64) + (0 if b is None else np.asarray(b, np.float64))
+    return np.maximum(y, 0.0) if relu else y
+
+
+def inner_attention_f64(Q, K, V, key_dim):
+    """InnerAttentionLayer.call (:61-75) without its Dense layers: Q, K, V (..., 5 * key_dim)."""
+    f = np.float64
+    shp = Q.shape
+    q, k, v = (np.asarray(t, f).reshape(shp[:-1] + (5, key_dim)) for t in (Q, K, V))
+    w = q @ np.swapaxes(k, -1, -2) / np.sqrt(float(key_dim))
+    w = np.exp(w - w.max(-1, keepdims=True))
+    w = w / w.sum(-1, keepdims=True)
+    return (w @ v).reshape(shp)
+
+
+def attention_contract_f64(Q, K, V, heads, key_dim):
+    """AttentionLayer.call :35-42 on given projections: Q (G, H*D), K and V (G, S, H*D), raw reshape to heads."""
+    f = np.float64
+    G, S, HD = K.shape
+    Qh = np.asarray(Q, f).reshape(G, heads, 1, key_dim)
+    Kh = np.asarray(K, f).reshape(G, heads, S, key_dim)
+    Vh = np.asarray(V, f).reshape(G, heads, S, key_dim)
+    w = Qh @ Kh.transpose(0, 1, 3, 2) / np.sqrt(float(key_dim))
+    w = np.exp(w - w.max(-1, keepdims=True))
+    w = w / w.sum(-1, keepdims=True)
+    return (w @ Vh).reshape(G, HD)

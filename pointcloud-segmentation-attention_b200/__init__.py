@@ -8,6 +8,9 @@ Import with ``importlib.import_module("pointcloud-segmentation-attention_b200")`
     from pcops_b200.tf_interpolate import three_nn, three_interpolate
     from pcops_b200.attention_layer import AttentionLayer, attention_contract
     from pcops_b200.pointnet_util import sample_and_group, sample_and_group_all, fp_interpolate
+    from pcops_b200.sa_modules import PointnetSAModule, PointnetSAModuleAttention, SharedMLP, dense_layer
+    from pcops_b200.model_pipeline import ScanNetAttentionModel        # the whole attention model, pre-allocated
+    from pcops_b200.experimental_layers import AttentionNetLayer, PoolingAttentionNetLayer
 
 Everything computes in libpcops.so (include/pcops.h); there is no CPU or eager fallback.
 """

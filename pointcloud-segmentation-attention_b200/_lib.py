@@ -55,6 +55,7 @@ SIGNATURES = {
     "pc_attention_layer_prepare": (_i, [_i, _i] + [_vp] * 8),
     "pc_attention_layer_fwd_prepared": (_i, [_i, _i, _i, _vp, _sz] + [_vp] * 10),
     "pc_attention_fwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pc_inner_attention_fwd": (_i, [_sz, _i, _vp, _vp, _vp, _vp, _vp]),
     "pc_attention_bwd": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pc_scene_cells_workspace_bytes": (_sz, [_i, _i]),
     "pc_scene_bbox": (_i, [_i, _vp, _vp, _vp]),

@@ -141,7 +141,7 @@ class AttentionLayer(torch.nn.Module):
         hd = self.key_dim * self.num_heads
         C = inp.shape[-1]
         if (FUSED_LAYER and not torch.is_grad_enabled() and C in (64, 128, 256, 512) and hd == C and inp.shape[-2] == 32
-                and self.key_dim == 4):
+                and self.key_dim == 4 and query.shape[-1] == C):   # (a 3-wide query, pooling_attention_layer.py:38, is not)
             # inference at the four ScanNet attention widths: projections + contraction in one tensor-core kernel,
             # K and V never stored
             lead = inp.shape[:-2]

@@ -125,7 +125,7 @@ attention_fwd_kernel(size_t heads_total, int S, int H, const float *__restrict__
   const size_t stride = (size_t)gridDim.x * kAttWarps;
   size_t gh = (size_t)blockIdx.x * kAttWarps + (threadIdx.x >> 5);  // g*H + h
   const float rsd = 1.0f / sqrtf((float)D);
-  if constexpr (NS == 1) {
+  if constexpr (NS == 1 && D <= 16) {   // (wider heads: the double-buffered rows would not fit the register file)
     // (g,h) chunk: K + g*S*H*D + h*S*D == K + gh*S*D ;  Q + g*H*D + h*D == Q + gh*D
     const bool has = lane < S;
     float kc[D], vc[D], qc[D];
@@ -365,6 +365,70 @@ attention_bwd_kernel(size_t heads_total, int S, int H, const float *__restrict__
   if (lane == 0) store_row<D, VEC>(dQ + gh * D, gq);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// InnerAttentionLayer (attention_layer.py:48-78): attention ACROSS THE 5 HEADS of one point.  Per row: Q, K, V (5, kd)
+// (a raw reshape of the (5 kd) Dense outputs), weights = softmax_j(Q_i . K_j / sqrt(kd)) (5 x 5), out_i = sum_j w_ij V_j.
+// A thread per row; rows are 5 kd floats (kd multiple of 4: 128-bit loads).  Pure streaming of 3 reads + 1 write.
+template <int KD>
+__global__ void __launch_bounds__(128)
+inner_attention_kernel(size_t rows, const float *__restrict__ Q, const float *__restrict__ K, const float *__restrict__ V,
+                       float *__restrict__ out) {
+  constexpr int H = 5, W = H * KD;
+  const float rsd = 1.0f / sqrtf((float)KD);
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+    const float *q = Q + r * W, *k = K + r * W, *v = V + r * W;
+    float w[H][H];
+#pragma unroll
+    for (int i = 0; i < H; ++i)
+#pragma unroll
+      for (int j = 0; j < H; ++j) w[i][j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < KD; ++d) {
+      float qd[H], kd_[H];
+#pragma unroll
+      for (int i = 0; i < H; ++i) { qd[i] = __ldg(q + i * KD + d); kd_[i] = __ldg(k + i * KD + d); }
+#pragma unroll
+      for (int i = 0; i < H; ++i)
+#pragma unroll
+        for (int j = 0; j < H; ++j) w[i][j] = fmaf(qd[i], kd_[j], w[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < H; ++j) { w[i][j] *= rsd; mx = fmaxf(mx, w[i][j]); }
+#pragma unroll
+      for (int j = 0; j < H; ++j) { w[i][j] = expf(w[i][j] - mx); sum += w[i][j]; }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int j = 0; j < H; ++j) w[i][j] *= inv;
+    }
+    float *o = out + r * W;
+#pragma unroll
+    for (int d = 0; d < KD; ++d) {
+      float vd[H];
+#pragma unroll
+      for (int j = 0; j < H; ++j) vd[j] = __ldg(v + j * KD + d);
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) acc = fmaf(w[i][j], vd[j], acc);
+        o[i * KD + d] = acc;
+      }
+    }
+  }
+}
+
+template <int KD>
+int launch_inner(size_t rows, const float *Q, const float *K, const float *V, float *out, cudaStream_t st) {
+  size_t blocks = (rows + 127) / 128;
+  const size_t cap = (size_t)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  inner_attention_kernel<KD><<<(unsigned)blocks, 128, 0, st>>>(rows, Q, K, V, out);
+  PC_RETURN_LAUNCH_STATUS();
+}
+
 template <int D, int NS, bool VEC>
 int launch_fwd(size_t heads, int S, int H, const float *Q, const float *K, const float *V, float *out,
                cudaStream_t st) {
@@ -388,7 +452,7 @@ int launch_bwd(size_t heads, int S, int H, const float *Q, const float *K, const
 namespace {
 int check_att(int G, int S, int H, int D) {
   if (G < 0 || S <= 0 || H <= 0 || D <= 0) return PC_ERR_INVALID_ARGUMENT;
-  if (!(D == 1 || D == 2 || D == 4 || D == 8 || D == 16) || S > 128) return PC_ERR_UNSUPPORTED;
+  if (!(D == 1 || D == 2 || D == 4 || D == 8 || D == 16 || D == 32 || D == 64) || S > 128) return PC_ERR_UNSUPPORTED;
   if ((size_t)G * H > 0x7fffffffu * (size_t)pc::kAttWarps) return PC_ERR_UNSUPPORTED;
   return PC_OK;
 }
@@ -415,7 +479,9 @@ extern "C" int pc_attention_fwd(int G, int S, int H, int D, const float *Q, cons
     case 2: PC_FWD(2, false);
     case 4: if (vec) PC_FWD(4, true); else PC_FWD(4, false);
     case 8: if (vec) PC_FWD(8, true); else PC_FWD(8, false);
-    default: if (vec) PC_FWD(16, true); else PC_FWD(16, false);
+    case 16: if (vec) PC_FWD(16, true); else PC_FWD(16, false);
+    case 32: if (vec) PC_FWD(32, true); else PC_FWD(32, false);   // key_dim of the experimental layers (attention_layer.py:128-210)
+    default: if (vec) PC_FWD(64, true); else PC_FWD(64, false);
   }
 #undef PC_FWD
 }
@@ -441,7 +507,25 @@ extern "C" int pc_attention_bwd(int G, int S, int H, int D, const float *Q, cons
     case 2: PC_BWD(2, false);
     case 4: if (vec) PC_BWD(4, true); else PC_BWD(4, false);
     case 8: if (vec) PC_BWD(8, true); else PC_BWD(8, false);
-    default: if (vec) PC_BWD(16, true); else PC_BWD(16, false);
+    case 16: if (vec) PC_BWD(16, true); else PC_BWD(16, false);
+    case 32: if (vec) PC_BWD(32, true); else PC_BWD(32, false);
+    default: if (vec) PC_BWD(64, true); else PC_BWD(64, false);
   }
 #undef PC_BWD
+}
+
+extern "C" int pc_inner_attention_fwd(size_t rows, int key_dim, const float *Q, const float *K, const float *V, float *out,
+                                      pc_stream_t stream) {
+  if (key_dim <= 0) return PC_ERR_INVALID_ARGUMENT;
+  if (rows == 0) return PC_OK;
+  if (!Q || !K || !V || !out) return PC_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (key_dim) {
+    case 4: return pc::launch_inner<4>(rows, Q, K, V, out, st);
+    case 8: return pc::launch_inner<8>(rows, Q, K, V, out, st);
+    case 16: return pc::launch_inner<16>(rows, Q, K, V, out, st);
+    case 32: return pc::launch_inner<32>(rows, Q, K, V, out, st);
+    case 64: return pc::launch_inner<64>(rows, Q, K, V, out, st);
+    default: return PC_ERR_UNSUPPORTED;
+  }
 }
