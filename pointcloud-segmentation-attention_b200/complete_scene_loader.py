@@ -194,6 +194,122 @@ def chunk_scene(points, npoints=NPOINTS, device=None):
     return SceneChunks(point_sets, src_index, masks, orig, d_desc, npoints)
 
 
+class _PendingScan:
+    """One scan inside chunk_scenes(): the four device passes of chunk_scene() as stages separated by the host
+    decisions they need -- A: bounding box; B: cell membership (needs the box on the host: float64 cell bounds);
+    C: candidate-chunk mask sums (needs the cell counts on the host: numpy's RNG draws, chunk descriptors);
+    D: assembly (needs the mask sums on the host: which chunks survive).  Every stage ends with an asynchronous copy
+    into pinned memory and an event, so the host only ever waits for this scan's own small kernels."""
+
+    def __init__(self, pts, npoints, stream):
+        self.pts, self.npoints, self.st, self.stage = pts, npoints, stream, 0
+        self.dev = pts.device
+        L, c_st = _lib.lib(), _lib.ctypes.c_void_p(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            self.bb = torch.empty(6, dtype=torch.float32, device=self.dev)
+            _lib.check(L.pc_scene_bbox(pts.shape[0], _lib.ptr(pts), _lib.ptr(self.bb), c_st), "scene_bbox")
+            self.h_bb = torch.empty(6, dtype=torch.float32).pin_memory()
+            self.h_bb.copy_(self.bb, non_blocking=True)
+            self.ev = torch.cuda.Event()
+            self.ev.record(stream)
+
+    def ready(self):
+        return self.ev.query()
+
+    def advance(self):
+        """Run the next stage (waits for the previous one).  Stage C consumes numpy's global RNG: the caller runs it in
+        scan order."""
+        L, c_st = _lib.lib(), _lib.ctypes.c_void_p(self.st.cuda_stream)
+        self.ev.synchronize()
+        n, dev = int(self.pts.shape[0]), self.dev
+        with torch.cuda.stream(self.st):
+            if self.stage == 0:      # B
+                bb = self.h_bb.numpy()
+                self.boxes = _cell_boxes(bb[:3], bb[3:])
+                ncells = self.boxes.shape[0]
+                self.d_boxes = torch.from_numpy(self.boxes).to(dev)
+                self.cell_base = torch.empty(ncells + 1, dtype=torch.int32, device=dev)
+                self.cell_list = torch.empty(max(1, 4 * n), dtype=torch.int32, device=dev)
+                self.inner = torch.empty(max(1, 4 * n), dtype=torch.uint8, device=dev)
+                self.ws = _lib.workspace(L.pc_scene_cells_workspace_bytes(n, ncells), dev)
+                _lib.check(L.pc_scene_cells(n, ncells, _lib.ptr(self.pts), _lib.ptr(self.d_boxes), _lib.ptr(self.cell_base),
+                                            _lib.ptr(self.cell_list), _lib.ptr(self.inner), _lib.ptr(self.ws), c_st), "scene_cells")
+                self.h_base = torch.empty(ncells + 1, dtype=torch.int32).pin_memory()
+                self.h_base.copy_(self.cell_base, non_blocking=True)
+            elif self.stage == 1:    # C
+                base = self.h_base.numpy().astype(np.int64)
+                self.desc, order, fill = _plan_chunks(base, self.npoints)
+                self.d_order = torch.from_numpy(order).to(dev)
+                self.d_fill = torch.from_numpy(fill).to(dev)
+                d_desc = torch.from_numpy(self.desc).to(dev)
+                self.masksum = torch.empty(len(self.desc), dtype=torch.int32, device=dev)
+                _lib.check(L.pc_scene_chunk_masksum(len(self.desc), self.npoints, _lib.ptr(d_desc), _lib.ptr(self.d_order),
+                                                    _lib.ptr(self.inner), _lib.ptr(self.masksum), c_st), "scene_chunk_masksum")
+                self.h_mask = torch.empty(len(self.desc), dtype=torch.int32).pin_memory()
+                self.h_mask.copy_(self.masksum, non_blocking=True)
+                self._keep_alive = d_desc
+            else:                    # D
+                keep = np.nonzero(self.h_mask.numpy() > 0)[0]
+                if len(keep) == 0:
+                    raise ValueError("need at least one array to concatenate")
+                d_desc = torch.from_numpy(np.ascontiguousarray(self.desc[keep])).to(dev)
+                C, npts = len(keep), self.npoints
+                src_index = torch.empty((C, npts), dtype=torch.int32, device=dev)
+                point_sets = torch.empty((C, npts, 3), dtype=torch.float32, device=dev)
+                masks = torch.empty((C, npts), dtype=torch.uint8, device=dev)
+                orig = torch.empty((C, npts), dtype=torch.int64, device=dev)
+                _lib.check(L.pc_scene_chunk_assemble(C, npts, _lib.ptr(d_desc), _lib.ptr(self.d_order), _lib.ptr(self.d_fill),
+                                                     _lib.ptr(self.cell_list), _lib.ptr(self.inner), _lib.ptr(self.pts),
+                                                     _lib.ptr(src_index), _lib.ptr(point_sets), _lib.ptr(masks), _lib.ptr(orig),
+                                                     c_st), "scene_chunk_assemble")
+                self.result = SceneChunks(point_sets, src_index, masks, orig, d_desc, npts)
+            self.ev = torch.cuda.Event()
+            self.ev.record(self.st)
+            self.stage += 1
+        return self.stage == 3
+
+
+def chunk_scenes(scans, npoints=NPOINTS, lookahead=2, stream=None):
+    """Chunk a SEQUENCE of scans (float32 CUDA tensors (N_i, 3)) with up to ``lookahead`` later scans in flight: the
+    bounding-box and cell-membership passes of scans i+1, i+2 run (on ``stream``, default a stream of its own) while
+    scan i is being planned on the host and consumed by the caller, so the three host round trips of a scan overlap
+    with device work instead of idling the GPU.  Yields (SceneChunks, event): wait for the event on the consuming
+    stream before using the tensors.  numpy's global RNG is consumed strictly in scan order (stage C runs only for
+    the oldest scan), so the chunks equal those of calling chunk_scene() scan after scan under the same seed."""
+    from collections import deque
+    it = iter(scans)
+    pend = deque()
+    st = stream
+
+    def start():
+        nonlocal st
+        pts = next(it, None)
+        if pts is None:
+            return
+        if not (isinstance(pts, torch.Tensor) and pts.is_cuda and pts.dtype == torch.float32 and pts.dim() == 2 and pts.shape[1] == 3):
+            raise TypeError("chunk_scenes expects float32 CUDA tensors of shape (N, 3)")
+        if st is None:
+            st = torch.cuda.Stream(device=pts.device)
+        st.wait_stream(torch.cuda.current_stream(pts.device))     # the scan may just have been produced there
+        with torch.cuda.device(pts.device):
+            pend.append(_PendingScan(pts.contiguous(), npoints, st))
+
+    for _ in range(lookahead + 1):
+        start()
+    while pend:
+        for ps in list(pend)[1:]:          # younger scans: the RNG-free stage B as soon as their box has arrived
+            if ps.stage == 0 and ps.ready():
+                with torch.cuda.device(ps.dev):
+                    ps.advance()
+        head = pend[0]
+        with torch.cuda.device(head.dev):
+            while not head.advance():
+                pass
+        pend.popleft()
+        start()
+        yield head.result, head.ev
+
+
 def get_all_subsets_with_all_points_for_scene_features(points, features, get_sample_weights):
     """complete_scene_loader.py:4-117.  ``features[0]`` are the labels when ``get_sample_weights`` (:66)."""
     as_numpy = isinstance(points, np.ndarray)

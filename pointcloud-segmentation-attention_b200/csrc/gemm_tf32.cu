@@ -46,6 +46,7 @@ constexpr int kStage = 2 * kABlock + 2 * kBBlock;   // 96 KB: A_hi | A_lo | B_hi
 constexpr int kThreads = 288;
 constexpr int kMaxN = 1024;                // bias staged in shared memory
 constexpr int kPatch = 32 * 36;            // floats per epilogue warp: 32 rows x 32 columns, rows padded to 36
+constexpr int kFixedBytes = 24 * 1024;     // bias, patches, barriers of the forward kernel in front of its operand ring
 
 __host__ __device__ inline int block_offset(int row, int k) {  // byte offset of (row, k) inside one K block, k < 32
   return (row >> 3) * kSBO + (row & 7) * 128 + (((k >> 2) ^ (row & 7)) << 4) + (k & 3) * 4;
@@ -121,20 +122,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
 __global__ void __launch_bounds__(kThreads, 1)
-dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, size_t ldo, size_t ldp, int relu, int vec_x,
+dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int nst, int nacc, size_t ldo, size_t ldp, int relu, int vec_x,
                   int vec_o, const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
                   float *__restrict__ out, float *__restrict__ pooled) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *stage_buf = smem;                                          // [2][A_hi | A_lo | B_hi | B_lo]
-  float *s_bias = reinterpret_cast<float *>(smem + 2 * kStage);             // kMaxN
+  // fixed part first (kFixedBytes), then the operand ring: nst stages of [A_hi 16 KB | A_lo 16 KB | B_hi | B_lo], B parts
+  // sw x 128 bytes each -- 2 stages at sw = 256, 3 at 128, 4 below: a narrow layer's block is handed over through the
+  // same mbarrier / tcgen05.commit round trips as a wide one, so it needs more blocks in flight to hide them
+  float *s_bias = reinterpret_cast<float *>(smem);                          // kMaxN
   float *s_patch = s_bias + kMaxN;                                          // 4 x kPatch
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_patch + 4 * kPatch);     // full[2], empty[2], t_full[2], t_empty[2]
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_patch + 4 * kPatch);     // full[4], empty[4], t_full[8], t_empty[8]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 24);
+  unsigned char *stage_buf = smem + kFixedBytes;
+  const int b_half = sw * 128, stage_bytes = 2 * kABlock + 2 * b_half;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
-  const uint32_t full[2] = {bar0, bar0 + 8}, empty[2] = {bar0 + 16, bar0 + 24};
-  const uint32_t t_full[2] = {bar0 + 32, bar0 + 40}, t_empty[2] = {bar0 + 48, bar0 + 56};
+  const uint32_t full0 = bar0, empty0 = bar0 + 32;                          // full[s] = full0 + 8 s, empty[s] = empty0 + 8 s
+  // nacc TMEM accumulators of sw columns each (2 at sw = 256 ... 8 at sw <= 64): an item's accumulator travels MMA ->
+  // commit -> epilogue -> arrive -> MMA, and with two accumulators that round trip (about 4 us) capped a CTA at one item
+  // per ~2 us whatever the item's size
+  const uint32_t t_full0 = bar0 + 64, t_empty0 = bar0 + 128;                // t_full[a] = t_full0 + 8 a, ...
 
   if (warp == 8) {  // the whole TMEM: two 256-column fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -143,11 +151,13 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(128u));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty[s]), "r"(1u));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full[s]), "r"(1u));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty[s]), "r"(128u));
+    for (int s = 0; s < 4; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(128u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(1u));
+    }
+    for (int s = 0; s < 8; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full0 + 8 * s), "r"(1u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty0 + 8 * s), "r"(128u));
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -195,19 +205,19 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
       const int w = it_ / nkb, kb = it_ - w * nkb;
       const int col0 = ((blockIdx.x + w * (int)gridDim.x) % nchunk) * sw;
       const int nc = min(sw, N - col0);
-      const int s = it_ & 1;
-      mbar_wait(empty[s], ((it_ >> 1) & 1) ^ 1);       // the MMAs that read this stage two blocks ago have completed
-      unsigned char *st = stage_buf + s * kStage;
+      const int s = it_ % nst;
+      mbar_wait(empty0 + 8 * s, ((it_ / nst) & 1) ^ 1);   // the MMAs that read this stage nst blocks ago have completed
+      unsigned char *st = stage_buf + s * stage_bytes;
       if (tid == 0) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
         const unsigned char *src = image + ((size_t)(col0 / kMaxNc) * nkb + kb) * (2 * kBBlock) + (size_t)(col0 % kMaxNc) * 128;
-        const uint32_t dst = stage_s + s * kStage + 2 * kABlock;
+        const uint32_t dst = stage_s + s * stage_bytes + 2 * kABlock;
         const uint32_t bytes = (uint32_t)((nc + 15) & ~15) * 128u;   // the MMA's N is a multiple of 16: zero rows beyond nc
-        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full[s]), "r"(2u * bytes) : "memory");
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(2u * bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(src), "r"(bytes), "r"(full[s])
+                     "l"(src), "r"(bytes), "r"(full0 + 8 * s)
                      : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + kBBlock),
-                     "l"(src + kBBlock), "r"(bytes), "r"(full[s])
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + b_half),
+                     "l"(src + kBBlock), "r"(bytes), "r"(full0 + 8 * s)
                      : "memory");
       }
 #pragma unroll
@@ -222,8 +232,11 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
         *reinterpret_cast<float4 *>(st + kABlock + off) = l;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * s) : "memory");
     };
+    // Two K blocks ahead.  (Four blocks ahead -- 64 KB of loads in flight per SM -- was measured and made every layer
+    // SLOWER, 62 -> 92 us at SA1, 55 -> 87 us at FP4, with plain and with volatile loads: the per-block cost of these
+    // layers is not the global-load latency.)
     float4 bufA[8], bufB[8];
     fetch(bufA, 0);
     fetch(bufB, 1);
@@ -240,29 +253,29 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
     if (lane == 0) {
       int it = 0, w = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
-        const int a = w & 1;
+        const int a = w % nacc;
         const int nc = min(sw, N - (item % nchunk) * sw);
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc rounded up to 16, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-        mbar_wait(t_empty[a], ((w >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        mbar_wait(t_empty0 + 8 * a, ((w / nacc) & 1) ^ 1);      // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t acc = 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it & 1;
-          mbar_wait(full[s], (it >> 1) & 1);
+          const int s = it % nst;
+          mbar_wait(full0 + 8 * s, (it / nst) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = stage_s + s * kStage, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + kBBlock;
+          const uint32_t a_hi = stage_s + s * stage_bytes, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + b_half;
           for (int split = 0; split < nsplit; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi [, X_lo W_lo: fp32-grade]
             const uint32_t as = (split >= 2) ? a_lo : a_hi, bs = (split & 1) ? b_lo : b_hi;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              mma_tf32(tmem + a * kMaxNc, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
+              mma_tf32(tmem + a * sw, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
               acc = 1;
             }
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty[s]) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_full[a]) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_full0 + 8 * a) : "memory");
       }
     }
   } else {
@@ -271,12 +284,12 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
     float *patch = s_patch + qtr * kPatch;
     int w = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
-      const int a = w & 1, tile = item / nchunk, col0 = (item - tile * nchunk) * sw;
+      const int a = w % nacc, tile = item / nchunk, col0 = (item - tile * nchunk) * sw;
       const int nc = min(sw, N - col0);
       const size_t row0 = (size_t)tile * kRows + qtr * 32;    // this warp's 32 rows
-      mbar_wait(t_full[a], (w >> 1) & 1);
+      mbar_wait(t_full0 + 8 * a, (w / nacc) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * kMaxNc;
+      const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * sw;
       for (int c0 = 0; c0 < nc; c0 += 32) {
         uint32_t v[32];
         PCG_TMEM_LD32(taddr + c0, v);
@@ -336,7 +349,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the accumulator is handed back
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty[a]) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty0 + 8 * a) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -348,12 +361,30 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, siz
 
 // ---------------------------------------------------------------------------------------------------------------
 // Weight gradient: dW (K, N) = X^T (K, rows) . dY (rows, N), db (N) = column sums of dY.
-// The reduction dimension is the ROW index, so both operands are transposed on the way into shared memory: producers
-// read 32 rows x (128 | nc) columns of X / dY with 128-bit loads (lane = row, so that the scattered 4-byte stores of a
-// warp -- element (column, row) of the K-major operand -- fall into 32 different banks of the swizzled layout) and write
-// TF32 hi / lo parts.  Work item = (tile of 128 input channels, chunk of <= 256 output channels, split of the rows);
-// each item leaves its partial product in the workspace, a second kernel adds the partials in ascending split order
-// (deterministic; no float atomics).  db is accumulated by the same producers (items of channel tile 0 only).
+// The reduction dimension is the ROW index, i.e. both operands are "MN-major" in UMMA terms: a block of 32 rows x 128
+// (or nc) columns of X / dY, row-major as it lies in HBM, IS a canonical MN-major operand (layout below).  So the
+// producers load coalesced float4s exactly as
+// the forward kernel does, split them into TF32 hi / lo and store 128 bits at a time; the instruction descriptor sets
+// the a_major / b_major bits.  (A first version transposed both operands in the producers with lane = row: 32
+// different cache lines per load instruction and 192 scalar stores per thread and block -- 887 us for 524288 x 64 x 64
+// under ncu; this one: see DESIGN.md.)  Work item = (tile of 128 input channels, chunk of <= 256 output channels,
+// split of the rows); each item leaves its partial product in the workspace, a second kernel adds the partials in
+// ascending split order (deterministic; no float atomics).  db is accumulated by the same producers (items of channel
+// tile 0 only).
+// For 32-bit MN-major operands the tensor core accepts ONE shared-memory layout (CUTLASS sm100_common.inl:92: "for
+// mn-major tf32 operands, SW128_32B is the only available smem layout"; with plain SWIZZLE_128B the MMAs ran and produced
+// zeros): atoms of 4 k-rows x 128 bytes, the row's four 32-byte chunks XOR-ed by (row & 3) -- Swizzle<2,5,2>, descriptor
+// layout type 1.  Atoms of one 4-row group are 512 bytes apart (LBO), groups follow each other (SBO); an MMA of K = 8
+// spans two groups.
+__device__ __forceinline__ int mn_offset(int krow, int quad, int atoms_per_group) {  // byte offset of float4 (k-row, column quad)
+  return ((krow >> 2) * atoms_per_group + (quad >> 3)) * 512 + (krow & 3) * 128 + (((((quad & 7) >> 1) ^ (krow & 3)) << 5) | ((quad & 1) << 4));
+}
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {  // MN-major, SWIZZLE_128B_BASE32B
+  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | ((lbo >> 4) << 16);
+  const uint32_t hi = (sbo >> 4) | (1u << 14) | (1u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int splits, size_t rows_per_split, int vec_x,
                         int vec_y, const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ part_w,
@@ -361,7 +392,8 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *stage_buf = smem;
   float *s_patch = reinterpret_cast<float *>(smem + 2 * kStage);
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_patch + 4 * kPatch);
+  float *s_red = s_patch + 4 * kPatch;                                      // 64 float4: the producers' db exchange
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_red + 256);
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
@@ -398,7 +430,10 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
   };
 
   if (warp < 4) {
-    // ---------------------------------------------------------------- producers (lane = row of the 32-row block)
+    // ---------------------------------------------------------------- producers: coalesced loads, 128-bit stores
+    // thread t takes float4 t + 128 i of the block: X (32 rows x 32 quads): row = i4 >> 5, quad = i4 & 31 (i < 8);
+    // dY (32 rows x 64 quads): row = i4 >> 6, quad = i4 & 63 (i < 16).  The loads of block b + 1 are issued right after
+    // block b has been stored, so they fly while the tensor core works on b.
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int mj = item / splits, mt = mj / nchunk, j = mj - mt * nchunk, sp = item - mj * splits;
@@ -407,19 +442,15 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
       int nblk;
       item_rows(item, r_lo, nblk);
       const size_t r_end = r_lo + rows_per_split < rows ? r_lo + rows_per_split : rows;
-      float bsum[16][4];                                 // column sums of dY over this item's rows (this lane's rows)
+      float4 xa[8], yb[16];
+      auto fetch = [&](int blk) {
+        const size_t row0 = r_lo + (size_t)blk * kKB;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bsum[i][0] = bsum[i][1] = bsum[i][2] = bsum[i][3] = 0.f;
-      for (int blk = 0; blk < nblk; ++blk, ++it) {
-        const size_t row = r_lo + (size_t)blk * kKB + lane;
-        const bool rin = row < r_end;
-        float4 xa[8], yb[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {                    // X: columns 128 mt + 4 (8 warp + i) ..
-          const int c0 = mt * kRows + 4 * (warp * 8 + i);
+        for (int i = 0; i < 8; ++i) {
+          const int i4 = tid + 128 * i, r = i4 >> 5, c0 = mt * kRows + 4 * (i4 & 31);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rin && c0 < K) {
-            const float *src = x + row * ldx + c0;
+          if (blk < nblk && row0 + r < r_end && c0 < K) {
+            const float *src = x + (row0 + r) * ldx + c0;
             if (vec_x && c0 + 3 < K) v = __ldg(reinterpret_cast<const float4 *>(src));
             else {
               v.x = __ldg(src);
@@ -431,11 +462,11 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
           xa[i] = v;
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {                   // dY: columns 256 j + 4 (16 warp + i) ..
-          const int cl = 4 * (warp * 16 + i), c0 = j * kMaxNc + cl;
+        for (int i = 0; i < 16; ++i) {
+          const int i4 = tid + 128 * i, r = i4 >> 6, cl = 4 * (i4 & 63);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rin && cl < nc) {
-            const float *src = dy + row * ldy + c0;
+          if (blk < nblk && row0 + r < r_end && cl < nc) {
+            const float *src = dy + (row0 + r) * ldy + j * kMaxNc + cl;
             if (vec_y && cl + 3 < nc) v = __ldg(reinterpret_cast<const float4 *>(src));
             else {
               v.x = __ldg(src);
@@ -445,51 +476,57 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
             }
           }
           yb[i] = v;
-          bsum[i][0] += v.x; bsum[i][1] += v.y; bsum[i][2] += v.z; bsum[i][3] += v.w;
         }
+      };
+      // column sums of dY: thread t always holds the same column quad (t & 63) of rows (t >> 6) + 2 i
+      float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      fetch(0);
+      for (int blk = 0; blk < nblk; ++blk, ++it) {
         const int s = it & 1;
         mbar_wait(empty[s], ((it >> 1) & 1) ^ 1);
         unsigned char *st = stage_buf + s * kStage;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int m0 = 4 * (warp * 8 + i);
-          const float v[4] = {xa[i].x, xa[i].y, xa[i].z, xa[i].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float h = tf32_rna(v[e]), l = tf32_rna(v[e] - h);
-            const int off = block_offset(m0 + e, lane);
-            *reinterpret_cast<float *>(st + off) = h;
-            *reinterpret_cast<float *>(st + kABlock + off) = l;
-          }
+          const int i4 = tid + 128 * i;
+          const float4 v = xa[i];
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          const int off = mn_offset(i4 >> 5, i4 & 31, 4);
+          *reinterpret_cast<float4 *>(st + off) = h;
+          *reinterpret_cast<float4 *>(st + kABlock + off) = l;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int n0 = 4 * (warp * 16 + i);
-          if (n0 < nc) {                                   // warp-uniform
-            const float v[4] = {yb[i].x, yb[i].y, yb[i].z, yb[i].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float h = tf32_rna(v[e]), l = tf32_rna(v[e] - h);
-              const int off = block_offset(n0 + e, lane);
-              *reinterpret_cast<float *>(st + 2 * kABlock + off) = h;
-              *reinterpret_cast<float *>(st + 2 * kABlock + kBBlock + off) = l;
-            }
-          }
+          const int i4 = tid + 128 * i;
+          const float4 v = yb[i];
+          bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          const int off = mn_offset(i4 >> 6, i4 & 63, 8);
+          *reinterpret_cast<float4 *>(st + 2 * kABlock + off) = h;
+          *reinterpret_cast<float4 *>(st + 2 * kABlock + kBBlock + off) = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full[s]) : "memory");
+        fetch(blk + 1);
       }
-      if (mt == 0 && part_b) {                             // db partial of (chunk j, split sp): sum over the 32 lanes = rows
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v = bsum[i][e];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PC_FULL_MASK, v, o);
-            const int cl = 4 * (warp * 16 + i) + e;
-            if (lane == 0 && cl < nc) part_b[(size_t)sp * N + j * kMaxNc + cl] = v;
-          }
+      if (mt == 0 && part_b) {
+        // db partial of (chunk j, split sp): threads t and t + 64 hold the same column quad (rows of different parity):
+        // combined through shared memory in a fixed order
+        float4 *red = reinterpret_cast<float4 *>(s_red);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid >= 64) red[tid - 64] = bsum;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < 64) {
+          const float4 o = red[tid];
+          const int cl = 4 * tid;
+          float *dst = part_b + (size_t)sp * N + j * kMaxNc + cl;
+          if (cl < nc) dst[0] = bsum.x + o.x;
+          if (cl + 1 < nc) dst[1] = bsum.y + o.y;
+          if (cl + 2 < nc) dst[2] = bsum.z + o.z;
+          if (cl + 3 < nc) dst[3] = bsum.w + o.w;
         }
       }
     }
@@ -500,7 +537,9 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
         const int a = w & 1, j = (item / splits) % nchunk;
         const int nc = min(kMaxNc, N - j * kMaxNc);
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        // D = F32, A = B = TF32, BOTH MN-major (bits 15, 16), N = nc rounded up to 16, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
         size_t r_lo;
         int nblk;
         item_rows(item, r_lo, nblk);
@@ -516,8 +555,9 @@ dense_bwd_weight_kernel(size_t rows, int K, size_t ldx, int N, size_t ldy, int s
           for (int split = 0; split < 3; ++split) {
             const uint32_t as = (split == 2) ? a_lo : a_hi, bs = (split == 1) ? b_lo : b_hi;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              mma_tf32(tmem + a * kMaxNc, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
+            for (int kk = 0; kk < 4; ++kk) {   // rows 8 kk .. 8 kk + 7 = two 4-row groups; a group is 4 atoms (2 KB) of A, 8 (4 KB) of B
+              mma_tf32(tmem + a * kMaxNc, smem_desc_mn(as + kk * 4096, 512, 2048), smem_desc_mn(bs + kk * 8192, 512, 4096),
+                       idesc, acc);
               acc = 1;
             }
           }
@@ -616,26 +656,33 @@ int launch_prep(int K, int N, size_t sk, size_t sn, const float *w, unsigned cha
 int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, size_t ldp, int relu, const float *x,
                  const unsigned char *image, const float *bias, float *out, float *pooled, cudaStream_t st,
                  int nsplit = 3) {
-  const size_t smem = 2 * (size_t)kStage + (kMaxN + 4 * kPatch) * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+  static_assert((kMaxN + 4 * kPatch) * sizeof(float) + 24 * sizeof(uint64_t) + 16 <= kFixedBytes, "fixed part");
   const int ntiles = (int)((rows + kRows - 1) / kRows);
   // output columns per item: narrower units only when the launch has very few (tile, unit) items -- every unit of a
   // tile stages the tile's A operand again, so splitting 64 items into 128 made SA4's layers slower (23 -> 33 us) while
   // splitting FP1's 8 items into 64 made them faster
   int sw = kMaxNc;
   while (sw > 32 && (long long)ntiles * ((N + sw - 1) / sw) <= num_sms() / 4) sw >>= 1;
+  if (sw > N) sw = (N + 31) / 32 * 32 > 32 ? (N + 31) / 32 * 32 : 32;   // one unit narrower than 256: a smaller B block
   const int nitems = ntiles * ((N + sw - 1) / sw);
   const int grid = nitems < num_sms() ? nitems : num_sms();
+  const size_t stage_bytes = 2 * (size_t)kABlock + 2 * (size_t)sw * 128;
+  int nst = (int)((227 * 1024 - kFixedBytes) / stage_bytes);
+  nst = nst > 4 ? 4 : nst;
+  int nacc = 512 / sw;
+  nacc = nacc > 8 ? 8 : nacc;
+  const size_t smem = kFixedBytes + (size_t)nst * stage_bytes;
   const int vec_x = (ldx % 4 == 0) && aligned16(x);
   const int vec_o = (ldo % 4 == 0) && aligned16(out);
   if (pool == 1) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
-    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else if (pool == 2) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
-    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
-    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   }
   PC_RETURN_LAUNCH_STATUS();
 }
@@ -714,7 +761,7 @@ extern "C" int pc_dense_bwd_weight(size_t rows, int K, int N, const float *x, si
   size_t rps = (rows + sp - 1) / sp;
   rps = (rps + pc::kKB - 1) / pc::kKB * pc::kKB;
   float *part_w = (float *)workspace, *part_b = part_w + (size_t)sp * K * N;
-  const size_t smem = 2 * (size_t)pc::kStage + 4 * pc::kPatch * sizeof(float) + 8 * sizeof(uint64_t) + 16;
+  const size_t smem = 2 * (size_t)pc::kStage + (4 * pc::kPatch + 256) * sizeof(float) + 8 * sizeof(uint64_t) + 16;
   PC_CUDA_TRY(pc::allow_smem(pc::dense_bwd_weight_kernel, smem));
   const int nitems = ((K + pc::kRows - 1) / pc::kRows) * ((N + pc::kMaxNc - 1) / pc::kMaxNc) * sp;
   const int grid = nitems < pc::num_sms() ? nitems : pc::num_sms();

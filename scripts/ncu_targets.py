@@ -18,7 +18,7 @@ import pcops_b200 as ops  # noqa: E402
 from pcops_b200 import complete_scene_loader as csl  # noqa: E402
 from pcops_b200 import synth  # noqa: E402
 
-groups = set(sys.argv[1:]) or {"fps", "geom", "grads", "knn", "scene", "big"}
+groups = set(sys.argv[1:]) or {"fps", "geom", "grads", "knn", "scene", "big", "dense", "att"}
 dev = torch.device("cuda")
 B = 16
 xyz_np, feat_np = synth.scannet_batch(0, B, 8192)
@@ -79,4 +79,18 @@ if "big" in groups:          # fps_cluster_kernel (8 CTAs per scene) and the coo
     profiled(lambda: ops.farthest_point_sample(256, xb))
     xc = torch.rand((2, 1 << 20, 3), generator=g, device=dev)
     profiled(lambda: ops.farthest_point_sample(64, xc))
+if "dense" in groups:        # the tcgen05 Dense engine at a wide-row (SA1 layer 2) and a square (FP4) shape, and the weight gradient
+    from pcops_b200 import sa_modules as sam
+    for rows, K, N in ((B * 1024 * 32, 32, 32), (B * 8192, 128, 128), (B * 64 * 32, 259, 256)):
+        xx = torch.randn((rows, K), generator=g, device=dev)
+        img = sam.DenseImage(torch.randn((K, N), generator=g, device=dev), torch.randn(N, generator=g, device=dev))
+        profiled(lambda: sam.dense(xx, img, True))
+    xx = torch.randn((B * 1024 * 32, 64), generator=g, device=dev)
+    dy = torch.randn((B * 1024 * 32, 64), generator=g, device=dev)
+    profiled(lambda: sam.dense_weight_grad(xx, dy))
+if "att" in groups:          # attention contraction (lane = head, bulk-copy staging) and its backward at SA1
+    Q = torch.randn((B * 1024, 64), generator=g, device=dev)
+    K_ = torch.randn((B * 1024, 32, 64), generator=g, device=dev)
+    V_ = torch.randn((B * 1024, 32, 64), generator=g, device=dev)
+    profiled(lambda: ops.attention_contract(Q, K_, V_, 16, 4))
 print("done", sorted(groups))
