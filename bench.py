@@ -415,7 +415,7 @@ def run_config4(torch, np, args, pipes, rank, world, dev, sharding, with_cpu):
         (complete_scene_loader.chunk_scenes: the host round trips of scan i+1, i+2 overlap the device work of scan i);
         numpy's RNG is consumed in scan order, so the chunks are those of the sequential reference."""
         held, out = [], None
-        for i, (chunks, ev) in enumerate(csl.chunk_scenes((scans[k % S][1][0] for k in range(n_scans)), lookahead=2)):
+        for i, (chunks, ev) in enumerate(csl.chunk_scenes((scans[k % S][1][0] for k in range(n_scans)), lookahead=2, background=True)):
             cur.wait_event(ev)
             bp_, bl_, keep = consume(i, chunks)
             held.append(keep)

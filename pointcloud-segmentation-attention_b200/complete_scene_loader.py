@@ -269,13 +269,71 @@ class _PendingScan:
         return self.stage == 3
 
 
-def chunk_scenes(scans, npoints=NPOINTS, lookahead=2, stream=None):
+def chunk_scenes(scans, npoints=NPOINTS, lookahead=2, stream=None, background=False):
     """Chunk a SEQUENCE of scans (float32 CUDA tensors (N_i, 3)) with up to ``lookahead`` later scans in flight: the
     bounding-box and cell-membership passes of scans i+1, i+2 run (on ``stream``, default a stream of its own) while
     scan i is being planned on the host and consumed by the caller, so the three host round trips of a scan overlap
     with device work instead of idling the GPU.  Yields (SceneChunks, event): wait for the event on the consuming
     stream before using the tensors.  numpy's global RNG is consumed strictly in scan order (stage C runs only for
-    the oldest scan), so the chunks equal those of calling chunk_scene() scan after scan under the same seed."""
+    the oldest scan), so the chunks equal those of calling chunk_scene() scan after scan under the same seed.
+
+    background=True runs all of that on a worker thread that stays up to ``lookahead`` + 1 finished scans ahead of
+    the consumer: the host planning of a scan (numpy's shuffle of every cell, a few ms, GIL released) then overlaps
+    the consumer's own launches instead of alternating with them.  The worker owns numpy's global RNG and the
+    ``scans`` iterator until the generator is exhausted or closed: the consumer must not draw from np.random
+    meanwhile, and scans must be complete on the stream that is current when iteration starts."""
+    if not background:
+        yield from _chunk_scenes(scans, npoints, lookahead, stream, None)
+        return
+    import queue
+    import threading
+    q, stop = queue.Queue(maxsize=lookahead + 1), threading.Event()
+    caller_stream = _CurrentStreams().get             # current streams are thread-local: capture the consumer's here
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                pass
+        return False
+
+    def work():
+        try:
+            for item in _chunk_scenes(scans, npoints, lookahead, stream, caller_stream):
+                if not put(item):
+                    return
+            put(None)
+        except BaseException as e:                    # re-raised in the consumer
+            put(e)
+
+    t = threading.Thread(target=work, name="pcops-chunker", daemon=True)
+    t.start()
+    try:
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+        t.join()
+
+
+class _CurrentStreams:
+    """The CONSUMER thread's current stream per device, captured when chunk_scenes(background=True) starts."""
+
+    def __init__(self):
+        self._s = {torch.device("cuda", d): torch.cuda.current_stream(d) for d in range(torch.cuda.device_count())}
+
+    def get(self, dev):
+        return self._s[torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())]
+
+
+def _chunk_scenes(scans, npoints, lookahead, stream, caller_stream):
     from collections import deque
     it = iter(scans)
     pend = deque()
@@ -290,7 +348,8 @@ def chunk_scenes(scans, npoints=NPOINTS, lookahead=2, stream=None):
             raise TypeError("chunk_scenes expects float32 CUDA tensors of shape (N, 3)")
         if st is None:
             st = torch.cuda.Stream(device=pts.device)
-        st.wait_stream(torch.cuda.current_stream(pts.device))     # the scan may just have been produced there
+        # the scan may just have been produced on the consumer's stream
+        st.wait_stream(caller_stream(pts.device) if caller_stream else torch.cuda.current_stream(pts.device))
         with torch.cuda.device(pts.device):
             pend.append(_PendingScan(pts.contiguous(), npoints, st))
 

@@ -141,3 +141,36 @@ def test_chunker_has_no_cpu_path_and_rejects_bad_input():
     p = (rng.random((8192, 3)) * 1.4).astype(np.float32)
     with pytest.raises(ValueError):                       # the reference raises here too (:89-90)
         csl.chunk_scene(p)
+
+
+@pytest.mark.gpu
+def test_pipelined_chunker_equals_scan_after_scan():
+    """chunk_scenes() keeps later scans in flight but draws numpy's RNG in scan order: same chunks as chunk_scene()
+    called scan after scan under the same seed, and as the oracle."""
+    from oracle import synth
+    dev = torch.device("cuda")
+    scans = [synth.whole_scene(s)[0] for s in (3, 4, 5, 6, 7)]
+    d_scans = [torch.from_numpy(p).to(dev) for p in scans]
+    np.random.seed(77)
+    want = [csl.chunk_scene(p) for p in d_scans]
+    np.random.seed(77)
+    want_cpu = [oracle_sc.get_all_subsets_with_all_points_for_scene_numpy_test(p, p.astype(np.uint8), p) for p in scans[:2]]
+    for lookahead, background in ((0, False), (1, False), (2, True), (7, False), (0, True)):
+        np.random.seed(77)
+        got = []
+        for chunks, ev in csl.chunk_scenes(iter(d_scans), lookahead=lookahead, background=background):
+            torch.cuda.current_stream().wait_event(ev)
+            got.append(chunks)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            for name in ("point_sets", "src_index", "masks", "orig_idx"):
+                assert torch.equal(getattr(a, name), getattr(b, name)), (lookahead, name)
+    for a, w in zip(got, want_cpu):
+        assert np.array_equal(a.point_sets.cpu().numpy(), w[0])
+    assert list(csl.chunk_scenes([])) == []
+    for background in (False, True):                      # errors of the worker thread surface in the consumer
+        with pytest.raises(TypeError):
+            list(csl.chunk_scenes([np.zeros((10, 3), np.float32)], background=background))
+    gen = csl.chunk_scenes(iter(d_scans), lookahead=1, background=True)   # closing early stops the worker
+    next(gen)
+    gen.close()
