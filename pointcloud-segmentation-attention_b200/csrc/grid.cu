@@ -25,7 +25,16 @@ namespace pc {
 namespace {
 
 constexpr int kMaxCells = 16384;  // 64 KB shared-memory histogram in the build kernel
-constexpr int kBuildThreads = 1024;
+// 256 threads / <= 64 registers: small enough to sit beside a resident 512-thread FPS CTA (45 k of the SM's 64 k
+// registers).  With 1024-thread build CTAs the pipelined step lost 7 % (69.6 k -> 75.0 k scenes/s): they only fitted
+// on the few SMs no FPS CTA held and every binned op of every batch in flight queued for those.
+#ifndef PCOPS_BUILD_THREADS
+#define PCOPS_BUILD_THREADS 256
+#endif
+#ifndef PCOPS_BUILD_MINB
+#define PCOPS_BUILD_MINB 4
+#endif
+constexpr int kBuildThreads = PCOPS_BUILD_THREADS;
 constexpr int kHdrInts = 16;
 
 struct GridHdr {  // 16 x 4 bytes, first thing in a scene's workspace
@@ -66,10 +75,10 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float *s_red
 // CTA (s, 1) bins the QUERY cloud by the same cells (so that 32 consecutive sorted queries are spatial neighbours) --
 // it derives the grid header from the candidates itself (the same reduction over the same data gives the same bits;
 // one extra pass over 12 n bytes) instead of waiting for a second launch behind the first.
-__global__ void __launch_bounds__(kBuildThreads, 1)
-grid_build_kernel(int nc, int nq, float min_edge, int mode, const float *__restrict__ xyz_c,
+__global__ void __launch_bounds__(kBuildThreads, PCOPS_BUILD_MINB)
+grid_build_kernel(int nc, int nq, float min_edge, int mode, int max_cells, const float *__restrict__ xyz_c,
                   const float *__restrict__ xyz_q, int *__restrict__ ws_c, int *__restrict__ ws_q) {
-  extern __shared__ int s_cnt[];  // kMaxCells
+  extern __shared__ int s_cnt[];  // max_cells
   __shared__ float s_red[32];
   __shared__ GridHdr s_hdr;
   __shared__ int s_warp[32];
@@ -120,7 +129,7 @@ grid_build_kernel(int nc, int nq, float min_edge, int mode, const float *__restr
     int nx = 1, ny = 1, nz = 1;
     for (int it = 0; it < 1024; ++it) {  // coarsen until the grid fits the histogram (1.25^1024 > FLT_MAX: bounded)
       const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
-      if (fx * fy * fz <= (float)kMaxCells) { nx = (int)fx; ny = (int)fy; nz = (int)fz; break; }
+      if (fx * fy * fz <= (float)max_cells) { nx = (int)fx; ny = (int)fy; nz = (int)fz; break; }
       h *= 1.25f;
       if (!isfinite(h)) { h = 3.0e38f; break; }  // one cell
     }
@@ -155,7 +164,7 @@ grid_build_kernel(int nc, int nq, float min_edge, int mode, const float *__restr
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      const int w = s_warp[lane];
+      const int w = lane < kBuildThreads / 32 ? s_warp[lane] : 0;
       int iw = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -511,9 +520,14 @@ three_nn_tile_kernel(int n, int m, float one, const int *__restrict__ ws_c, cons
 
 int build_pair(int b, int nc, int nq, float min_edge, int mode, const float *xyz_c, const float *xyz_q, int *ws_c,
                int *ws_q, cudaStream_t st) {
-  const size_t smem = (size_t)kMaxCells * sizeof(int);
-  PC_CUDA_TRY(allow_smem(grid_build_kernel, smem));
-  grid_build_kernel<<<dim3(b, 2), kBuildThreads, smem, st>>>(nc, nq, min_edge, mode, xyz_c, xyz_q, ws_c, ws_q);
+  // The histogram (and with it the finest grid) is sized by the candidate count: two cells per candidate is finer than
+  // either op wants (the build coarsens the cell edge until the grid fits -- results do not depend on the edge), and a
+  // build CTA that reserves 8 KB instead of 64 KB finds room on an SM whose shared memory an FPS CTA half fills.
+  int max_cells = 2 * nc;
+  max_cells = max_cells < 1024 ? 1024 : max_cells > kMaxCells ? kMaxCells : max_cells;
+  const size_t smem = (size_t)max_cells * sizeof(int);
+  PC_CUDA_TRY(allow_smem(grid_build_kernel, (size_t)kMaxCells * sizeof(int)));
+  grid_build_kernel<<<dim3(b, 2), kBuildThreads, smem, st>>>(nc, nq, min_edge, mode, max_cells, xyz_c, xyz_q, ws_c, ws_q);
   PC_RETURN_LAUNCH_STATUS();
 }
 
