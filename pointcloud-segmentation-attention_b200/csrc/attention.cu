@@ -200,13 +200,37 @@ attention_fwd_kernel(size_t heads_total, int S, int H, const float *__restrict__
 // HBM peak -- an HBM stream that is nearly issue-bound, and that competes for issue slots with the FPS CTAs it shares
 // SMs with in the pipeline.  Here a warp owns 32 CONSECUTIVE heads = one contiguous 16 KB run of K and one of V (the
 // raw reshape, attention_layer.py:35, makes head gh the 128 floats at offset 128 gh).  Lane 0 issues one cp.async.bulk
-// per run into the warp's shared-memory ring (mbarrier complete_tx; three blocks ahead), and lane l then walks the
+// per run into the warp's shared-memory ring (mbarrier complete_tx), and lane l then walks the
 // 32 pseudo-keys of head l out of shared memory with 128-bit loads: logits and maximum in a first pass over K, exp and
 // the weighted sum in a second pass over V -- no shuffles, no reductions, ~16 warp instructions per KB.  Lane l visits
 // its samples in the rotated order (s + l) mod 32, which keeps every quarter-warp's eight 16-byte accesses in eight
 // different bank groups (the heads are 512 bytes apart).
-constexpr int kLhWarps = 2;                 // warps per CTA, each with its own ring: 2 x 48 KB = 96 KB, which still fits
-constexpr int kLhSlots = 3;                 // next to an FPS CTA (128 KB) on the same SM
+// Footprint, measured in the pipelined step (8 batches in flight, FPS CTAs resident on 128 SMs with 128 KB of shared
+// memory and 45 k registers each), scenes/s of the whole step:
+//   warps/CTA x ring slots x blocks/warp   2x3 persistent 75.5 k | 1x3x16 77.8 k | 1x4x16 76.0 k | 1x6x16 72.0 k
+//                                          1x2x16 80.1 k | 1x2x32 82.5 k | 1x2x64 83.6 k | 1x2x128 83.6 k | 1x2x256 78.8 k
+// The kernel is an HBM stream that shares every SM with other kernels: what pays is a SMALL shared-memory reservation
+// (32 KB CTAs find room beside an FPS CTA plus a tile-kernel CTA; 96 KB ones queued for the few free SMs) and FEW,
+// long-lived warps (one 16 KB bulk copy in flight per warp is enough once a hundred warps stream; more warps only take
+// issue slots and L2 bandwidth from the kernels in flight next to it).  A lone launch wants the opposite (SA1 alone:
+// 46 us with 592 warps x 3 slots, 58 us with 296 x 2, 86 us with 148 x 2); the default -- two single-warp CTAs per SM,
+// two slots, K / V copies marked evict-first in L2 (+1.5 k scenes/s: 500 MB read once no longer evict the gathers'
+// working sets) -- gives 82.3 k scenes/s in the step against 83.6 k for the narrowest variant.  The variants stay
+// selectable for A/B builds.
+#ifndef PCOPS_LH_EVICT_FIRST
+#define PCOPS_LH_EVICT_FIRST 1   // L2 evict-first policy on the K / V bulk copies
+#endif
+#ifndef PCOPS_LH_WARPS
+#define PCOPS_LH_WARPS 1
+#endif
+#ifndef PCOPS_LH_BPW
+#define PCOPS_LH_BPW -2    // consecutive 32-head blocks per warp; -t: equal shares over about t CTAs per SM
+#endif
+#ifndef PCOPS_LH_SLOTS
+#define PCOPS_LH_SLOTS 2   // ring slots per warp: K of block b in one, V in the other; the next K lands during the V pass
+#endif
+constexpr int kLhWarps = PCOPS_LH_WARPS;
+constexpr int kLhSlots = PCOPS_LH_SLOTS;
 constexpr int kLhSlotBytes = 32 * 128 * 4;  // one slot = the K (or V) run of 32 heads = 16 KB
 
 __device__ __forceinline__ void lh_wait(uint32_t bar, uint32_t parity) {
@@ -221,7 +245,7 @@ __device__ __forceinline__ void lh_wait(uint32_t bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(kLhWarps * 32)
-attention_fwd_lanehead_kernel(size_t heads_total, const float *__restrict__ Q, const float *__restrict__ K,
+attention_fwd_lanehead_kernel(size_t heads_total, int bpw, const float *__restrict__ Q, const float *__restrict__ K,
                               const float *__restrict__ V, float *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char lh_smem[];
   __shared__ __align__(8) uint64_t s_bar[kLhWarps][kLhSlots];
@@ -236,11 +260,16 @@ attention_fwd_lanehead_kernel(size_t heads_total, const float *__restrict__ Q, c
   }
   __syncwarp();
   const size_t nblocks = (heads_total + 31) / 32;
-  const size_t wstride = (size_t)gridDim.x * kLhWarps;
-  const size_t first = (size_t)blockIdx.x * kLhWarps + warp;
-  const int my_blocks = first < nblocks ? (int)((nblocks - 1 - first) / wstride) + 1 : 0;
-  const int nseq = 2 * my_blocks;   // the warp's copy sequence: K of block 0, V of block 0, K of block 1, ... ; slot = seq % 3
+  // a warp owns bpw CONSECUTIVE blocks
+  const size_t wstride = 1;
+  const size_t first = ((size_t)blockIdx.x * kLhWarps + warp) * (size_t)bpw;
+  const int my_blocks = first < nblocks ? (int)(nblocks - first < (size_t)bpw ? nblocks - first : (size_t)bpw) : 0;
+  const int nseq = 2 * my_blocks;   // the warp's copy sequence: K of block 0, V of block 0, K of block 1, ... ; slot = seq % kLhSlots
 
+#if PCOPS_LH_EVICT_FIRST
+  uint64_t policy;   // K and V are read exactly once: do not let 500 MB of them push the gathers' working sets out of L2
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+#endif
   auto issue = [&](int seq) {
     const size_t h0 = (first + (size_t)(seq >> 1) * wstride) * 32;
     const uint32_t nh = (uint32_t)((heads_total - h0 < 32) ? heads_total - h0 : 32);
@@ -248,10 +277,17 @@ attention_fwd_lanehead_kernel(size_t heads_total, const float *__restrict__ Q, c
     const int slot = seq % kLhSlots;
     const float *src = ((seq & 1) ? V : K) + h0 * 128;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + 8 * slot), "r"(bytes) : "memory");
+#if PCOPS_LH_EVICT_FIRST
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     ring_s + slot * kLhSlotBytes),
+                 "l"(src), "r"(bytes), "r"(bar_s + 8 * slot), "l"(policy)
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      ring_s + slot * kLhSlotBytes),
                  "l"(src), "r"(bytes), "r"(bar_s + 8 * slot)
                  : "memory");
+#endif
   };
   if (lane == 0)
     for (int seq = 0; seq < kLhSlots && seq < nseq; ++seq) issue(seq);
@@ -275,7 +311,7 @@ attention_fwd_lanehead_kernel(size_t heads_total, const float *__restrict__ Q, c
         mx = fmaxf(mx, lg);
       }
     }
-    __syncwarp();   // every lane is done with the K slot: refill it with the copy three steps ahead
+    __syncwarp();   // every lane is done with the K slot: refill it with the copy kLhSlots steps ahead
     if (lane == 0 && seq_k + kLhSlots < nseq) issue(seq_k + kLhSlots);
     float sum = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
     lh_wait(bar_s + 8 * (seq_v % kLhSlots), (uint32_t)((seq_v / kLhSlots) & 1));
@@ -299,10 +335,14 @@ int launch_fwd_lanehead(size_t heads, const float *Q, const float *K, const floa
   const size_t smem = (size_t)kLhWarps * kLhSlots * kLhSlotBytes;
   PC_CUDA_TRY(allow_smem(attention_fwd_lanehead_kernel, smem));
   const size_t nblocks = (heads + 31) / 32;
-  size_t grid = (nblocks + kLhWarps - 1) / kLhWarps;
-  const size_t cap = (size_t)num_sms() * 2;   // two 96 KB CTAs fit an SM that holds no FPS CTA, one fits next to it
-  if (grid > cap) grid = cap;
-  attention_fwd_lanehead_kernel<<<(unsigned)grid, kLhWarps * 32, smem, st>>>(heads, Q, K, V, out);
+  long bpw = PCOPS_LH_BPW;
+  if (bpw <= 0) {   // -t: about t CTAs per SM (0: as many as fit), equal contiguous shares of at most 64 blocks
+    const size_t ctas = (size_t)num_sms() * (bpw < 0 ? (size_t)-bpw : (size_t)(4 / kLhWarps));
+    bpw = (long)((nblocks + ctas * kLhWarps - 1) / (ctas * kLhWarps));
+    bpw = bpw > 64 ? 64 : bpw < 1 ? 1 : bpw;
+  }
+  const size_t grid = (nblocks + bpw * kLhWarps - 1) / (bpw * kLhWarps);
+  attention_fwd_lanehead_kernel<<<(unsigned)grid, kLhWarps * 32, smem, st>>>(heads, (int)bpw, Q, K, V, out);
   PC_RETURN_LAUNCH_STATUS();
 }
 
