@@ -40,12 +40,14 @@ class ScanNetGeometry:
         self.B, self.N, self.CF = batch, npoints, feat_channels
         # diagnostics only: which parts of the forward to enqueue ("fps": the FPS chain, "side": everything else)
         self.parts = tuple(parts)
+        self.skip = ()   # diagnostics only (scripts/ablate.py): op-name prefixes left out of the forward
         self.fuse_gather = fuse_gather  # pc_fps_gather instead of pc_fps + pc_gather_point
         # pc_sa_group (group xyz + centre + group features + concat) and pc_fp_interpolate (weights + interpolate)
         # instead of two GroupPoint calls / weights + ThreeInterpolate: what sample_and_group / pointnet_fp_module need.
         # Off by default here: it produces MORE than the reference-signature ops the benchmark counts (the concatenated
         # tensor on top of grouped_xyz); the wrappers in pointnet_util.py use it, where it replaces 4-5 launches.
         self.fuse_layers = fuse_layers
+        self.fuse_fp = fuse_layers       # pc_fp_interpolate instead of three_weights + three_interpolate
         self.grid = grid  # cell-grid ball query / three_nn (same outputs as the all-pairs kernels, far fewer pair tests)
         self.dev = torch.device(device)
         self.attention = attention
@@ -280,7 +282,7 @@ class ScanNetGeometry:
         else:
             run("three_nn_" + tag, side, lambda: L.pc_three_nn(
                 B, n, m, p(fp["xyz1"]), p(fp["xyz2"]), p(fp["dist"]), p(fp["idx"]), st))
-        if self.fuse_layers:
+        if self.fuse_fp:
             run("fp_interpolate_" + tag, side, lambda: L.pc_fp_interpolate(
                 B, n, m, c, 0, p(fp["dist"]), p(fp["idx"]), p(fp["points2"]), None, p(fp["out"]), p(fp["w"]), st))
         else:
@@ -300,6 +302,8 @@ class ScanNetGeometry:
         fp_of = {fp["level"]: fp for fp in self.fps}
 
         def run(name, stream, call):
+            if self.skip and name.startswith(self.skip):
+                return
             if probes is not None and name in probes:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
