@@ -203,7 +203,7 @@ interp_vec4_kernel(I total_vec, RowDecode<I> dec /* a = c4, b = n */, int m, con
 }
 
 
-// c % 128 == 0 (every FP level of the ScanNet models: 128 / 256 / 512 channels): a warp owns 32 consecutive rows, lane r
+// c % 128 == 0 (every FP level of the ScanNet models: 128 / 256 / 512 channels): a warp owns rpw (<= 32) consecutive rows, lane r
 // fetches (idx, weight) of row r ONCE, the warp then walks the rows two at a time -- (i, w) broadcast by shuffle, a lane
 // covers the float4 columns lane, lane + 32, ... -- with six independent 128-bit row loads in flight per lane.  The
 // thread-per-float4 kernel above re-reads the six (idx, weight) words and re-decodes the row for every float4: 45 warp
@@ -212,18 +212,18 @@ interp_vec4_kernel(I total_vec, RowDecode<I> dec /* a = c4, b = n */, int m, con
 #define PCOPS_INTERP_ROWS 1
 #endif
 __global__ void __launch_bounds__(256)
-interp_rows_kernel(size_t rows, int n, int m, int c4, const float4 *__restrict__ points, const int *__restrict__ idx,
+interp_rows_kernel(size_t rows, int rpw, int n, int m, int c4, const float4 *__restrict__ points, const int *__restrict__ idx,
                    const float *__restrict__ weight, float4 *__restrict__ out) {
   const int lane = threadIdx.x & 31;
   const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t r0 = warp_global * 32; r0 < rows; r0 += nwarps * 32) {
-    const size_t my = min(r0 + lane, rows - 1);
+  for (size_t r0 = warp_global * rpw; r0 < rows; r0 += nwarps * rpw) {
+    const size_t my = min(r0 + (lane & (rpw - 1)), rows - 1);   // rpw is a power of two: lanes >= rpw mirror the first ones
     const int i1 = __ldg(idx + my * 3 + 0), i2 = __ldg(idx + my * 3 + 1), i3 = __ldg(idx + my * 3 + 2);
     const float w1 = __ldg(weight + my * 3 + 0), w2 = __ldg(weight + my * 3 + 1), w3 = __ldg(weight + my * 3 + 2);
     const float4 *base = points + (my / n) * (size_t)m * c4;   // scene of this lane's row
     const float4 *p1 = base + (size_t)i1 * c4, *p2 = base + (size_t)i2 * c4, *p3 = base + (size_t)i3 * c4;
-    const int nr = (int)min((size_t)32, rows - r0);
+    const int nr = (int)min((size_t)rpw, rows - r0);
     for (int rr = 0; rr < nr; rr += 2) {
       const int rb = min(rr + 1, nr - 1);
       const float4 *a1 = (const float4 *)__shfl_sync(PC_FULL_MASK, (unsigned long long)p1, rr),
@@ -269,12 +269,13 @@ template <class I>
 void launch_interp(size_t total, int c, int n, int m, const float *points, const int *idx, const float *weight,
                    float *out, cudaStream_t st) {
   const size_t rows = c > 0 ? total / (size_t)c : 0;
-  if (PCOPS_INTERP_ROWS && c % 128 == 0 && c > 0 && aligned16(points) && aligned16(out) &&
-      (rows + 31) / 32 >= (size_t)num_sms() * 4) {   // enough 32-row groups to give every SM four warps
-    size_t blocks = ((rows + 31) / 32 + 7) / 8;
+  int rpw = 32;   // rows per warp: fewer when 32-row groups would leave the SMs short of warps (16 per SM wanted)
+  while (rpw > 4 && (rows + rpw - 1) / rpw < (size_t)num_sms() * 48) rpw >>= 1;
+  if (PCOPS_INTERP_ROWS && c % 128 == 0 && c > 0 && aligned16(points) && aligned16(out) && rpw >= 8) {   // small launches: thread-per-float4 kernel
+    size_t blocks = ((rows + rpw - 1) / rpw + 7) / 8;
     const size_t cap = (size_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    interp_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, n, m, c / 4, (const float4 *)points, idx, weight, (float4 *)out);
+    interp_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, rpw, n, m, c / 4, (const float4 *)points, idx, weight, (float4 *)out);
   } else if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
     const size_t nv = total / 4;
     const int blocks = resident_grid((const void *)interp_vec4_kernel<I>, 256, 0, (nv + 256 * kInterpUnroll - 1) / (256 * kInterpUnroll));
