@@ -44,6 +44,16 @@ constexpr int kABlock = kRows * 128;       // 16 KB: A K-block (hi or lo)
 constexpr int kBBlock = kMaxNc * 128;      // 32 KB: B K-block (hi or lo) at full width
 constexpr int kStage = 2 * kABlock + 2 * kBBlock;   // 96 KB: A_hi | A_lo | B_hi | B_lo
 constexpr int kThreads = 288;
+#ifndef PCOPS_DENSE_PWARPS
+#define PCOPS_DENSE_PWARPS 8
+#endif
+#ifndef PCOPS_DENSE_AHEAD
+#define PCOPS_DENSE_AHEAD 2
+#endif
+constexpr int kFwdPW = PCOPS_DENSE_PWARPS;          // producer warps of the forward kernel (4 or 8)
+constexpr int kFwdAhead = PCOPS_DENSE_AHEAD;        // K blocks a producer thread holds in registers ahead of the ring
+constexpr int kFwdThreads = (kFwdPW + 5) * 32;      // producers, four epilogue warps, the MMA issuer
+constexpr int kF4 = 1024 / (kFwdPW * 32);           // float4s of a 128 x 32 block per producer thread
 constexpr int kMaxN = 1024;                // bias staged in shared memory
 constexpr int kPatch = 32 * 36;            // floats per epilogue warp: 32 rows x 32 columns, rows padded to 36
 constexpr int kFixedBytes = 24 * 1024;     // bias, patches, barriers of the forward kernel in front of its operand ring
@@ -107,13 +117,26 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                          \
       : "r"(addr))
 
+#ifndef PCOPS_DENSE_WAIT
+#define PCOPS_DENSE_WAIT 0   // 0: bare try_wait loop; 1: try_wait with a suspend-time hint; 2: nanosleep back-off
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0, spins = 0;
   do {
+#if PCOPS_DENSE_WAIT == 1
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity), "r"(20000u)
+                 : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
                  : "r"(bar), "r"(parity)
                  : "memory");
+#endif
+#if PCOPS_DENSE_WAIT == 2
+    if (!ok) __nanosleep(64);
+#endif
     if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost arrival
   } while (!ok);
 }
@@ -121,7 +144,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // kPool: 0 = store Y (rows, N) to out; 1 = store the maximum over each group of 32 rows, (rows / 32, N), to pooled;
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int nst, int nacc, size_t ldo, size_t ldp, int relu, int vec_x,
                   int vec_o, const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
                   float *__restrict__ out, float *__restrict__ pooled) {
@@ -144,7 +167,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   // per ~2 us whatever the item's size
   const uint32_t t_full0 = bar0 + 64, t_empty0 = bar0 + 128;                // t_full[a] = t_full0 + 8 a, ...
 
-  if (warp == 8) {  // the whole TMEM: two 256-column fp32 accumulators
+  if (warp == kFwdPW + 4) {  // the whole TMEM
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(s_tmem)),
                  "r"(512u));
@@ -152,7 +175,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   }
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(128u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"((uint32_t)(kFwdPW * 32)));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(1u));
     }
     for (int s = 0; s < 8; ++s) {
@@ -161,7 +184,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  for (int i = tid; i < N; i += kThreads) s_bias[i] = bias ? __ldg(bias + i) : 0.f;
+  for (int i = tid; i < N; i += kFwdThreads) s_bias[i] = bias ? __ldg(bias + i) : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -174,17 +197,23 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   const int nitems = ntiles * nchunk;                 // item = tile * nchunk + u: a tile's units run on neighbouring CTAs
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage_buf);
 
-  if (warp < 4) {
+  if (warp < kFwdPW) {
     // ---------------------------------------------------------------- producers
     const int my_items = blockIdx.x < nitems ? (nitems - 1 - blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int n_it = my_items * nkb;
-    auto fetch = [&](float4 (&buf)[8], int it_) {   // thread t takes float4 t + 128 i -> row (i4 >> 3), quad i4 & 7
+    auto fetch = [&](float4 (&buf)[kF4], int it_) {   // thread t takes float4 t + kFwdPW * 32 * i -> row (i4 >> 3), quad i4 & 7
       const int w = it_ / nkb, kb = it_ - w * nkb;
       const int tile = (blockIdx.x + w * (int)gridDim.x) / nchunk;
       const size_t row0 = (size_t)tile * kRows;
+      if (it_ < n_it && vec_x && row0 + kRows <= rows && kb * kKB + kKB <= K) {   // whole block in range: no per-element tests
+        const float4 *src = reinterpret_cast<const float4 *>(x + (row0 + (tid >> 3)) * ldx + kb * kKB) + (tid & 7);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+        for (int i = 0; i < kF4; ++i) buf[i] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(src) + (size_t)(kFwdPW * 4 * i) * ldx));
+        return;
+      }
+#pragma unroll
+      for (int i = 0; i < kF4; ++i) {
+        const int i4 = tid + kFwdPW * 32 * i, row = i4 >> 3, kq = i4 & 7;
         const int k0 = kb * kKB + kq * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (it_ < n_it && row0 + row < rows && k0 < K) {
@@ -201,7 +230,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
         buf[i] = v;
       }
     };
-    auto produce = [&](const float4 (&buf)[8], int it_) {
+    auto produce = [&](const float4 (&buf)[kF4], int it_) {
       const int w = it_ / nkb, kb = it_ - w * nkb;
       const int col0 = ((blockIdx.x + w * (int)gridDim.x) % nchunk) * sw;
       const int nc = min(sw, N - col0);
@@ -221,8 +250,8 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
                      : "memory");
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int i4 = tid + 128 * i, row = i4 >> 3, kq = i4 & 7;
+      for (int i = 0; i < kF4; ++i) {
+        const int i4 = tid + kFwdPW * 32 * i, row = i4 >> 3, kq = i4 & 7;
         const float4 v = buf[i];
         float4 h, l;
         h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -234,21 +263,22 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * s) : "memory");
     };
-    // Two K blocks ahead.  (Four blocks ahead -- 64 KB of loads in flight per SM -- was measured and made every layer
-    // SLOWER, 62 -> 92 us at SA1, 55 -> 87 us at FP4, with plain and with volatile loads: the per-block cost of these
-    // layers is not the global-load latency.)
-    float4 bufA[8], bufB[8];
-    fetch(bufA, 0);
-    fetch(bufB, 1);
-    for (int it = 0; it < n_it; it += 2) {
-      produce(bufA, it);
-      fetch(bufA, it + 2);
-      if (it + 1 < n_it) {
-        produce(bufB, it + 1);
-        fetch(bufB, it + 3);
+    // kFwdAhead K blocks ahead, in registers: kFwdPW * 32 threads x kFwdAhead x kF4 float4 = the bytes in flight per SM
+    // (32 KB with 4 warps x 2 x 8; 64 KB with 8 warps x 4 x 4).  The loop is unrolled over the buffers so that every
+    // buffer index is a compile-time constant (a dynamically indexed buffer array lives in local memory).
+    float4 buf[kFwdAhead][kF4];
+#pragma unroll
+    for (int u = 0; u < kFwdAhead; ++u) fetch(buf[u], u);
+    for (int it = 0; it < n_it; it += kFwdAhead) {
+#pragma unroll
+      for (int u = 0; u < kFwdAhead; ++u) {
+        if (it + u < n_it) {
+          produce(buf[u], it + u);
+          fetch(buf[u], it + u + kFwdAhead);
+        }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kFwdPW + 4) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       int it = 0, w = 0;
@@ -279,7 +309,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue (warps 4-7: TMEM lane quarters 0-3)
+    // ---------------------------------------------------------------- epilogue (four warps: TMEM lane quarters warp & 3)
     const int qtr = warp & 3;
     float *patch = s_patch + qtr * kPatch;
     int w = 0;
@@ -296,10 +326,12 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const float *cb = s_bias + col0 + c0;
         float y[32];
+        if (relu) {   // one uniform branch instead of a predicate per element (NaN handling as before: fmaxf(NaN, 0) = 0)
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          y[t] = __uint_as_float(v[t]) + cb[t];
-          if (relu) y[t] = fmaxf(y[t], 0.f);
+          for (int t = 0; t < 32; ++t) y[t] = fmaxf(__uint_as_float(v[t]) + cb[t], 0.f);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) y[t] = __uint_as_float(v[t]) + cb[t];
         }
         if (kPool) {
           // the warp's 32 lanes are the 32 samples of neighbourhood row0 / 32: maximum per column, lane t keeps column t
@@ -330,6 +362,13 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
             *reinterpret_cast<float4 *>(patch + lane * 36 + 4 * t) = make_float4(y[4 * t], y[4 * t + 1], y[4 * t + 2], y[4 * t + 3]);
           __syncwarp();
           const int rr = lane >> 3, cq = (lane & 7) * 4;
+          if (vec_o && row0 + 32 <= rows && c0 + 32 <= nc) {   // whole 32 x 32 patch in range
+            float *dst = out + (row0 + rr) * ldo + (size_t)col0 + c0 + cq;
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+              *reinterpret_cast<float4 *>(dst + (size_t)(4 * t) * ldo) = *reinterpret_cast<const float4 *>(patch + (4 * t + rr) * 36 + cq);
+            continue;
+          }
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int r = 4 * t + rr;
@@ -354,7 +393,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kFwdPW + 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
   }
 }
@@ -676,13 +715,13 @@ int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, si
   const int vec_o = (ldo % 4 == 0) && aligned16(out);
   if (pool == 1) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
-    dense_tf32_kernel<1><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<1><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else if (pool == 2) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
-    dense_tf32_kernel<2><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<2><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
-    dense_tf32_kernel<0><<<grid, kThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<0><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   }
   PC_RETURN_LAUNCH_STATUS();
 }

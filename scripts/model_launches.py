@@ -12,6 +12,9 @@ from pcops_b200 import synth  # noqa: E402
 from pcops_b200.model_pipeline import ScanNetAttentionModel  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+if len(sys.argv) > 2:      # A/B runs: path of an alternative libpcops build
+    from pcops_b200 import _lib
+    _lib.LIB_PATH = os.path.abspath(sys.argv[2])
 x, f = synth.scannet_batch(0, B, 8192)
 m = ScanNetAttentionModel(B, 8192, 6)
 m.set_inputs(torch.from_numpy(x), torch.from_numpy(f))
