@@ -44,6 +44,12 @@ constexpr int kABlock = kRows * 128;       // 16 KB: A K-block (hi or lo)
 constexpr int kBBlock = kMaxNc * 128;      // 32 KB: B K-block (hi or lo) at full width
 constexpr int kStage = 2 * kABlock + 2 * kBBlock;   // 96 KB: A_hi | A_lo | B_hi | B_lo
 constexpr int kThreads = 288;
+#ifndef PCOPS_DENSE_STUB
+#define PCOPS_DENSE_STUB 0   // timing experiments only: 1 no TF32 split, 2 no output stores, 3 no input loads
+#endif
+#ifndef PCOPS_DENSE_WARP_ARRIVE
+#define PCOPS_DENSE_WARP_ARRIVE 1   // 1: one mbarrier arrival per warp (after __syncwarp) instead of one per thread
+#endif
 #ifndef PCOPS_DENSE_PWARPS
 #define PCOPS_DENSE_PWARPS 8
 #endif
@@ -141,6 +147,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
+// Position of a warp role in the CTA's item sequence (item = blockIdx.x + w * gridDim.x = tile * nchunk + chunk) and in
+// the K blocks of the item, advanced by additions only: the roles used to recompute (w, kb, tile, chunk, stage, phase)
+// from a flat counter with six runtime integer divisions per block -- ~0.6 us of dependent latency per 128-row tile on
+// the single-thread MMA issuer and every producer thread, more than the MMAs themselves (stub measurements).
+struct ItemCursor {
+  int tile, chunk, kb;
+  __device__ __forceinline__ void next_block(int nkb, int dt, int dc, int nchunk) {
+    if (++kb == nkb) {
+      kb = 0;
+      tile += dt;
+      chunk += dc;
+      if (chunk >= nchunk) { chunk -= nchunk; ++tile; }
+    }
+  }
+  __device__ __forceinline__ void next_item(int dt, int dc, int nchunk) {
+    tile += dt;
+    chunk += dc;
+    if (chunk >= nchunk) { chunk -= nchunk; ++tile; }
+  }
+};
+struct RingCursor {   // slot index and mbarrier phase of a ring of n slots
+  int s;
+  uint32_t ph;
+  __device__ __forceinline__ void next(int n) {
+    if (++s == n) { s = 0; ph ^= 1u; }
+  }
+};
+
 // kPool: 0 = store Y (rows, N) to out; 1 = store the maximum over each group of 32 rows, (rows / 32, N), to pooled;
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
@@ -175,12 +209,12 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   }
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"((uint32_t)(kFwdPW * 32)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"((uint32_t)(PCOPS_DENSE_WARP_ARRIVE ? kFwdPW : kFwdPW * 32)));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(1u));
     }
     for (int s = 0; s < 8; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_full0 + 8 * s), "r"(1u));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty0 + 8 * s), "r"(128u));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_empty0 + 8 * s), "r"(PCOPS_DENSE_WARP_ARRIVE ? 4u : 128u));
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -194,18 +228,29 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   // (few rows): then 128 / 64 / 32, a contiguous slice of the 256-column image slot (8-row groups are 1 KB apart)
   const int nkb = (K + kKB - 1) / kKB, nchunk = (N + sw - 1) / sw;
   const int ntiles = (int)((rows + kRows - 1) / kRows);
-  const int nitems = ntiles * nchunk;                 // item = tile * nchunk + u: a tile's units run on neighbouring CTAs
+  // item = tile * nchunk + u: a tile's units run on neighbouring CTAs
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage_buf);
+  const int dt = (int)gridDim.x / nchunk, dc = (int)gridDim.x - dt * nchunk;     // item += gridDim.x in (tile, chunk) steps
+  const int tile0 = (int)blockIdx.x / nchunk, chunk0 = (int)blockIdx.x - tile0 * nchunk;
 
   if (warp < kFwdPW) {
     // ---------------------------------------------------------------- producers
-    const int my_items = blockIdx.x < nitems ? (nitems - 1 - blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int n_it = my_items * nkb;
-    auto fetch = [&](float4 (&buf)[kF4], int it_) {   // thread t takes float4 t + kFwdPW * 32 * i -> row (i4 >> 3), quad i4 & 7
-      const int w = it_ / nkb, kb = it_ - w * nkb;
-      const int tile = (blockIdx.x + w * (int)gridDim.x) / nchunk;
-      const size_t row0 = (size_t)tile * kRows;
-      if (it_ < n_it && vec_x && row0 + kRows <= rows && kb * kKB + kKB <= K) {   // whole block in range: no per-element tests
+    // two cursors: the loads run kFwdAhead blocks ahead of the conversion into the ring
+    ItemCursor fc{tile0, chunk0, 0}, pc_{tile0, chunk0, 0};
+    RingCursor ring{0, 1u};                          // producers wait for "empty": parity starts flipped
+    auto fetch = [&](float4 (&buf)[kF4]) {   // thread t takes float4 t + kFwdPW * 32 * i -> row (i4 >> 3), quad i4 & 7
+      const int kb = fc.kb;
+      const bool in_range = fc.tile < ntiles;
+      const size_t row0 = (size_t)fc.tile * kRows;
+      fc.next_block(nkb, dt, dc, nchunk);
+#if PCOPS_DENSE_STUB == 3 || PCOPS_DENSE_STUB == 7 || PCOPS_DENSE_STUB >= 8
+      if (true) {
+#pragma unroll
+        for (int i = 0; i < kF4; ++i) buf[i] = make_float4(1.f, 2.f, 3.f, (float)kb);
+        return;
+      }
+#endif
+      if (in_range && vec_x && row0 + kRows <= rows && kb * kKB + kKB <= K) {   // whole block in range: no per-element tests
         const float4 *src = reinterpret_cast<const float4 *>(x + (row0 + (tid >> 3)) * ldx + kb * kKB) + (tid & 7);
 #pragma unroll
         for (int i = 0; i < kF4; ++i) buf[i] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(src) + (size_t)(kFwdPW * 4 * i) * ldx));
@@ -216,7 +261,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
         const int i4 = tid + kFwdPW * 32 * i, row = i4 >> 3, kq = i4 & 7;
         const int k0 = kb * kKB + kq * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (it_ < n_it && row0 + row < rows && k0 < K) {
+        if (in_range && row0 + row < rows && k0 < K) {
           const float *src = x + (row0 + row) * ldx + k0;
           if (vec_x && k0 + 3 < K) {
             v = __ldg(reinterpret_cast<const float4 *>(src));
@@ -230,14 +275,16 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
         buf[i] = v;
       }
     };
-    auto produce = [&](const float4 (&buf)[kF4], int it_) {
-      const int w = it_ / nkb, kb = it_ - w * nkb;
-      const int col0 = ((blockIdx.x + w * (int)gridDim.x) % nchunk) * sw;
+    auto produce = [&](const float4 (&buf)[kF4]) {
+      const int kb = pc_.kb;
+      const int col0 = pc_.chunk * sw;
       const int nc = min(sw, N - col0);
-      const int s = it_ % nst;
-      mbar_wait(empty0 + 8 * s, ((it_ / nst) & 1) ^ 1);   // the MMAs that read this stage nst blocks ago have completed
+      const int s = ring.s;
+      mbar_wait(empty0 + 8 * s, ring.ph);   // the MMAs that read this stage nst blocks ago have completed
+      pc_.next_block(nkb, dt, dc, nchunk);
+      ring.next(nst);
       unsigned char *st = stage_buf + s * stage_bytes;
-      if (tid == 0) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
+      if (tid == 0 && PCOPS_DENSE_STUB < 10) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
         const unsigned char *src = image + ((size_t)(col0 / kMaxNc) * nkb + kb) * (2 * kBBlock) + (size_t)(col0 % kMaxNc) * 128;
         const uint32_t dst = stage_s + s * stage_bytes + 2 * kABlock;
         const uint32_t bytes = (uint32_t)((nc + 15) & ~15) * 128u;   // the MMA's N is a multiple of 16: zero rows beyond nc
@@ -249,18 +296,30 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
                      "l"(src + kBBlock), "r"(bytes), "r"(full0 + 8 * s)
                      : "memory");
       }
+#if PCOPS_DENSE_STUB == 7 || PCOPS_DENSE_STUB >= 8
+      for (int i = 0; i < 0; ++i) {
+#else
 #pragma unroll
       for (int i = 0; i < kF4; ++i) {
+#endif
         const int i4 = tid + kFwdPW * 32 * i, row = i4 >> 3, kq = i4 & 7;
         const float4 v = buf[i];
         float4 h, l;
+#if PCOPS_DENSE_STUB == 1
+        h = v; l = v;
+#else
         h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
         l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+#endif
         const int off = block_offset(row, kq * 4);
         *reinterpret_cast<float4 *>(st + off) = h;
         *reinterpret_cast<float4 *>(st + kABlock + off) = l;
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's stores, visible to the tensor core's proxy
+#if PCOPS_DENSE_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0)
+#endif
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * s) : "memory");
     };
     // kFwdAhead K blocks ahead, in registers: kFwdPW * 32 threads x kFwdAhead x kF4 float4 = the bytes in flight per SM
@@ -268,38 +327,50 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
     // buffer index is a compile-time constant (a dynamically indexed buffer array lives in local memory).
     float4 buf[kFwdAhead][kF4];
 #pragma unroll
-    for (int u = 0; u < kFwdAhead; ++u) fetch(buf[u], u);
-    for (int it = 0; it < n_it; it += kFwdAhead) {
+    for (int u = 0; u < kFwdAhead; ++u) fetch(buf[u]);
+    while (pc_.tile < ntiles) {
 #pragma unroll
       for (int u = 0; u < kFwdAhead; ++u) {
-        if (it + u < n_it) {
-          produce(buf[u], it + u);
-          fetch(buf[u], it + u + kFwdAhead);
+        if (pc_.tile < ntiles) {
+          produce(buf[u]);
+          fetch(buf[u]);
         }
       }
     }
   } else if (warp == kFwdPW + 4) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      int it = 0, w = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
-        const int a = w % nacc;
-        const int nc = min(sw, N - (item % nchunk) * sw);
+      ItemCursor c{tile0, chunk0, 0};
+      RingCursor ring{0, 0u}, accr{0, 1u};             // waits for "full" stages; waits for "empty" accumulators
+      for (; c.tile < ntiles; c.next_item(dt, dc, nchunk)) {
+        const int a = accr.s;
+        const int nc = min(sw, N - c.chunk * sw);
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc rounded up to 16, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-        mbar_wait(t_empty0 + 8 * a, ((w / nacc) & 1) ^ 1);      // the epilogue has drained this accumulator
+        mbar_wait(t_empty0 + 8 * a, accr.ph);      // the epilogue has drained this accumulator
+        accr.next(nacc);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t acc = 0;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % nst;
-          mbar_wait(full0 + 8 * s, (it / nst) & 1);
+        const uint32_t d_tmem = tmem + a * sw;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = ring.s;
+          mbar_wait(full0 + 8 * s, ring.ph);
+          ring.next(nst);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = stage_s + s * stage_bytes, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + b_half;
+          // descriptors of the four operand parts; a K step of 8 (32 bytes) is +2 in the 16-byte address field
+          const uint64_t d_ah = smem_desc(a_hi), d_al = smem_desc(a_lo), d_bh = smem_desc(b_hi), d_bl = smem_desc(b_lo);
+#if PCOPS_DENSE_STUB == 4
+          for (int split = 0; split < 1; ++split) {
+#elif PCOPS_DENSE_STUB == 5 || PCOPS_DENSE_STUB == 9 || PCOPS_DENSE_STUB == 11
+          for (int split = 0; split < 0; ++split) {
+#else
           for (int split = 0; split < nsplit; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi [, X_lo W_lo: fp32-grade]
-            const uint32_t as = (split >= 2) ? a_lo : a_hi, bs = (split & 1) ? b_lo : b_hi;
+#endif
+            const uint64_t da = (split >= 2) ? d_al : d_ah, db = (split & 1) ? d_bl : d_bh;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              mma_tf32(tmem + a * sw, smem_desc(as + kk * 32), smem_desc(bs + kk * 32), idesc, acc);
+              mma_tf32(d_tmem, da + 2u * kk, db + 2u * kk, idesc, acc);
               acc = 1;
             }
           }
@@ -312,15 +383,21 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
     // ---------------------------------------------------------------- epilogue (four warps: TMEM lane quarters warp & 3)
     const int qtr = warp & 3;
     float *patch = s_patch + qtr * kPatch;
-    int w = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++w) {
-      const int a = w % nacc, tile = item / nchunk, col0 = (item - tile * nchunk) * sw;
+    ItemCursor c{tile0, chunk0, 0};
+    RingCursor accr{0, 0u};
+    for (; c.tile < ntiles; c.next_item(dt, dc, nchunk)) {
+      const int a = accr.s, col0 = c.chunk * sw;
       const int nc = min(sw, N - col0);
-      const size_t row0 = (size_t)tile * kRows + qtr * 32;    // this warp's 32 rows
-      mbar_wait(t_full0 + 8 * a, (w / nacc) & 1);
+      const size_t row0 = (size_t)c.tile * kRows + qtr * 32;    // this warp's 32 rows
+      mbar_wait(t_full0 + 8 * a, accr.ph);
+      accr.next(nacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * sw;
+#if PCOPS_DENSE_STUB == 6 || PCOPS_DENSE_STUB >= 8
+      for (int c0 = 0; c0 < 0; c0 += 32) {
+#else
       for (int c0 = 0; c0 < nc; c0 += 32) {
+#endif
         uint32_t v[32];
         PCG_TMEM_LD32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -362,6 +439,9 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
             *reinterpret_cast<float4 *>(patch + lane * 36 + 4 * t) = make_float4(y[4 * t], y[4 * t + 1], y[4 * t + 2], y[4 * t + 3]);
           __syncwarp();
           const int rr = lane >> 3, cq = (lane & 7) * 4;
+#if PCOPS_DENSE_STUB == 2
+          if (y[0] != 12345.678f) continue;
+#endif
           if (vec_o && row0 + 32 <= rows && c0 + 32 <= nc) {   // whole 32 x 32 patch in range
             float *dst = out + (row0 + rr) * ldo + (size_t)col0 + c0 + cq;
 #pragma unroll
@@ -388,6 +468,10 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the accumulator is handed back
+#if PCOPS_DENSE_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0)
+#endif
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(t_empty0 + 8 * a) : "memory");
     }
   }
