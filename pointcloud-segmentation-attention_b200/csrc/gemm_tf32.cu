@@ -50,6 +50,9 @@ constexpr int kThreads = 288;
 #ifndef PCOPS_DENSE_WARP_ARRIVE
 #define PCOPS_DENSE_WARP_ARRIVE 1   // 1: one mbarrier arrival per warp (after __syncwarp) instead of one per thread
 #endif
+#ifndef PCOPS_DENSE_PAIR
+#define PCOPS_DENSE_PAIR 1
+#endif
 #ifndef PCOPS_DENSE_PWARPS
 #define PCOPS_DENSE_PWARPS 8
 #endif
@@ -179,7 +182,7 @@ struct RingCursor {   // slot index and mbarrier phase of a ring of n slots
 // 2 = both (the attention-and-pooling module needs the activations for the attention layer and their maximum).
 template <int kPool>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int nst, int nacc, size_t ldo, size_t ldp, int relu, int vec_x,
+dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int nst, int nacc, int pair, size_t ldo, size_t ldp, int relu, int vec_x,
                   int vec_o, const float *__restrict__ x, const unsigned char *__restrict__ image, const float *__restrict__ bias,
                   float *__restrict__ out, float *__restrict__ pooled) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -192,6 +195,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 24);
   unsigned char *stage_buf = smem + kFixedBytes;
   const int b_half = sw * 128, stage_bytes = 2 * kABlock + 2 * b_half;
+  const int aw = pair ? 2 * sw : sw;                                        // TMEM columns of one accumulator
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
@@ -346,12 +350,14 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
         const int a = accr.s;
         const int nc = min(sw, N - c.chunk * sw);
         // instruction descriptor: D = F32, A = B = TF32, both K-major, N = nc rounded up to 16, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+        const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
+        const uint32_t idesc = idesc0 | ((uint32_t)(((nc + 15) & ~15) >> 3) << 17);
+        const uint32_t idesc2 = idesc0 | ((uint32_t)((2 * sw) >> 3) << 17);   // paired: N = [W_hi | W_lo], 2 sw columns
         mbar_wait(t_empty0 + 8 * a, accr.ph);      // the epilogue has drained this accumulator
         accr.next(nacc);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t acc = 0;
-        const uint32_t d_tmem = tmem + a * sw;
+        const uint32_t d_tmem = tmem + a * aw;
         for (int kb = 0; kb < nkb; ++kb) {
           const int s = ring.s;
           mbar_wait(full0 + 8 * s, ring.ph);
@@ -367,6 +373,21 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
 #else
           for (int split = 0; split < nsplit; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi [, X_lo W_lo: fp32-grade]
 #endif
+            if (pair) {
+              // An MMA of this shape costs ~85 cycles whatever its N (the 128 x 32-byte A operand comes out of shared
+              // memory each time), so the W_hi and W_lo halves of the stage -- contiguous, sw rows each -- go in as ONE
+              // 2 sw-column operand: X_hi [W_hi | W_lo] -> accumulator columns [0, sw) and [sw, 2 sw), then X_lo W_hi
+              // (X_lo [W_hi | W_lo] with four products) on top; the epilogue adds the two column blocks.
+              if (split >= 2) break;
+              const uint64_t da = split ? d_al : d_ah;
+              const uint32_t id = (split == 0 || nsplit == 4) ? idesc2 : idesc;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                mma_tf32(d_tmem, da + 2u * kk, d_bh + 2u * kk, id, acc | (uint32_t)split);
+                acc = 1;
+              }
+              continue;
+            }
             const uint64_t da = (split >= 2) ? d_al : d_ah, db = (split & 1) ? d_bl : d_bh;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -392,7 +413,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
       mbar_wait(t_full0 + 8 * a, accr.ph);
       accr.next(nacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * sw;
+      const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * aw;
 #if PCOPS_DENSE_STUB == 6 || PCOPS_DENSE_STUB >= 8
       for (int c0 = 0; c0 < 0; c0 += 32) {
 #else
@@ -400,7 +421,15 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
 #endif
         uint32_t v[32];
         PCG_TMEM_LD32(taddr + c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (pair) {   // second column block: the X_hi W_lo (+ X_lo W_lo) part
+          uint32_t v2[32];
+          PCG_TMEM_LD32(taddr + sw + c0, v2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + __uint_as_float(v2[t]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         const float *cb = s_bias + col0 + c0;
         float y[32];
         if (relu) {   // one uniform branch instead of a predicate per element (NaN handling as before: fmaxf(NaN, 0) = 0)
@@ -792,20 +821,23 @@ int launch_dense(int pool, size_t rows, int K, size_t ldx, int N, size_t ldo, si
   const size_t stage_bytes = 2 * (size_t)kABlock + 2 * (size_t)sw * 128;
   int nst = (int)((227 * 1024 - kFixedBytes) / stage_bytes);
   nst = nst > 4 ? 4 : nst;
-  int nacc = 512 / sw;
+  // [W_hi | W_lo] as one MMA operand where it measured faster (sw = 32: 40 -> 36 us at SA1; at sw = 64 the halved
+  // number of accumulators and the doubled TMEM reads of the epilogue cost more than the four saved MMAs per block)
+  const int pair = PCOPS_DENSE_PAIR && sw <= 32;
+  int nacc = 512 / (pair ? 2 * sw : sw);
   nacc = nacc > 8 ? 8 : nacc;
   const size_t smem = kFixedBytes + (size_t)nst * stage_bytes;
   const int vec_x = (ldx % 4 == 0) && aligned16(x);
   const int vec_o = (ldo % 4 == 0) && aligned16(out);
   if (pool == 1) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<1>, smem));
-    dense_tf32_kernel<1><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<1><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, pair, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else if (pool == 2) {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<2>, smem));
-    dense_tf32_kernel<2><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<2><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, pair, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   } else {
     PC_CUDA_TRY(allow_smem(dense_tf32_kernel<0>, smem));
-    dense_tf32_kernel<0><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
+    dense_tf32_kernel<0><<<grid, kFwdThreads, smem, st>>>(rows, K, ldx, N, sw, nsplit, nst, nacc, pair, ldo, ldp, relu, vec_x, vec_o, x, image, bias, out, pooled);
   }
   PC_RETURN_LAUNCH_STATUS();
 }
