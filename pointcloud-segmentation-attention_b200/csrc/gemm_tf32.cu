@@ -44,9 +44,6 @@ constexpr int kABlock = kRows * 128;       // 16 KB: A K-block (hi or lo)
 constexpr int kBBlock = kMaxNc * 128;      // 32 KB: B K-block (hi or lo) at full width
 constexpr int kStage = 2 * kABlock + 2 * kBBlock;   // 96 KB: A_hi | A_lo | B_hi | B_lo
 constexpr int kThreads = 288;
-#ifndef PCOPS_DENSE_STUB
-#define PCOPS_DENSE_STUB 0   // timing experiments only: 1 no TF32 split, 2 no output stores, 3 no input loads
-#endif
 #ifndef PCOPS_DENSE_WARP_ARRIVE
 #define PCOPS_DENSE_WARP_ARRIVE 1   // 1: one mbarrier arrival per warp (after __syncwarp) instead of one per thread
 #endif
@@ -126,26 +123,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                          \
       : "r"(addr))
 
-#ifndef PCOPS_DENSE_WAIT
-#define PCOPS_DENSE_WAIT 0   // 0: bare try_wait loop; 1: try_wait with a suspend-time hint; 2: nanosleep back-off
-#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // bare try_wait loop: a suspend-time hint on try_wait and a nanosleep back-off were both measured, no difference
   uint32_t ok = 0, spins = 0;
   do {
-#if PCOPS_DENSE_WAIT == 1
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(bar), "r"(parity), "r"(20000u)
-                 : "memory");
-#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
                  : "r"(bar), "r"(parity)
                  : "memory");
-#endif
-#if PCOPS_DENSE_WAIT == 2
-    if (!ok) __nanosleep(64);
-#endif
     if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device on a lost arrival
   } while (!ok);
 }
@@ -247,13 +232,6 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
       const bool in_range = fc.tile < ntiles;
       const size_t row0 = (size_t)fc.tile * kRows;
       fc.next_block(nkb, dt, dc, nchunk);
-#if PCOPS_DENSE_STUB == 3 || PCOPS_DENSE_STUB == 7 || PCOPS_DENSE_STUB >= 8
-      if (true) {
-#pragma unroll
-        for (int i = 0; i < kF4; ++i) buf[i] = make_float4(1.f, 2.f, 3.f, (float)kb);
-        return;
-      }
-#endif
       if (in_range && vec_x && row0 + kRows <= rows && kb * kKB + kKB <= K) {   // whole block in range: no per-element tests
         const float4 *src = reinterpret_cast<const float4 *>(x + (row0 + (tid >> 3)) * ldx + kb * kKB) + (tid & 7);
 #pragma unroll
@@ -288,7 +266,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
       pc_.next_block(nkb, dt, dc, nchunk);
       ring.next(nst);
       unsigned char *st = stage_buf + s * stage_bytes;
-      if (tid == 0 && PCOPS_DENSE_STUB < 10) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
+      if (tid == 0) {  // B block: hi and lo halves of the image slot, nc rows of 128 bytes each
         const unsigned char *src = image + ((size_t)(col0 / kMaxNc) * nkb + kb) * (2 * kBBlock) + (size_t)(col0 % kMaxNc) * 128;
         const uint32_t dst = stage_s + s * stage_bytes + 2 * kABlock;
         const uint32_t bytes = (uint32_t)((nc + 15) & ~15) * 128u;   // the MMA's N is a multiple of 16: zero rows beyond nc
@@ -300,21 +278,13 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
                      "l"(src + kBBlock), "r"(bytes), "r"(full0 + 8 * s)
                      : "memory");
       }
-#if PCOPS_DENSE_STUB == 7 || PCOPS_DENSE_STUB >= 8
-      for (int i = 0; i < 0; ++i) {
-#else
 #pragma unroll
       for (int i = 0; i < kF4; ++i) {
-#endif
         const int i4 = tid + kFwdPW * 32 * i, row = i4 >> 3, kq = i4 & 7;
         const float4 v = buf[i];
         float4 h, l;
-#if PCOPS_DENSE_STUB == 1
-        h = v; l = v;
-#else
         h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
         l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-#endif
         const int off = block_offset(row, kq * 4);
         *reinterpret_cast<float4 *>(st + off) = h;
         *reinterpret_cast<float4 *>(st + kABlock + off) = l;
@@ -366,13 +336,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
           const uint32_t a_hi = stage_s + s * stage_bytes, a_lo = a_hi + kABlock, b_hi = a_hi + 2 * kABlock, b_lo = b_hi + b_half;
           // descriptors of the four operand parts; a K step of 8 (32 bytes) is +2 in the 16-byte address field
           const uint64_t d_ah = smem_desc(a_hi), d_al = smem_desc(a_lo), d_bh = smem_desc(b_hi), d_bl = smem_desc(b_lo);
-#if PCOPS_DENSE_STUB == 4
-          for (int split = 0; split < 1; ++split) {
-#elif PCOPS_DENSE_STUB == 5 || PCOPS_DENSE_STUB == 9 || PCOPS_DENSE_STUB == 11
-          for (int split = 0; split < 0; ++split) {
-#else
           for (int split = 0; split < nsplit; ++split) {  // X_hi W_hi, X_hi W_lo, X_lo W_hi [, X_lo W_lo: fp32-grade]
-#endif
             if (pair) {
               // An MMA of this shape costs ~85 cycles whatever its N (the 128 x 32-byte A operand comes out of shared
               // memory each time), so the W_hi and W_lo halves of the stage -- contiguous, sw rows each -- go in as ONE
@@ -414,11 +378,7 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
       accr.next(nacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem + ((uint32_t)(qtr * 32) << 16) + a * aw;
-#if PCOPS_DENSE_STUB == 6 || PCOPS_DENSE_STUB >= 8
-      for (int c0 = 0; c0 < 0; c0 += 32) {
-#else
       for (int c0 = 0; c0 < nc; c0 += 32) {
-#endif
         uint32_t v[32];
         PCG_TMEM_LD32(taddr + c0, v);
         if (pair) {   // second column block: the X_hi W_lo (+ X_lo W_lo) part
@@ -468,9 +428,6 @@ dense_tf32_kernel(size_t rows, int K, size_t ldx, int N, int sw, int nsplit, int
             *reinterpret_cast<float4 *>(patch + lane * 36 + 4 * t) = make_float4(y[4 * t], y[4 * t + 1], y[4 * t + 2], y[4 * t + 3]);
           __syncwarp();
           const int rr = lane >> 3, cq = (lane & 7) * 4;
-#if PCOPS_DENSE_STUB == 2
-          if (y[0] != 12345.678f) continue;
-#endif
           if (vec_o && row0 + 32 <= rows && c0 + 32 <= nc) {   // whole 32 x 32 patch in range
             float *dst = out + (row0 + rr) * ldo + (size_t)col0 + c0 + cq;
 #pragma unroll
