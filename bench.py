@@ -80,6 +80,8 @@ def parse():
     ap.add_argument("--train", type=int, default=1, help="1: also time config 3 (forward + the registered gradients)")
     ap.add_argument("--train-depth", type=int, default=4, help="batches in flight for the config-3 region")
     ap.add_argument("--skip-probe", action="store_true")
+    ap.add_argument("--hint", type=int, default=0, help="pc_set_concurrency_hint for the pipelined regions (0: the number of "
+                    "batches in flight of each region); lone-launch probes always run with 1")
     return ap.parse_args()
 
 
@@ -827,6 +829,14 @@ def main():
         else:
             pl.forward(overlap, probes)
 
+    # The library sizes its streaming kernels by the number of launches the caller overlaps (pc_set_concurrency_hint):
+    # each pipelined region announces its batches in flight BEFORE its graphs are captured (grid sizes are baked into
+    # a graph); every lone-launch measurement below (probes, steady-state gathers, configs 1 and 5) runs with 1.
+    from pcops_b200 import _lib as pclib
+
+    def hint(n):
+        pclib.set_concurrency_hint(args.hint if args.hint > 0 and n > 1 else n)
+    hint(D)
     # warm-up (also sets per-device kernel attributes before any graph capture)
     for i in range(max(W, D)):
         step_resident(i)
@@ -892,6 +902,7 @@ def main():
     train = None
     if args.train and args.attention:
         TD = max(1, min(D, args.train_depth))
+        hint(TD)
         tp = pipes[:TD]
         for pl in tp:
             pl.allocate_backward(seed=4321 + rank)
@@ -923,6 +934,7 @@ def main():
     with_layers = None
     if args.attention_layers and args.attention:
         LD = max(1, min(D, 4))
+        hint(LD)
         lp = [ScanNetGeometry(B, NPOINTS, 6, dev, attention=True, seed=rank * 64 + 32 + d, own_streams=True,
                               grid=bool(args.grid), attention_layers=True) for d in range(LD)]
         for pl in lp:
@@ -956,6 +968,7 @@ def main():
         try:
             from pcops_b200.model_pipeline import ScanNetAttentionModel
             MD = max(1, min(D, 4))
+            hint(MD)
             models = [ScanNetAttentionModel(B, NPOINTS, 6, dev, seed=rank * 16 + d) for d in range(MD)]
             for md in models:
                 md.set_inputs(dev_xyz[0], dev_feat[0])
@@ -992,6 +1005,7 @@ def main():
 
     # ---- timed region 4: config 4, whole scans through the GPU chunker + forward + map_back -------------------
     config4 = None
+    hint(D)
     if args.scenes > 0 and args.attention and not args.fuse_layers:
         c4_ms = -1.0
         try:
@@ -1022,6 +1036,7 @@ def main():
     fp32_peak_tops = nsm * 128 * sm_max * 1e6 / 1e12   # un-fused fp32 instructions/s (one op per lane per clock)
 
     # ---- region 5: config 5, the geometry-op scaling sweep (no collective inside; one vector reduce after) ------
+    hint(1)
     config5 = None
     if args.config5:
         for pl in pipes[1:]:
@@ -1178,7 +1193,10 @@ def main():
         "config": base_config(B, world),
         "run_config": {"rank_cpu_affinity": numa, "streams_per_batch": 5 if overlap else 1, "cuda_graph": use_graph,
                        "input_ring": R, "batches_in_flight": D, "neighbour_search": "cell grid" if args.grid else "all pairs",
-                       "min_seconds": args.min_seconds, "lib": os.path.basename(pcops_b200._lib.LIB_PATH)},
+                       "min_seconds": args.min_seconds, "lib": os.path.basename(pcops_b200._lib.LIB_PATH),
+                       "concurrency_hint": "pc_set_concurrency_hint(batches in flight) for the pipelined regions%s, 1 for "
+                                           "every lone-launch figure (rooflines, gathers_steady_state, configs 1 and 5)"
+                                           % (" (forced to %d)" % args.hint if args.hint > 0 else "")},
         "fps_us_per_scene": {"sa1_batch_latency_us": top_ms * 1e3, "sa1_us_per_scene_throughput": top_ms * 1e3 / B},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_block / K, "repeats": e2e_reps, "result_checksum": checksum,

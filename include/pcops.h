@@ -57,6 +57,14 @@ typedef void *pc_stream_t; /* cudaStream_t */
 PC_API int pc_version(void);                   /* 100*major + minor */
 PC_API const char *pc_error_string(int code);  /* PC_ERR_* names, or cudaGetErrorString for positive codes */
 PC_API int pc_num_sms(void);                   /* SM count of the current device (grid sizing / tests); <0 on error */
+/* Concurrency hint (process-wide, default 1): how many independent launches of this library the caller keeps in
+ * flight on the device at once (e.g. the number of batches a multi-stream / multi-graph pipeline overlaps).  Results
+ * never depend on it.  The streaming kernels (group_point, three_interpolate, the feature pro- / epilogues, the attention
+ * contraction) size their grids and shared-memory rings for a lone launch when it is 1, and as fewer, longer-lived CTAs
+ * with small reservations when it is larger: inside a mix of co-resident kernels that raised the whole ScanNet step
+ * by 4 %, while a lone launch sized that way is up to 2 x slower.  n >= 1, else PC_ERR_INVALID_ARGUMENT. */
+PC_API int pc_set_concurrency_hint(int n);
+PC_API int pc_get_concurrency_hint(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Sampling library (reference: sampling/tf_sampling_g.cu, sampling/tf_sampling.cpp)

@@ -25,6 +25,8 @@ SIGNATURES = {
     "pc_version": (_i, []),
     "pc_error_string": (ctypes.c_char_p, [_i]),
     "pc_num_sms": (_i, []),
+    "pc_set_concurrency_hint": (_i, [_i]),
+    "pc_get_concurrency_hint": (_i, []),
     "pc_fps_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_fps": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_fps_gather": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -170,3 +172,13 @@ def workspace(nbytes, device):
     if nbytes == 0:
         return None
     return torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+
+
+def set_concurrency_hint(n):
+    """Tell the library how many independent launches the caller keeps in flight (pc_set_concurrency_hint): 1 (default)
+    sizes the streaming kernels for a lone launch, larger values as few long-lived CTAs that co-reside with other
+    kernels.  Results never depend on it.  Returns the previous value."""
+    L = lib()
+    old = L.pc_get_concurrency_hint()
+    check(L.pc_set_concurrency_hint(int(n)), "pc_set_concurrency_hint")
+    return old

@@ -1,4 +1,5 @@
 // Library-level entry points of libpcops.so: version, error strings, device queries.
+#include <atomic>
 #include <mutex>
 #include "common.cuh"
 
@@ -37,6 +38,9 @@ cudaError_t allow_smem_cached(const void *kernel, size_t bytes) {
   return cudaSuccess;
 }
 
+static std::atomic<int> g_concurrency_hint{1};
+int concurrency_hint() { return g_concurrency_hint.load(std::memory_order_relaxed); }
+
 int resident_grid(const void *kernel, int threads, size_t smem, size_t needed) {
   // occupancy per (kernel, threads, smem), cached: cudaOccupancyMaxActiveBlocksPerMultiprocessor costs microseconds
   struct Entry { const void *k; int threads; size_t smem; int occ; };
@@ -53,13 +57,23 @@ int resident_grid(const void *kernel, int threads, size_t smem, size_t needed) {
       if (used < 64) table[used++] = Entry{kernel, threads, smem, occ};
     }
   }
-  size_t g = (size_t)num_sms() * (size_t)occ;
+  const int h = concurrency_hint();
+  const int per_sm = occ / h > 1 ? occ / h : 1;
+  size_t g = (size_t)num_sms() * (size_t)per_sm;
   if (g > needed) g = needed;
   return g < 1 ? 1 : (int)g;
 }
 }  // namespace pc
 
 extern "C" int pc_version(void) { return 100; }
+
+extern "C" int pc_set_concurrency_hint(int n) {
+  if (n < 1) return PC_ERR_INVALID_ARGUMENT;
+  pc::g_concurrency_hint.store(n, std::memory_order_relaxed);
+  return PC_OK;
+}
+
+extern "C" int pc_get_concurrency_hint(void) { return pc::concurrency_hint(); }
 
 extern "C" int pc_num_sms(void) {
   int dev = 0, v = 0;

@@ -209,28 +209,15 @@ attention_fwd_kernel(size_t heads_total, int S, int H, const float *__restrict__
 // memory and 45 k registers each), scenes/s of the whole step:
 //   warps/CTA x ring slots x blocks/warp   2x3 persistent 75.5 k | 1x3x16 77.8 k | 1x4x16 76.0 k | 1x6x16 72.0 k
 //                                          1x2x16 80.1 k | 1x2x32 82.5 k | 1x2x64 83.6 k | 1x2x128 83.6 k | 1x2x256 78.8 k
-// The kernel is an HBM stream that shares every SM with other kernels: what pays is a SMALL shared-memory reservation
-// (32 KB CTAs find room beside an FPS CTA plus a tile-kernel CTA; 96 KB ones queued for the few free SMs) and FEW,
-// long-lived warps (one 16 KB bulk copy in flight per warp is enough once a hundred warps stream; more warps only take
-// issue slots and L2 bandwidth from the kernels in flight next to it).  A lone launch wants the opposite (SA1 alone:
-// 46 us with 592 warps x 3 slots, 58 us with 296 x 2, 86 us with 148 x 2); the default -- two single-warp CTAs per SM,
-// two slots, K / V copies marked evict-first in L2 (+1.5 k scenes/s: 500 MB read once no longer evict the gathers'
-// working sets) -- gives 82.3 k scenes/s in the step against 83.6 k for the narrowest variant.  The variants stay
-// selectable for A/B builds.
-#ifndef PCOPS_LH_EVICT_FIRST
-#define PCOPS_LH_EVICT_FIRST 1   // L2 evict-first policy on the K / V bulk copies
-#endif
-#ifndef PCOPS_LH_WARPS
-#define PCOPS_LH_WARPS 1
-#endif
-#ifndef PCOPS_LH_BPW
-#define PCOPS_LH_BPW -2    // consecutive 32-head blocks per warp; -t: equal shares over about t CTAs per SM
-#endif
-#ifndef PCOPS_LH_SLOTS
-#define PCOPS_LH_SLOTS 2   // ring slots per warp: K of block b in one, V in the other; the next K lands during the V pass
-#endif
-constexpr int kLhWarps = PCOPS_LH_WARPS;
-constexpr int kLhSlots = PCOPS_LH_SLOTS;
+// The kernel is an HBM stream that shares every SM with other kernels: what pays THERE is a small shared-memory
+// reservation (32 KB CTAs find room beside an FPS CTA plus a tile-kernel CTA; 96 KB ones queued for the few free SMs)
+// and FEW, long-lived warps (one 16 KB bulk copy in flight per warp is enough once a hundred warps stream; more warps
+// only take issue slots and L2 bandwidth from the kernels in flight next to it).  A lone launch wants the opposite (SA1
+// alone: 46 us with 592 warps x 3 slots, 58 us with 296 x 2, 86 us with 148 x 2).  So the shape follows the caller's
+// concurrency hint (pc_set_concurrency_hint): 1 -> four single-warp CTAs per SM with three slots; 2..7 -> two per SM,
+// two slots; >= 8 -> one per SM, two slots.  K / V copies carry an L2 evict-first policy (+1.5 k scenes/s: 500 MB read
+// once no longer evict the gathers' working sets).
+constexpr int kLhMaxSlots = 3;
 constexpr int kLhSlotBytes = 32 * 128 * 4;  // one slot = the K (or V) run of 32 heads = 16 KB
 
 __device__ __forceinline__ void lh_wait(uint32_t bar, uint32_t parity) {
@@ -244,63 +231,59 @@ __device__ __forceinline__ void lh_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
-__global__ void __launch_bounds__(kLhWarps * 32)
-attention_fwd_lanehead_kernel(size_t heads_total, int bpw, const float *__restrict__ Q, const float *__restrict__ K,
+__global__ void __launch_bounds__(32)
+attention_fwd_lanehead_kernel(size_t heads_total, int bpw, int nslots, const float *__restrict__ Q, const float *__restrict__ K,
                               const float *__restrict__ V, float *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char lh_smem[];
-  __shared__ __align__(8) uint64_t s_bar[kLhWarps][kLhSlots];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *ring = lh_smem + (size_t)warp * kLhSlots * kLhSlotBytes;
+  __shared__ __align__(8) uint64_t s_bar[kLhMaxSlots];
+  const int lane = threadIdx.x;
+  unsigned char *ring = lh_smem;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_bar[warp][0]);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kLhSlots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8 * i), "r"(1u));
+    for (int i = 0; i < nslots; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8 * i), "r"(1u));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   __syncwarp();
   const size_t nblocks = (heads_total + 31) / 32;
-  // a warp owns bpw CONSECUTIVE blocks
-  const size_t wstride = 1;
-  const size_t first = ((size_t)blockIdx.x * kLhWarps + warp) * (size_t)bpw;
+  // the warp owns bpw CONSECUTIVE blocks of 32 heads
+  const size_t first = (size_t)blockIdx.x * (size_t)bpw;
   const int my_blocks = first < nblocks ? (int)(nblocks - first < (size_t)bpw ? nblocks - first : (size_t)bpw) : 0;
-  const int nseq = 2 * my_blocks;   // the warp's copy sequence: K of block 0, V of block 0, K of block 1, ... ; slot = seq % kLhSlots
+  const int nseq = 2 * my_blocks;   // the warp's copy sequence: K of block 0, V of block 0, K of block 1, ... round robin over the slots
 
-#if PCOPS_LH_EVICT_FIRST
   uint64_t policy;   // K and V are read exactly once: do not let 500 MB of them push the gathers' working sets out of L2
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-#endif
+  int issue_slot = 0;               // slot of the next copy to issue; copies are issued in sequence order
   auto issue = [&](int seq) {
-    const size_t h0 = (first + (size_t)(seq >> 1) * wstride) * 32;
+    const size_t h0 = (first + (size_t)(seq >> 1)) * 32;
     const uint32_t nh = (uint32_t)((heads_total - h0 < 32) ? heads_total - h0 : 32);
     const uint32_t bytes = nh * 512u;
-    const int slot = seq % kLhSlots;
+    const int slot = issue_slot;
+    issue_slot = issue_slot + 1 == nslots ? 0 : issue_slot + 1;
     const float *src = ((seq & 1) ? V : K) + h0 * 128;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s + 8 * slot), "r"(bytes) : "memory");
-#if PCOPS_LH_EVICT_FIRST
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      ring_s + slot * kLhSlotBytes),
                  "l"(src), "r"(bytes), "r"(bar_s + 8 * slot), "l"(policy)
                  : "memory");
-#else
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     ring_s + slot * kLhSlotBytes),
-                 "l"(src), "r"(bytes), "r"(bar_s + 8 * slot)
-                 : "memory");
-#endif
   };
   if (lane == 0)
-    for (int seq = 0; seq < kLhSlots && seq < nseq; ++seq) issue(seq);
+    for (int seq = 0; seq < nslots && seq < nseq; ++seq) issue(seq);
+  int slot = 0;                     // slot and phase of the next copy to consume
+  uint32_t phase = 0;
+  auto advance = [&]() {
+    if (++slot == nslots) { slot = 0; phase ^= 1u; }
+  };
   for (int b = 0; b < my_blocks; ++b) {
-    const size_t gh = (first + (size_t)b * wstride) * 32 + lane;
+    const size_t gh = (first + (size_t)b) * 32 + lane;
     const bool live = gh < heads_total;
     const float4 q = live ? __ldg(reinterpret_cast<const float4 *>(Q) + gh) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int seq_k = 2 * b, seq_v = 2 * b + 1;
-    const float4 *ks = reinterpret_cast<const float4 *>(ring + (size_t)(seq_k % kLhSlots) * kLhSlotBytes) + lane * 32;
-    const float4 *vs = reinterpret_cast<const float4 *>(ring + (size_t)(seq_v % kLhSlots) * kLhSlotBytes) + lane * 32;
+    const float4 *ks = reinterpret_cast<const float4 *>(ring + (size_t)slot * kLhSlotBytes) + lane * 32;
     float p[32];
     float mx = -INFINITY;
-    lh_wait(bar_s + 8 * (seq_k % kLhSlots), (uint32_t)((seq_k / kLhSlots) & 1));
+    lh_wait(bar_s + 8 * slot, phase);
+    advance();
     if (live) {
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
@@ -311,10 +294,12 @@ attention_fwd_lanehead_kernel(size_t heads_total, int bpw, const float *__restri
         mx = fmaxf(mx, lg);
       }
     }
-    __syncwarp();   // every lane is done with the K slot: refill it with the copy kLhSlots steps ahead
-    if (lane == 0 && seq_k + kLhSlots < nseq) issue(seq_k + kLhSlots);
+    __syncwarp();   // every lane is done with the K slot: refill it with the copy nslots steps ahead
+    if (lane == 0 && seq_k + nslots < nseq) issue(seq_k + nslots);
     float sum = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    lh_wait(bar_s + 8 * (seq_v % kLhSlots), (uint32_t)((seq_v / kLhSlots) & 1));
+    const float4 *vs = reinterpret_cast<const float4 *>(ring + (size_t)slot * kLhSlotBytes) + lane * 32;
+    lh_wait(bar_s + 8 * slot, phase);
+    advance();
     if (live) {
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
@@ -327,22 +312,22 @@ attention_fwd_lanehead_kernel(size_t heads_total, int bpw, const float *__restri
       reinterpret_cast<float4 *>(out)[gh] = make_float4(o0 * inv, o1 * inv, o2 * inv, o3 * inv);
     }
     __syncwarp();
-    if (lane == 0 && seq_v + kLhSlots < nseq) issue(seq_v + kLhSlots);
+    if (lane == 0 && seq_v + nslots < nseq) issue(seq_v + nslots);
   }
 }
 
 int launch_fwd_lanehead(size_t heads, const float *Q, const float *K, const float *V, float *out, cudaStream_t st) {
-  const size_t smem = (size_t)kLhWarps * kLhSlots * kLhSlotBytes;
-  PC_CUDA_TRY(allow_smem(attention_fwd_lanehead_kernel, smem));
+  const int h = concurrency_hint();
+  const int nslots = h == 1 ? 3 : 2;
+  const size_t per_sm = h == 1 ? 4 : h < 8 ? 2 : 1;
+  const size_t smem = (size_t)nslots * kLhSlotBytes;
+  PC_CUDA_TRY(allow_smem(attention_fwd_lanehead_kernel, (size_t)kLhMaxSlots * kLhSlotBytes));
   const size_t nblocks = (heads + 31) / 32;
-  long bpw = PCOPS_LH_BPW;
-  if (bpw <= 0) {   // -t: about t CTAs per SM (0: as many as fit), equal contiguous shares of at most 64 blocks
-    const size_t ctas = (size_t)num_sms() * (bpw < 0 ? (size_t)-bpw : (size_t)(4 / kLhWarps));
-    bpw = (long)((nblocks + ctas * kLhWarps - 1) / (ctas * kLhWarps));
-    bpw = bpw > 64 ? 64 : bpw < 1 ? 1 : bpw;
-  }
-  const size_t grid = (nblocks + bpw * kLhWarps - 1) / (bpw * kLhWarps);
-  attention_fwd_lanehead_kernel<<<(unsigned)grid, kLhWarps * 32, smem, st>>>(heads, (int)bpw, Q, K, V, out);
+  const size_t ctas = (size_t)num_sms() * per_sm;        // equal contiguous shares of at most 64 blocks
+  size_t bpw = (nblocks + ctas - 1) / ctas;
+  bpw = bpw > 64 ? 64 : bpw < 1 ? 1 : bpw;
+  const size_t grid = (nblocks + bpw - 1) / bpw;
+  attention_fwd_lanehead_kernel<<<(unsigned)grid, 32, smem, st>>>(heads, (int)bpw, nslots, Q, K, V, out);
   PC_RETURN_LAUNCH_STATUS();
 }
 

@@ -94,11 +94,14 @@ struct FastDiv {
   __device__ __forceinline__ uint32_t div(uint32_t x) const { return (uint32_t)(((unsigned long long)x * m) >> s); }
 };
 // Grid size for a grid-stride kernel: every SM filled to the kernel's real occupancy, never more CTAs than `needed`
-// (a second, partially filled wave costs a short HBM-bound kernel up to half its run time).
+// (a second, partially filled wave costs a short HBM-bound kernel up to half its run time); with a concurrency hint h
+// the occupancy is divided by h (at least one CTA per SM): co-resident kernels of other batches fill the rest.
 int resident_grid(const void *kernel, int threads, size_t smem, size_t needed);
 
 // SM count of the current device, cached per device id.
 int num_sms();
+// pc_set_concurrency_hint(): independent launches the caller keeps in flight (>= 1).
+int concurrency_hint();
 // Opt a kernel into > 48 KB dynamic shared memory (idempotent; cheap).
 // The attribute is set once per (kernel, device) and raised only when a larger size is asked for, so steady-state
 // calls (and calls made while a stream is being captured into a CUDA graph) touch no driver state.

@@ -273,7 +273,8 @@ void launch_interp(size_t total, int c, int n, int m, const float *points, const
   while (rpw > 4 && (rows + rpw - 1) / rpw < (size_t)num_sms() * 48) rpw >>= 1;
   if (PCOPS_INTERP_ROWS && c % 128 == 0 && c > 0 && aligned16(points) && aligned16(out) && rpw >= 8) {   // small launches: thread-per-float4 kernel
     size_t blocks = ((rows + rpw - 1) / rpw + 7) / 8;
-    const size_t cap = (size_t)num_sms() * 8;
+    const int h = concurrency_hint();
+    const size_t cap = (size_t)num_sms() * (size_t)(8 / h > 1 ? 8 / h : 1);   // CTAs per SM: 8 alone, fewer among co-resident kernels
     if (blocks > cap) blocks = cap;
     interp_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, rpw, n, m, c / 4, (const float4 *)points, idx, weight, (float4 *)out);
   } else if (c % 4 == 0 && aligned16(points) && aligned16(out)) {

@@ -15,6 +15,7 @@ if len(sys.argv) > 2:
     _lib.LIB_PATH = os.path.abspath(sys.argv[2])
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
+_lib.set_concurrency_hint(int(os.environ.get('HINT', D)))   # HINT=1: lone-launch shapes, for comparison
 x, f = synth.scannet_batch(0, B, N)
 dx, df = torch.from_numpy(x).to(dev), torch.from_numpy(f).to(dev)
 cur = torch.cuda.current_stream(dev)

@@ -7,5 +7,5 @@ for lib in "$@"; do
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 r=d['rooflines']; g=d['gathers_steady_state']
-print('$name value %.0f e2e %.0f lone interp us:' % (d['value'], d['e2e']['value']), [round(r['three_interpolate_fp%d'%i]['ms']*1e3,1) for i in (1,2,3,4)], 'steady', {k: round(v['frac'],3) for k,v in g.items() if 'interp' in k})"
+print('$name value %.0f e2e %.0f lone interp us:' % (d['value'], d['e2e']['value']), [round(r['three_interpolate_fp%d'%i]['ms']*1e3,1) for i in (1,2,3,4)], 'group_feat', [round(r['group_feat_sa%d'%i]['ms']*1e3,1) for i in (1,2,3,4)], 'steady', {k[:22]: round(v['frac'],3) for k,v in g.items()})"
 done

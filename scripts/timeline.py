@@ -11,7 +11,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pcops_b200 import synth                      # noqa: E402
+from pcops_b200 import _lib, synth               # noqa: E402
 from pcops_b200.pipeline import ScanNetGeometry   # noqa: E402
 
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 8
@@ -19,6 +19,7 @@ STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 48
 B, N = 16, 8192
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
+_lib.set_concurrency_hint(D)     # the streaming kernels size themselves for D batches in flight
 x, f = synth.scannet_batch(0, B, N)
 dx, df = torch.from_numpy(x).to(dev), torch.from_numpy(f).to(dev)
 pipes = [ScanNetGeometry(B, N, 6, dev, attention=True, seed=d, own_streams=True, grid=True) for d in range(D)]

@@ -610,3 +610,34 @@ def test_attention_layer_fused_matches_oracle(G, C):
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     np.testing.assert_allclose(npy(a), npy(b), rtol=2e-5, atol=2e-5)   # fp32 cuBLAS composition vs fused
+
+
+@pytest.mark.gpu
+def test_concurrency_hint_changes_launch_shapes_not_results():
+    """pc_set_concurrency_hint sizes the streaming kernels for a lone launch (1) or for co-residency with other launches
+    (> 1): group_point, three_interpolate and the attention contraction must return the same bits either way."""
+    from pcops_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(5)
+    B, n, m, ns = 4, 2048, 512, 32
+    feat = torch.randn((B, n, 64), generator=g, device=dev)
+    idx = torch.randint(0, n, (B, m, ns), generator=g, device=dev, dtype=torch.int32)
+    p2 = torch.randn((B, m, 128), generator=g, device=dev)
+    i3 = torch.randint(0, m, (B, n, 3), generator=g, device=dev, dtype=torch.int32)
+    w = torch.rand((B, n, 3), generator=g, device=dev)
+    Q = torch.randn((B * m, 64), generator=g, device=dev)
+    K = torch.randn((B * m, ns, 64), generator=g, device=dev)
+    V = torch.randn((B * m, ns, 64), generator=g, device=dev)
+    with pytest.raises(ValueError):
+        _lib.set_concurrency_hint(0)
+    old = _lib.set_concurrency_hint(1)
+    try:
+        want = (ops.group_point(feat, idx), ops.three_interpolate(p2, i3, w), ops.attention_contract(Q, K, V, 16, 4))
+        for h in (2, 4, 8, 64):
+            assert _lib.set_concurrency_hint(h) in (1, 2, 4, 8)
+            got = (ops.group_point(feat, idx), ops.three_interpolate(p2, i3, w), ops.attention_contract(Q, K, V, 16, 4))
+            for a, b in zip(got, want):
+                assert torch.equal(a, b), h
+    finally:
+        _lib.set_concurrency_hint(old)
+    assert _lib.lib().pc_get_concurrency_hint() == old
