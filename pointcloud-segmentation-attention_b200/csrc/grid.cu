@@ -25,16 +25,11 @@ namespace pc {
 namespace {
 
 constexpr int kMaxCells = 16384;  // 64 KB shared-memory histogram in the build kernel
-// 256 threads / <= 64 registers: small enough to sit beside a resident 512-thread FPS CTA (45 k of the SM's 64 k
-// registers).  With 1024-thread build CTAs the pipelined step lost 7 % (69.6 k -> 75.0 k scenes/s): they only fitted
-// on the few SMs no FPS CTA held and every binned op of every batch in flight queued for those.
-#ifndef PCOPS_BUILD_THREADS
-#define PCOPS_BUILD_THREADS 256
-#endif
-#ifndef PCOPS_BUILD_MINB
-#define PCOPS_BUILD_MINB 4
-#endif
-constexpr int kBuildThreads = PCOPS_BUILD_THREADS;
+// Build CTA size follows the caller's concurrency hint.  Alone, 1024 threads finish a scene soonest (23 us at SA1).
+// Among co-resident kernels a 1024-thread CTA with a 64 KB histogram (51 k registers) fits on no SM that holds a
+// 512-thread FPS CTA (45 k of the SM's 64 k registers): with eight batches in flight every binned op of every batch
+// queued for the ~20 FPS-free SMs, and 256-thread CTAs (<= 64 registers) with a histogram sized by the candidate count
+// took the pipelined step from 69.6 k to 75.5 k scenes/s -- although the lone build takes 19-35 us that way.
 constexpr int kHdrInts = 16;
 
 struct GridHdr {  // 16 x 4 bytes, first thing in a scene's workspace
@@ -75,7 +70,8 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float *s_red
 // CTA (s, 1) bins the QUERY cloud by the same cells (so that 32 consecutive sorted queries are spatial neighbours) --
 // it derives the grid header from the candidates itself (the same reduction over the same data gives the same bits;
 // one extra pass over 12 n bytes) instead of waiting for a second launch behind the first.
-__global__ void __launch_bounds__(kBuildThreads, PCOPS_BUILD_MINB)
+template <int kBuildThreads>
+__global__ void __launch_bounds__(kBuildThreads, kBuildThreads == 1024 ? 1 : 4)
 grid_build_kernel(int nc, int nq, float min_edge, int mode, int max_cells, const float *__restrict__ xyz_c,
                   const float *__restrict__ xyz_q, int *__restrict__ ws_c, int *__restrict__ ws_q) {
   extern __shared__ int s_cnt[];  // max_cells
@@ -523,11 +519,17 @@ int build_pair(int b, int nc, int nq, float min_edge, int mode, const float *xyz
   // The histogram (and with it the finest grid) is sized by the candidate count: two cells per candidate is finer than
   // either op wants (the build coarsens the cell edge until the grid fits -- results do not depend on the edge), and a
   // build CTA that reserves 8 KB instead of 64 KB finds room on an SM whose shared memory an FPS CTA half fills.
-  int max_cells = 2 * nc;
+  const bool lone = concurrency_hint() == 1;
+  int max_cells = lone ? kMaxCells : 2 * nc;
   max_cells = max_cells < 1024 ? 1024 : max_cells > kMaxCells ? kMaxCells : max_cells;
   const size_t smem = (size_t)max_cells * sizeof(int);
-  PC_CUDA_TRY(allow_smem(grid_build_kernel, (size_t)kMaxCells * sizeof(int)));
-  grid_build_kernel<<<dim3(b, 2), kBuildThreads, smem, st>>>(nc, nq, min_edge, mode, max_cells, xyz_c, xyz_q, ws_c, ws_q);
+  if (lone) {
+    PC_CUDA_TRY(allow_smem(grid_build_kernel<1024>, (size_t)kMaxCells * sizeof(int)));
+    grid_build_kernel<1024><<<dim3(b, 2), 1024, smem, st>>>(nc, nq, min_edge, mode, max_cells, xyz_c, xyz_q, ws_c, ws_q);
+  } else {
+    PC_CUDA_TRY(allow_smem(grid_build_kernel<256>, (size_t)kMaxCells * sizeof(int)));
+    grid_build_kernel<256><<<dim3(b, 2), 256, smem, st>>>(nc, nq, min_edge, mode, max_cells, xyz_c, xyz_q, ws_c, ws_q);
+  }
   PC_RETURN_LAUNCH_STATUS();
 }
 

@@ -615,7 +615,8 @@ def test_attention_layer_fused_matches_oracle(G, C):
 @pytest.mark.gpu
 def test_concurrency_hint_changes_launch_shapes_not_results():
     """pc_set_concurrency_hint sizes the streaming kernels for a lone launch (1) or for co-residency with other launches
-    (> 1): group_point, three_interpolate and the attention contraction must return the same bits either way."""
+    (> 1): group_point, three_interpolate, the attention contraction and the cell-grid searches (build CTA size, histogram
+    size) must return the same bits either way."""
     from pcops_b200 import _lib
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(5)
@@ -632,10 +633,16 @@ def test_concurrency_hint_changes_launch_shapes_not_results():
         _lib.set_concurrency_hint(0)
     old = _lib.set_concurrency_hint(1)
     try:
-        want = (ops.group_point(feat, idx), ops.three_interpolate(p2, i3, w), ops.attention_contract(Q, K, V, 16, 4))
+        xyz = torch.rand((B, n, 3), generator=g, device=dev)
+        new_xyz = xyz[:, :m].contiguous()
+
+        def run():
+            return (ops.group_point(feat, idx), ops.three_interpolate(p2, i3, w), ops.attention_contract(Q, K, V, 16, 4),
+                    *ops.query_ball_point(0.1, ns, xyz, new_xyz), *ops.three_nn(xyz, new_xyz))
+        want = run()
         for h in (2, 4, 8, 64):
             assert _lib.set_concurrency_hint(h) in (1, 2, 4, 8)
-            got = (ops.group_point(feat, idx), ops.three_interpolate(p2, i3, w), ops.attention_contract(Q, K, V, 16, 4))
+            got = run()
             for a, b in zip(got, want):
                 assert torch.equal(a, b), h
     finally:
