@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="scenes per GPU per step (the config names 16)")
     ap.add_argument("--ring", type=int, default=4, help="distinct input batches cycled through")
     ap.add_argument("--graph", type=int, default=1, help="1: replay each forward as a CUDA graph (default); 0: eager")
-    ap.add_argument("--depth", type=int, default=8, help="independent batches in flight (pipeline instances, own streams)")
+    ap.add_argument("--depth", type=int, default=9, help="independent batches in flight (pipeline instances, own streams)")
     ap.add_argument("--attention", type=int, default=1, help="0: leave the attention contraction out (diagnostics only)")
     ap.add_argument("--fuse-layers", type=int, default=0, help="1: pc_sa_group / pc_fp_interpolate instead of the op pairs")
     ap.add_argument("--grid", type=int, default=1, help="1: cell-grid ball query / three_nn; 0: all-pairs kernels")
