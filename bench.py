@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="scenes per GPU per step (the config names 16)")
     ap.add_argument("--ring", type=int, default=4, help="distinct input batches cycled through")
     ap.add_argument("--graph", type=int, default=1, help="1: replay each forward as a CUDA graph (default); 0: eager")
-    ap.add_argument("--depth", type=int, default=9, help="independent batches in flight (pipeline instances, own streams)")
+    ap.add_argument("--depth", type=int, default=8, help="independent batches in flight (pipeline instances, own streams)")
     ap.add_argument("--attention", type=int, default=1, help="0: leave the attention contraction out (diagnostics only)")
     ap.add_argument("--fuse-layers", type=int, default=0, help="1: pc_sa_group / pc_fp_interpolate instead of the op pairs")
     ap.add_argument("--grid", type=int, default=1, help="1: cell-grid ball query / three_nn; 0: all-pairs kernels")
@@ -783,6 +783,8 @@ def main():
         for pl in ps:
             cur.wait_stream(pl.main)
 
+    rank_spread = []
+
     def timed_region(step, ps, sampler=None):
         """K steps x `repeats` inside ONE event pair on `cur` (forked to / joined from the pipelines' streams), repeats
         agreed over the ranks so that the region lasts >= --min-seconds.  Returns (ms per K-step block, repeats, host
@@ -818,7 +820,9 @@ def main():
         torch.cuda.synchronize(dev)
         t1 = time.time()
         sharding.barrier()
-        ms = sharding.max_over_ranks(e0.elapsed_time(e1))
+        own = e0.elapsed_time(e1)
+        ms = sharding.max_over_ranks(own)
+        rank_spread.append(-sharding.max_over_ranks(-own) / ms)       # fastest rank / slowest rank, per region
         return ms / reps, reps, t_enq / reps, t0, t1
 
     def step_resident(i, probes=None, graph=False):
@@ -1188,6 +1192,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_block / K, "timed_repeats": reps, "steps_timed": K * reps,
+        "fastest_over_slowest_rank": rank_spread[:2],      # [value region, e2e region]: 1.0 = all ranks equally fast
         "host_enqueue_ms_per_step": 1e3 * enq_s / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": base_config(B, world),
