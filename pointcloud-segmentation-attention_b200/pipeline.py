@@ -18,7 +18,9 @@ Streams: the four FPS calls form a strictly sequential chain (level l+1 samples 
 stream (high priority: FPS is latency-bound and occupies only B SMs); everything else of level l runs on side stream l
 behind a per-level event, so grouping / interpolation / attention of all levels overlap each other and the FPS chain.
 The sequence is CUDA-graph capturable (no allocation, no host sync inside).  Independent batches overlap further by
-running several ``ScanNetGeometry`` instances, each on its own streams (bench.py --depth).
+running several ``ScanNetGeometry`` instances, each on its own streams (bench.py --depth); tell the library how many
+with ``_lib.set_concurrency_hint(instances)`` BEFORE ``capture()`` -- it then launches its streaming kernels as few
+long-lived CTAs that co-reside with the other batches' kernels (grid sizes are baked into a captured graph).
 
 All integer results a host consumer reads back (FPS, ball and three_nn indices, counts) are views into ONE contiguous
 device buffer, so a step's result is a single device-to-host copy.
