@@ -303,6 +303,15 @@ PC_API int pc_scene_sample_weights(int nchunks, int npoints, const int *desc, co
 PC_API int pc_map_back_winner(size_t rows, int nres, const long long *orig_idx, const unsigned char *mask, int *winner,
                        pc_stream_t stream);
 
+/* HOST function (no device work): the permutation np.random.shuffle(arange(n)) produces on a legacy MT19937 RandomState,
+ * complete_scene_loader.py:17-18 -- the per-cell shuffle of the chunker, numpy's stream restated in C (same draws, ~5 x
+ * faster than numpy's generic shuffle).  mt_key[624] / mt_pos: the state as np.random.get_state() returns it, advanced
+ * in place (hand it back with np.random.set_state()).  perm: n ints. */
+PC_API int pc_host_legacy_shuffle(unsigned int *mt_key, int *mt_pos, int n, int *perm);
+/* HOST function: np.random.choice(high, count, replace=True) (= legacy randint(0, high, size=count)) on the same state,
+ * complete_scene_loader.py:87 -- the fill-up indices of a cell's last chunk.  out: count ints in [0, high). */
+PC_API int pc_host_legacy_randint(unsigned int *mt_key, int *mt_pos, int high, int count, int *out);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Dense layers of the path on the tcgen05 tensor cores (csrc/gemm_tf32.cu), 3xTF32 split precision: fp32 in / out,
  * ~2e-6 of the output scale against a float64 product.  Reference: the 1x1 conv2d + batch norm + ReLU stack and the

@@ -26,6 +26,8 @@ SIGNATURES = {
     "pc_error_string": (ctypes.c_char_p, [_i]),
     "pc_num_sms": (_i, []),
     "pc_set_concurrency_hint": (_i, [_i]),
+    "pc_host_legacy_shuffle": (_i, [_vp, _vp, _i, _vp]),
+    "pc_host_legacy_randint": (_i, [_vp, _vp, _i, _i, _vp]),
     "pc_get_concurrency_hint": (_i, []),
     "pc_fps_workspace_bytes": (_sz, [_i, _i, _i]),
     "pc_fps": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),

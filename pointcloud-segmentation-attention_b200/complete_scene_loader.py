@@ -59,32 +59,75 @@ def _cell_boxes(coordmin, coordmax):
     return np.stack(boxes).astype(np.float32) if boxes else np.zeros((0, 12), np.float32)
 
 
+class _LegacyStream:
+    """numpy's global legacy RandomState, advanced in C for the duration of one scan's planning: the draws of
+    np.random.shuffle (complete_scene_loader.py:17-18) and np.random.choice (:87) through pc_host_legacy_shuffle /
+    pc_host_legacy_randint (csrc/host_rng.cu: MT19937 + numpy's masked-rejection draw, the same stream bit for bit,
+    ~1.5-2 x faster than numpy's generic shuffle, which was the largest share of the chunker's host time).  The state
+    is copied out once (np.random.get_state costs 0.1 ms), advanced in place and written back on exit -- also when
+    planning raises -- so later np.random calls continue the same stream.  A global state that is not the legacy
+    MT19937 (it always is for np.random.*) takes numpy's own functions."""
+
+    def __enter__(self):
+        st = np.random.get_state()
+        self.native = st[0] == "MT19937"
+        if self.native:
+            self.st = st
+            self.key = np.array(st[1], dtype=np.uint32, order="C", copy=True)
+            self.pos = _lib.ctypes.c_int(int(st[2]))
+            self.L = _lib.lib()
+        return self
+
+    def __exit__(self, *exc):
+        if self.native:
+            np.random.set_state((self.st[0], self.key, self.pos.value, self.st[3], self.st[4]))
+        return False
+
+    def shuffled_arange(self, n):
+        if not self.native:
+            order = np.arange(n)
+            np.random.shuffle(order)
+            return order.astype(np.int32)
+        perm = np.empty(n, dtype=np.int32)
+        _lib.check(self.L.pc_host_legacy_shuffle(self.key.ctypes.data, _lib.ctypes.addressof(self.pos), int(n),
+                                                 perm.ctypes.data), "pc_host_legacy_shuffle")
+        return perm
+
+    def choice(self, high, count):
+        if not self.native:
+            return np.random.choice(high, count, replace=True).astype(np.int32)
+        out = np.empty(count, dtype=np.int32)
+        _lib.check(self.L.pc_host_legacy_randint(self.key.ctypes.data, _lib.ctypes.addressof(self.pos), int(high), int(count),
+                                                 out.ctypes.data), "pc_host_legacy_randint")
+        return out
+
+
 def _plan_chunks(base, npoints=NPOINTS):
     """Host half of the chunker: numpy's global RNG stream in the reference's order -- per non-empty cell one
     np.random.shuffle (:17-18) and one np.random.choice (:87) -- and the candidate-chunk descriptors
     {list_base, order_off, start, rest, fill_off} the kernels consume.  base: (ncells+1) list offsets of the cells."""
     orders, fills, desc = [], [], []
     order_off = fill_off = 0
-    for cell in range(len(base) - 1):
-        Lc = int(base[cell + 1] - base[cell])
-        if Lc == 0:
-            continue                                                             # :39-40
-        order = np.arange(Lc)
-        np.random.shuffle(order)                                                 # :17-18 (same stream as on a list)
-        rest = Lc % npoints                                                      # :81
-        if rest == 0:
-            # the reference concatenates an empty list with a 2-D array here (:89-90): numpy's error, verbatim
-            raise ValueError("all the input arrays must have same number of dimensions, but the array at index 0 "
-                             "has 1 dimension(s) and the array at index 1 has 2 dimension(s)")
-        nfull = int(Lc / npoints)
-        fill = np.random.choice(Lc, npoints - rest, replace=True)                # :87
-        for k in range(nfull):                                                   # :56-79
-            desc.append((base[cell], order_off, k * npoints, npoints, 0))
-        desc.append((base[cell], order_off, nfull * npoints, rest, fill_off))    # :81-109
-        orders.append(order.astype(np.int32))
-        fills.append(fill.astype(np.int32))
-        order_off += Lc
-        fill_off += npoints - rest
+    with _LegacyStream() as rng:
+        for cell in range(len(base) - 1):
+            Lc = int(base[cell + 1] - base[cell])
+            if Lc == 0:
+                continue                                                         # :39-40
+            order = rng.shuffled_arange(Lc)                                      # :17-18 (same stream as on a list)
+            rest = Lc % npoints                                                  # :81
+            if rest == 0:
+                # the reference concatenates an empty list with a 2-D array here (:89-90): numpy's error, verbatim
+                raise ValueError("all the input arrays must have same number of dimensions, but the array at index 0 "
+                                 "has 1 dimension(s) and the array at index 1 has 2 dimension(s)")
+            nfull = int(Lc / npoints)
+            fill = rng.choice(Lc, npoints - rest)                                # :87
+            for k in range(nfull):                                               # :56-79
+                desc.append((base[cell], order_off, k * npoints, npoints, 0))
+            desc.append((base[cell], order_off, nfull * npoints, rest, fill_off))    # :81-109
+            orders.append(order)
+            fills.append(fill)
+            order_off += Lc
+            fill_off += npoints - rest
     if not desc:
         raise ValueError("need at least one array to concatenate")               # :111 on an empty scan
     return np.asarray(desc, dtype=np.int32), np.concatenate(orders), np.concatenate(fills)

@@ -174,3 +174,47 @@ def test_pipelined_chunker_equals_scan_after_scan():
     gen = csl.chunk_scenes(iter(d_scans), lookahead=1, background=True)   # closing early stops the worker
     next(gen)
     gen.close()
+
+
+def test_native_rng_stream_equals_numpy_legacy():
+    """pc_host_legacy_shuffle / pc_host_legacy_randint continue numpy's global legacy MT19937 stream bit for bit: the
+    planner's orders and fill indices equal np.random.shuffle / np.random.choice under the same seed, and numpy
+    continues from the same state afterwards (also across the 624-word regeneration and for one-point cells, where
+    numpy's randint draws nothing)."""
+    def numpy_plan(base, npoints=8192):
+        orders, fills = [], []
+        for cell in range(len(base) - 1):
+            Lc = int(base[cell + 1] - base[cell])
+            if Lc == 0:
+                continue
+            o = np.arange(Lc)
+            np.random.shuffle(o)                                   # complete_scene_loader.py:17-18
+            fills.append(np.random.choice(Lc, npoints - Lc % npoints, replace=True))   # :87
+            orders.append(o)
+        return np.concatenate(orders), np.concatenate(fills)
+    rs = np.random.RandomState(7)
+    for trial in range(12):
+        counts = rs.randint(0, 30000, size=rs.randint(1, 20))
+        counts[counts % 8192 == 0] += 1
+        if trial % 4 == 0:
+            counts[0] = 1
+        base = np.concatenate([[0], np.cumsum(counts)])
+        np.random.seed(trial)
+        np.random.random(trial * 53)                               # any position inside the 624-word block
+        want_o, want_f = numpy_plan(base)
+        want_tail = np.random.random(4)
+        np.random.seed(trial)
+        np.random.random(trial * 53)
+        _desc, got_o, got_f = csl._plan_chunks(base)
+        assert got_o.dtype == np.int32 and got_f.dtype == np.int32
+        assert np.array_equal(got_o, want_o) and np.array_equal(got_f, want_f)
+        assert np.array_equal(np.random.random(4), want_tail)      # numpy continues from the same state
+    # the state is written back when planning raises (a cell holding a multiple of npoints, as in the reference)
+    np.random.seed(3)
+    o = np.arange(8192)
+    np.random.shuffle(o)
+    want_tail = np.random.random(2)
+    np.random.seed(3)
+    with pytest.raises(ValueError):
+        csl._plan_chunks(np.array([0, 8192]))
+    assert np.array_equal(np.random.random(2), want_tail)
