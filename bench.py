@@ -1047,8 +1047,6 @@ def main():
     hint(1)
     config5 = None
     if args.config5:
-        for pl in pipes[1:]:
-            pass
         try:
             entries, times, Bt = run_config5(torch, args, rank, world, dev, sharding, fp32_peak_tops)
         except Exception as exc:
