@@ -1,5 +1,5 @@
-import os, sys, cProfile, pstats, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+import sys, cProfile, pstats, numpy as np, torch
+sys.path.insert(0, ".")   # run from the repository root
 from pcops_b200 import synth
 from pcops_b200 import complete_scene_loader as csl
 dev = torch.device("cuda:0")
