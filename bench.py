@@ -815,10 +815,9 @@ def main():
         t0 = time.time()
         e0.record(cur)
         fork(ps)
-        for _ in range(reps):
-            for i in range(K):
-                step(i)
-        join(ps)
+        for i in range(reps * K):          # ONE running index: the round robin over the batches in flight must not
+            step(i)                        # restart every K steps (K = 20, 8 batches: 4 of 20 steps would queue behind
+        join(ps)                           # the replay just issued on the same instance -- 10 % of the N > 1 figures)
         e1.record(cur)
         t_enq = time.time() - t0
         torch.cuda.synchronize(dev)
